@@ -1,0 +1,695 @@
+// C ABI (include/egohmr_b200.h): context, weight ingestion/repacking, step orchestration.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cudaTypedefs.h>
+
+#include "../../include/egohmr_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+int fail_cuda(const char* what, cudaError_t e) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return 1;
+}
+#define EHB_CUDA(expr)                                   \
+  do {                                                   \
+    cudaError_t _e = (expr);                             \
+    if (_e != cudaSuccess) return fail_cuda(#expr, _e);  \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t n, bool zero = false) {
+    if (n <= bytes && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n ? n : 1);
+    if (e != cudaSuccess) return e;
+    bytes = n;
+    if (zero) e = cudaMemset(p, 0, n ? n : 1);
+    return e;
+  }
+  template <typename T>
+  cudaError_t upload(const std::vector<T>& h) {
+    cudaError_t e = ensure(h.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  template <typename T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+};
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  return fn;
+}
+
+// 2-D fp16 row-major [rows][cols] tensor, box = [box_rows][32 halfs] with the 64-byte swizzle the UMMA descriptors use
+int make_tmap_f16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(__half)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+  return 0;
+}
+
+ehb::AdjMix make_adjmix(const float* adj, const float* adj2) {
+  // modulated_gcn_conv.py:42-43: adj = self.adj + self.adj2; adj = (adj.T + adj) / 2   (fp32)
+  float a[ehb::NJ][ehb::NJ];
+  for (int i = 0; i < ehb::NJ; ++i)
+    for (int j = 0; j < ehb::NJ; ++j) a[i][j] = adj[i * ehb::NJ + j] + adj2[i * ehb::NJ + j];
+  ehb::AdjMix m;
+  for (int j = 0; j < ehb::NJ; ++j)
+    for (int i = 0; i < ehb::NJ; ++i) {
+      const float s = (a[i][j] + a[j][i]) / 2.f;
+      if (i == j) {
+        m.diag[j] = s;
+        m.off[j][i] = 0.f;
+      } else {
+        m.off[j][i] = s;
+      }
+    }
+  return m;
+}
+
+void fold_bn(const ehb_gconv& g, std::vector<float>& scale, std::vector<float>& shift) {
+  const int C = g.out_dim;
+  scale.resize(C);
+  shift.resize(C);
+  for (int c = 0; c < C; ++c) {
+    const double sc = double(g.bn_weight[c]) / std::sqrt(double(g.bn_var[c]) + double(g.bn_eps));
+    scale[c] = float(sc);
+    shift[c] = float(double(g.bn_bias[c]) + (double(g.bias[c]) - double(g.bn_mean[c])) * sc);
+  }
+}
+
+__global__ void fill_rows_kernel(float* dst, const float* row, int n_rows, int width) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < static_cast<size_t>(n_rows) * width) dst[i] = row[i % width];
+}
+
+__global__ void denorm_kernel(const float* x, const float* mean, const float* std_, float* out, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __fadd_rn(__fmul_rn(x[i], std_[i % ehb::XDIM]), mean[i % ehb::XDIM]);
+}
+
+}  // namespace
+
+struct ehb_ctx {
+  int device = 0;
+  int num_sms = 0;
+  int64_t launches = 0;
+  int gemm_mode = 0;
+  float act_scale = 8.f;
+
+  // ---- denoiser
+  bool gcn_loaded = false;
+  int hid = 0, n_blocks = 0, img_dim = 0, cond_dim = 0, xfeat_dim = 0, temb_dim = 0, diffuse_fuse = 0;
+  struct Hidden {
+    ehb::AdjMix adj;
+    DevBuf mod_scaled, mod, bn_scale, bn_shift, w_hl, wcat;
+    float w_scale = 1.f;
+    CUtensorMap tmB;
+  };
+  std::vector<Hidden*> hidden;
+  ehb::AdjMix adj_in, adj_out;
+  DevBuf w_img, w_rest, w_temb, wx01, cx01, mod_in, bn_scale_in, bn_shift_in;
+  DevBuf wout, mod_out, bias_out;
+
+  // ---- conditioning
+  int n_img = 0, n_steps_cond = 0;
+  DevBuf a01, be01, ct01, vis;
+
+  // ---- chains
+  int n_bodies = 0, n_slots = 0, n_mtiles = 0;
+  DevBuf img_of_body, slot_body, slot_cond, body_slot;
+  DevBuf act_hl[2], res, mid, h_tmp;
+  CUtensorMap tmA[2];
+
+  // ---- sampler
+  int kind = 0;
+  std::vector<ehb::StepCoef> coef;
+  DevBuf mean, std_;
+  bool norm_set = false;
+
+  // ---- SMPL
+  bool smpl_loaded = false;
+  ehb::SmplDevice smpl{};
+  DevBuf s_vt, s_sd, s_pd, s_w, s_jt, s_jsd, s_ex;
+  DevBuf sc_R, sc_A, sc_j24, sc_pf, sc_p6;
+
+  DevBuf overflow;
+
+  ~ehb_ctx() {
+    for (auto* h : hidden) delete h;
+  }
+};
+
+extern "C" {
+
+const char* ehb_last_error(void) { return g_last_error.c_str(); }
+
+int64_t ehb_launch_count(const ehb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int ehb_ctx_create(int device, ehb_ctx** out) {
+  if (!out) return fail("ehb_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(std::string("ehb_ctx_create: no CUDA device (") + cudaGetErrorString(e) +
+                "); this library has no CPU fallback");
+  if (device < 0 || device >= n) return fail("ehb_ctx_create: bad device index");
+  EHB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  EHB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail("ehb_ctx_create: device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                ", this library is built for sm_100a only");
+  ehb_ctx* c = new ehb_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if (c->overflow.ensure(sizeof(int), true) != cudaSuccess) {
+    delete c;
+    return fail("ehb_ctx_create: cudaMalloc failed");
+  }
+  *out = c;
+  return 0;
+}
+
+void ehb_ctx_destroy(ehb_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  delete ctx;
+}
+
+int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode) {
+  if (!ctx) return fail("null ctx");
+  if (gemm_mode != 0 && gemm_mode != 1) return fail("gemm_mode must be 0 (tcgen05) or 1 (fp32 check)");
+  ctx->gemm_mode = gemm_mode;
+  return 0;
+}
+
+int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w) {
+  if (!ctx || !w) return fail("ehb_gcn_load: null argument");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  const int C = w->hid;
+  if (C <= 0 || C % 128 != 0) return fail("ehb_gcn_load: hid must be a positive multiple of 128");
+  if (w->n_layers != 2 * w->n_blocks + 2) return fail("ehb_gcn_load: n_layers must be 2*n_blocks + 2");
+  const int in_dim = w->cond_dim + w->xfeat_dim + w->temb_dim;
+  const ehb_gconv& gi = w->layers[0];
+  const ehb_gconv& go = w->layers[w->n_layers - 1];
+  if (gi.in_dim != in_dim || gi.out_dim != C) return fail("ehb_gcn_load: gconv_input shape mismatch");
+  if (go.in_dim != C || go.out_dim != 6) return fail("ehb_gcn_load: gconv_output shape mismatch");
+  if (!gi.bn_weight) return fail("ehb_gcn_load: gconv_input needs BatchNorm parameters");
+  ctx->hid = C;
+  ctx->n_blocks = w->n_blocks;
+  ctx->img_dim = w->img_dim;
+  ctx->cond_dim = w->cond_dim;
+  ctx->xfeat_dim = w->xfeat_dim;
+  ctx->temb_dim = w->temb_dim;
+  ctx->diffuse_fuse = w->diffuse_fuse;
+  const size_t C2 = 2 * static_cast<size_t>(C);
+
+  // ---- input layer: split W[2][in_dim][C] by feature block, columns concatenated as k*C + c
+  {
+    auto Wat = [&](int k, int r, int c) { return gi.W[(static_cast<size_t>(k) * in_dim + r) * C + c]; };
+    const int rest = w->cond_dim - w->img_dim;
+    std::vector<float> wi(static_cast<size_t>(w->img_dim) * C2), wr(static_cast<size_t>(rest) * C2),
+        wt(static_cast<size_t>(w->temb_dim) * C2);
+    for (int k = 0; k < 2; ++k)
+      for (int c = 0; c < C; ++c) {
+        for (int r = 0; r < w->img_dim; ++r) wi[r * C2 + k * C + c] = Wat(k, r, c);
+        for (int r = 0; r < rest; ++r) wr[r * C2 + k * C + c] = Wat(k, w->img_dim + r, c);
+        for (int r = 0; r < w->temb_dim; ++r) wt[r * C2 + k * C + c] = Wat(k, w->cond_dim + w->xfeat_dim + r, c);
+      }
+    // InputProcess folded through the x_feat rows: wx[k][d][c] = sum_f inproc_w[f][d] W_k[x0+f][c]; cx = inproc_b . W_k
+    std::vector<float> wx(2 * 6 * static_cast<size_t>(C)), cx(C2);
+    for (int k = 0; k < 2; ++k)
+      for (int c = 0; c < C; ++c) {
+        double acc[6] = {0, 0, 0, 0, 0, 0}, accb = 0;
+        for (int f = 0; f < w->xfeat_dim; ++f) {
+          const double wv = Wat(k, w->cond_dim + f, c);
+          for (int d = 0; d < 6; ++d) acc[d] += double(w->inproc_w[f * 6 + d]) * wv;
+          accb += double(w->inproc_b[f]) * wv;
+        }
+        for (int d = 0; d < 6; ++d) wx[(static_cast<size_t>(k) * 6 + d) * C + c] = float(acc[d]);
+        cx[k * C + c] = float(accb);
+      }
+    std::vector<float> mod(gi.M, gi.M + static_cast<size_t>(ehb::NJ) * C), sc, sh;
+    fold_bn(gi, sc, sh);
+    EHB_CUDA(ctx->w_img.upload(wi));
+    EHB_CUDA(ctx->w_rest.upload(wr));
+    EHB_CUDA(ctx->w_temb.upload(wt));
+    EHB_CUDA(ctx->wx01.upload(wx));
+    EHB_CUDA(ctx->cx01.upload(cx));
+    EHB_CUDA(ctx->mod_in.upload(mod));
+    EHB_CUDA(ctx->bn_scale_in.upload(sc));
+    EHB_CUDA(ctx->bn_shift_in.upload(sh));
+    ctx->adj_in = make_adjmix(w->adj, gi.adj2);
+  }
+
+  // ---- hidden layers
+  for (auto* h : ctx->hidden) delete h;
+  ctx->hidden.clear();
+  for (int l = 1; l <= 2 * w->n_blocks; ++l) {
+    const ehb_gconv& g = w->layers[l];
+    if (g.in_dim != C || g.out_dim != C || !g.bn_weight) return fail("ehb_gcn_load: hidden layer shape mismatch");
+    auto* h = new ehb_ctx::Hidden();
+    ctx->hidden.push_back(h);
+    h->adj = make_adjmix(w->adj, g.adj2);
+    float maxabs = 0.f;
+    const size_t nW = 2 * static_cast<size_t>(C) * C;
+    for (size_t i = 0; i < nW; ++i) maxabs = std::max(maxabs, std::fabs(g.W[i]));
+    if (!std::isfinite(maxabs)) return fail("ehb_gcn_load: non-finite weight");
+    // power-of-two scale putting max|W| in [8192, 16384): fp16 lo parts stay normal, no overflow
+    h->w_scale = maxabs > 0.f ? std::exp2(std::floor(std::log2(16384.f / maxabs)) ) : 1.f;
+    if (maxabs * h->w_scale >= 16384.f) h->w_scale *= 0.5f;
+    // B operand: row n' = nt*256 + k*128 + cl  (channel nt*128+cl of W[k]), columns [hi(K) | lo(K)]
+    std::vector<__half> whl(C2 * C2);
+    std::vector<float> wcat(static_cast<size_t>(C) * C2);
+    for (int k = 0; k < 2; ++k)
+      for (int kk = 0; kk < C; ++kk)
+        for (int c = 0; c < C; ++c) {
+          const float v = g.W[(static_cast<size_t>(k) * C + kk) * C + c];
+          wcat[kk * C2 + k * C + c] = v;
+          const float sv = v * h->w_scale;
+          const __half hi = __float2half_rn(sv);
+          const __half lo = __float2half_rn(sv - __half2float(hi));
+          const size_t np = static_cast<size_t>(c / 128) * 256 + k * 128 + (c % 128);
+          whl[np * C2 + kk] = hi;
+          whl[np * C2 + C + kk] = lo;
+        }
+    const float inv = 1.f / (ctx->act_scale * h->w_scale);
+    std::vector<float> mod(g.M, g.M + static_cast<size_t>(ehb::NJ) * C), mods(mod.size()), sc, sh;
+    for (size_t i = 0; i < mod.size(); ++i) mods[i] = mod[i] * inv;
+    fold_bn(g, sc, sh);
+    EHB_CUDA(h->w_hl.upload(whl));
+    EHB_CUDA(h->wcat.upload(wcat));
+    EHB_CUDA(h->mod.upload(mod));
+    EHB_CUDA(h->mod_scaled.upload(mods));
+    EHB_CUDA(h->bn_scale.upload(sc));
+    EHB_CUDA(h->bn_shift.upload(sh));
+    if (make_tmap_f16(&h->tmB, h->w_hl.p, C2, C2, 256)) return 1;
+  }
+
+  // ---- output layer
+  {
+    std::vector<float> wo(static_cast<size_t>(C) * 12);
+    for (int k = 0; k < 2; ++k)
+      for (int kk = 0; kk < C; ++kk)
+        for (int d = 0; d < 6; ++d) wo[static_cast<size_t>(kk) * 12 + k * 6 + d] = go.W[(static_cast<size_t>(k) * C + kk) * 6 + d];
+    std::vector<float> mo(go.M, go.M + ehb::NJ * 6), bo(go.bias, go.bias + 6);
+    EHB_CUDA(ctx->wout.upload(wo));
+    EHB_CUDA(ctx->mod_out.upload(mo));
+    EHB_CUDA(ctx->bias_out.upload(bo));
+    ctx->adj_out = make_adjmix(w->adj, go.adj2);
+  }
+  ctx->gcn_loaded = true;
+  ctx->n_bodies = 0;
+  return 0;
+}
+
+int ehb_set_norm(ehb_ctx* ctx, const float* mean, const float* std) {
+  if (!ctx || !mean || !std) return fail("ehb_set_norm: null argument");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  std::vector<float> m(mean, mean + ehb::XDIM), s(std, std + ehb::XDIM);
+  EHB_CUDA(ctx->mean.upload(m));
+  EHB_CUDA(ctx->std_.upload(s));
+  ctx->norm_set = true;
+  return 0;
+}
+
+int ehb_set_schedule(ehb_ctx* ctx, int kind, int n_steps, const float* coef) {
+  if (!ctx || !coef) return fail("ehb_set_schedule: null argument");
+  if (kind != ehb::SAMPLER_DDIM && kind != ehb::SAMPLER_DDPM) return fail("ehb_set_schedule: kind must be 0 or 1");
+  if (n_steps <= 0) return fail("ehb_set_schedule: n_steps must be positive");
+  ctx->kind = kind;
+  ctx->coef.resize(n_steps);
+  std::memcpy(ctx->coef.data(), coef, sizeof(ehb::StepCoef) * n_steps);
+  return 0;
+}
+
+int ehb_set_cond(ehb_ctx* ctx, int n_img, const float* img_feat, const float* rest_feat, const uint8_t* vis,
+                 int n_steps, const float* temb, void* stream_) {
+  if (!ctx || !img_feat || !rest_feat || !vis || !temb) return fail("ehb_set_cond: null argument");
+  if (!ctx->gcn_loaded) return fail("ehb_set_cond: call ehb_gcn_load first");
+  if (n_img <= 0 || n_steps <= 0) return fail("ehb_set_cond: n_img and n_steps must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int C = ctx->hid, C2 = 2 * C, rest = ctx->cond_dim - ctx->img_dim;
+  EHB_CUDA(ctx->a01.ensure(sizeof(float) * n_img * C2));
+  EHB_CUDA(ctx->be01.ensure(sizeof(float) * n_img * C2));
+  EHB_CUDA(ctx->ct01.ensure(sizeof(float) * n_steps * C2));
+  EHB_CUDA(ctx->vis.ensure(static_cast<size_t>(n_img) * ehb::NJ));
+  EHB_CUDA(cudaMemcpyAsync(ctx->vis.p, vis, static_cast<size_t>(n_img) * ehb::NJ, cudaMemcpyDeviceToDevice, stream));
+  EHB_CUDA(ehb::launch_sgemm_nn(img_feat, ctx->w_img.as<float>(), ctx->a01.as<float>(), n_img, C2, ctx->img_dim,
+                                ctx->img_dim, C2, C2, 0, stream));
+  {
+    const size_t n = static_cast<size_t>(n_img) * C2;
+    fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(ctx->be01.as<float>(),
+                                                                                 ctx->cx01.as<float>(), n_img, C2);
+    EHB_CUDA(cudaGetLastError());
+  }
+  EHB_CUDA(ehb::launch_sgemm_nn(rest_feat, ctx->w_rest.as<float>(), ctx->be01.as<float>(), n_img, C2, rest, rest, C2,
+                                C2, 1, stream));
+  EHB_CUDA(ehb::launch_sgemm_nn(temb, ctx->w_temb.as<float>(), ctx->ct01.as<float>(), n_steps, C2, ctx->temb_dim,
+                                ctx->temb_dim, C2, C2, 0, stream));
+  ctx->launches += 4;
+  ctx->n_img = n_img;
+  ctx->n_steps_cond = n_steps;
+  return 0;
+}
+
+int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body) {
+  if (!ctx || !img_of_body) return fail("ehb_set_bodies: null argument");
+  if (!ctx->gcn_loaded) return fail("ehb_set_bodies: call ehb_gcn_load first");
+  if (n_bodies <= 0) return fail("ehb_set_bodies: n_bodies must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  const int passes = ctx->diffuse_fuse ? 2 : 1;
+  const int n_slots = n_bodies * passes;
+  std::vector<int32_t> iob(img_of_body, img_of_body + n_bodies), sb(n_slots), bs(static_cast<size_t>(n_bodies) * 2, -1);
+  std::vector<uint8_t> scnd(n_slots);
+  for (int p = 0; p < passes; ++p)
+    for (int b = 0; b < n_bodies; ++b) {
+      const int s = p * n_bodies + b;
+      sb[s] = b;
+      scnd[s] = p == 0 ? 1 : 0;  // pass 0 = image-conditioned, pass 1 = image-masked
+      bs[b * 2 + p] = s;
+    }
+  for (int b = 0; b < n_bodies; ++b)
+    if (iob[b] < 0) return fail("ehb_set_bodies: negative image index");
+  EHB_CUDA(ctx->img_of_body.upload(iob));
+  EHB_CUDA(ctx->slot_body.upload(sb));
+  EHB_CUDA(ctx->slot_cond.upload(scnd));
+  EHB_CUDA(ctx->body_slot.upload(bs));
+  const int n_mtiles = (n_slots + ehb::SLOTS_PER_TILE - 1) / ehb::SLOTS_PER_TILE;
+  const size_t rows = static_cast<size_t>(n_mtiles) * ehb::TILE_ROWS;
+  const size_t C = ctx->hid;
+  if (n_mtiles != ctx->n_mtiles || !ctx->res.p) {
+    for (int i = 0; i < 2; ++i) {
+      EHB_CUDA(ctx->act_hl[i].ensure(rows * 2 * C * sizeof(__half), true));
+      EHB_CUDA(cudaMemset(ctx->act_hl[i].p, 0, rows * 2 * C * sizeof(__half)));
+      if (make_tmap_f16(&ctx->tmA[i], ctx->act_hl[i].p, rows, 2 * C, 128)) return 1;
+    }
+    EHB_CUDA(ctx->res.ensure(rows * C * sizeof(float), true));
+    EHB_CUDA(cudaMemset(ctx->res.p, 0, rows * C * sizeof(float)));
+  }
+  ctx->n_bodies = n_bodies;
+  ctx->n_slots = n_slots;
+  ctx->n_mtiles = n_mtiles;
+  EHB_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
+  const int L = static_cast<int>(ctx->hidden.size());
+  ehb_ctx::Hidden& h = *ctx->hidden[l];
+  ehb::HiddenLayerParams p;
+  p.adj = h.adj;
+  p.mod = h.mod_scaled.as<float>();
+  p.bn_scale = h.bn_scale.as<float>();
+  p.bn_shift = h.bn_shift.as<float>();
+  p.res = ctx->res.as<float>();
+  p.out_hl = ctx->act_hl[(l + 1) & 1].as<__half>();
+  p.overflow_flag = ctx->overflow.as<int>();
+  p.act_scale = ctx->act_scale;
+  p.C = ctx->hid;
+  p.n_mtiles = ctx->n_mtiles;
+  p.n_ntiles = ctx->hid / 128;
+  p.n_slots = ctx->n_slots;
+  const bool second = (l & 1) == 1;  // gconv2 of a _ResGraphConv: residual add, block-boundary output
+  p.add_res = second ? 1 : 0;
+  p.write_f32 = second ? 1 : 0;
+  p.write_hl = (l != L - 1) ? 1 : 0;
+  if (ctx->gemm_mode == 0) {
+    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB, p, ctx->num_sms, stream));
+    ctx->launches += 1;
+  } else {
+    const size_t rows = static_cast<size_t>(ctx->n_mtiles) * ehb::TILE_ROWS;
+    EHB_CUDA(ctx->mid.ensure(rows * ctx->hid * sizeof(float), true));
+    EHB_CUDA(ctx->h_tmp.ensure(rows * 2 * ctx->hid * sizeof(float)));
+    const float* xin = second ? ctx->mid.as<float>() : ctx->res.as<float>();
+    float* xout = second ? ctx->res.as<float>() : ctx->mid.as<float>();
+    EHB_CUDA(ehb::launch_gcn_hidden_simt(xin, h.wcat.as<float>(), ctx->h_tmp.as<float>(), p, h.mod.as<float>(), xout,
+                                         stream));
+    ctx->launches += 2;
+  }
+  return 0;
+}
+
+int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
+                           float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream_) {
+  if (!ctx || !x_t || !x_prev || !x0) return fail("ehb_denoise_step: null argument");
+  if (!ctx->gcn_loaded || ctx->n_bodies <= 0 || ctx->n_img <= 0) return fail("ehb_denoise_step: context not set up");
+  if (step < 0 || step >= static_cast<int>(ctx->coef.size()) || step >= ctx->n_steps_cond)
+    return fail("ehb_denoise_step: step out of range of the schedule / conditioning tables");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  {
+    ehb::InputLayerParams p;
+    p.adj = ctx->adj_in;
+    p.a01 = ctx->a01.as<float>();
+    p.be01 = ctx->be01.as<float>();
+    p.ct01 = ctx->ct01.as<float>();
+    p.wx01 = ctx->wx01.as<float>();
+    p.mod = ctx->mod_in.as<float>();
+    p.bn_scale = ctx->bn_scale_in.as<float>();
+    p.bn_shift = ctx->bn_shift_in.as<float>();
+    p.vis = ctx->vis.as<uint8_t>();
+    p.slot_body = ctx->slot_body.as<int32_t>();
+    p.slot_cond = ctx->slot_cond.as<uint8_t>();
+    p.img_of_body = ctx->img_of_body.as<int32_t>();
+    p.x_t = x_t;
+    p.res = ctx->res.as<float>();
+    p.out_hl = ctx->act_hl[0].as<__half>();
+    p.overflow_flag = ctx->overflow.as<int>();
+    p.act_scale = ctx->act_scale;
+    p.C = ctx->hid;
+    p.n_slots = ctx->n_slots;
+    p.step = step;
+    EHB_CUDA(ehb::launch_gcn_input(p, stream));
+    ctx->launches += 1;
+  }
+  for (int l = 0; l < static_cast<int>(ctx->hidden.size()); ++l)
+    if (run_hidden(ctx, l, stream)) return 1;
+  {
+    ehb::OutputLayerParams p;
+    p.adj = ctx->adj_out;
+    p.act = ctx->res.as<float>();
+    p.wout = ctx->wout.as<float>();
+    p.mod = ctx->mod_out.as<float>();
+    p.bias = ctx->bias_out.as<float>();
+    p.vis = ctx->vis.as<uint8_t>();
+    p.img_of_body = ctx->img_of_body.as<int32_t>();
+    p.body_slot = ctx->body_slot.as<int32_t>();
+    p.x_t = x_t;
+    p.noise = noise;
+    p.grad = grad;
+    p.x_prev = x_prev;
+    p.x0 = x0;
+    p.out_cond = out_cond;
+    p.out_uncond = out_uncond;
+    p.coef = ctx->coef[step];
+    p.kind = ctx->kind;
+    p.C = ctx->hid;
+    p.n_bodies = ctx->n_bodies;
+    p.diffuse_fuse = ctx->diffuse_fuse;
+    EHB_CUDA(ehb::launch_gcn_output(p, stream));
+    ctx->launches += 1;
+  }
+  return 0;
+}
+
+int ehb_denoise_step(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad, float* x_prev,
+                     float* x0, void* stream) {
+  return ehb_denoise_step_debug(ctx, step, x_t, noise, grad, x_prev, x0, nullptr, nullptr, stream);
+}
+
+int ehb_check_overflow(ehb_ctx* ctx, void* stream_) {
+  if (!ctx) return 0;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int flag = 0;
+  cudaMemcpyAsync(&flag, ctx->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, stream);
+  cudaStreamSynchronize(stream);
+  if (flag) cudaMemsetAsync(ctx->overflow.p, 0, sizeof(int), stream);
+  return flag;
+}
+
+int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* stream_) {
+  if (!ctx || !ms) return fail("ehb_time_hidden_layer: null argument");
+  if (!ctx->gcn_loaded || ctx->n_bodies <= 0) return fail("ehb_time_hidden_layer: context not set up");
+  if (layer < 1 || layer > static_cast<int>(ctx->hidden.size())) return fail("ehb_time_hidden_layer: bad layer");
+  if (iters <= 0) return fail("ehb_time_hidden_layer: iters must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaEvent_t e0, e1;
+  EHB_CUDA(cudaEventCreate(&e0));
+  EHB_CUDA(cudaEventCreate(&e1));
+  EHB_CUDA(cudaEventRecord(e0, stream));
+  for (int i = 0; i < iters; ++i)
+    if (run_hidden(ctx, layer - 1, stream)) return 1;
+  EHB_CUDA(cudaEventRecord(e1, stream));
+  EHB_CUDA(cudaEventSynchronize(e1));
+  float t = 0.f;
+  EHB_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms = t / iters;
+  return 0;
+}
+
+int ehb_rot6d_to_rotmat(ehb_ctx* ctx, const float* x6, int n, float* R, void* stream_) {
+  if (!ctx || !x6 || !R) return fail("ehb_rot6d_to_rotmat: null argument");
+  if (n < 0) return fail("ehb_rot6d_to_rotmat: negative n");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_rot6d_flat(x6, R, n, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += n > 0;
+  return 0;
+}
+
+int ehb_smpl_load(ehb_ctx* ctx, const ehb_smpl_model* m) {
+  if (!ctx || !m) return fail("ehb_smpl_load: null argument");
+  if (m->n_verts <= 0 || m->n_betas <= 0 || m->n_betas > 16 || m->n_extra < 0)
+    return fail("ehb_smpl_load: need n_verts > 0, 0 < n_betas <= 16, n_extra >= 0");
+  if (m->parents[0] >= 0) return fail("ehb_smpl_load: parents[0] must be -1");
+  for (int j = 1; j < ehb::NJ; ++j)
+    if (m->parents[j] < 0 || m->parents[j] >= j) return fail("ehb_smpl_load: parents must be topologically ordered");
+  for (int i = 0; i < m->n_extra; ++i)
+    if (m->extra_vertex_ids[i] < 0 || m->extra_vertex_ids[i] >= m->n_verts)
+      return fail("ehb_smpl_load: extra vertex id out of range");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  const int V = m->n_verts, NB = m->n_betas;
+  // J = J_regressor . v_shaped is linear in beta: J_template + J_shapedirs . beta  (smplx lbs.py vertices2joints)
+  std::vector<float> jt(ehb::NJ * 3), jsd(static_cast<size_t>(ehb::NJ) * 3 * NB);
+  for (int j = 0; j < ehb::NJ; ++j)
+    for (int k = 0; k < 3; ++k) {
+      double acc = 0;
+      for (int v = 0; v < V; ++v) acc += double(m->J_regressor[static_cast<size_t>(j) * V + v]) * m->v_template[v * 3 + k];
+      jt[j * 3 + k] = float(acc);
+      for (int l = 0; l < NB; ++l) {
+        double a2 = 0;
+        for (int v = 0; v < V; ++v)
+          a2 += double(m->J_regressor[static_cast<size_t>(j) * V + v]) * m->shapedirs[(static_cast<size_t>(v) * 3 + k) * NB + l];
+        jsd[(static_cast<size_t>(j) * 3 + k) * NB + l] = float(a2);
+      }
+    }
+  auto up = [&](DevBuf& b, const float* src, size_t n) {
+    std::vector<float> h(src, src + n);
+    return b.upload(h);
+  };
+  EHB_CUDA(up(ctx->s_vt, m->v_template, static_cast<size_t>(V) * 3));
+  EHB_CUDA(up(ctx->s_sd, m->shapedirs, static_cast<size_t>(V) * 3 * NB));
+  EHB_CUDA(up(ctx->s_pd, m->posedirs, static_cast<size_t>(207) * V * 3));
+  EHB_CUDA(up(ctx->s_w, m->lbs_weights, static_cast<size_t>(V) * ehb::NJ));
+  EHB_CUDA(ctx->s_jt.upload(jt));
+  EHB_CUDA(ctx->s_jsd.upload(jsd));
+  std::vector<int32_t> ex(m->extra_vertex_ids, m->extra_vertex_ids + m->n_extra);
+  if (ex.empty()) ex.push_back(0);
+  EHB_CUDA(ctx->s_ex.upload(ex));
+  ehb::SmplDevice& d = ctx->smpl;
+  d.v_template = ctx->s_vt.as<float>();
+  d.shapedirs = ctx->s_sd.as<float>();
+  d.posedirs = ctx->s_pd.as<float>();
+  d.lbs_weights = ctx->s_w.as<float>();
+  d.j_template = ctx->s_jt.as<float>();
+  d.j_shapedirs = ctx->s_jsd.as<float>();
+  d.extra_vids = ctx->s_ex.as<int32_t>();
+  for (int j = 0; j < ehb::NJ; ++j) d.parents[j] = m->parents[j];
+  d.V = V;
+  d.NB = NB;
+  d.n_extra = m->n_extra;
+  ctx->smpl_loaded = true;
+  return 0;
+}
+
+static int smpl_run(ehb_ctx* ctx, int n, const float* R, const float* betas, const int32_t* beta_index,
+                    const float* transl, float* verts, float* joints, cudaStream_t stream) {
+  EHB_CUDA(ctx->sc_A.ensure(static_cast<size_t>(n) * ehb::NJ * 12 * sizeof(float)));
+  EHB_CUDA(ctx->sc_j24.ensure(static_cast<size_t>(n) * ehb::NJ * 3 * sizeof(float)));
+  EHB_CUDA(ctx->sc_pf.ensure(static_cast<size_t>(n) * 207 * sizeof(float)));
+  EHB_CUDA(ehb::launch_smpl_pose(ctx->smpl, R, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_j24.as<float>(),
+                                 ctx->sc_pf.as<float>(), n, stream));
+  ctx->launches += 1;
+  if (verts) {
+    EHB_CUDA(ehb::launch_smpl_skin(ctx->smpl, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_pf.as<float>(), transl,
+                                   verts, n, stream));
+    ctx->launches += 1;
+  }
+  if (joints) {
+    if (!verts && ctx->smpl.n_extra > 0) return fail("joints need verts (vertex-picked extra joints)");
+    EHB_CUDA(ehb::launch_smpl_joints(ctx->smpl, ctx->sc_j24.as<float>(), verts, transl, joints, n, stream));
+    ctx->launches += 1;
+  }
+  return 0;
+}
+
+int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, const float* transl, float* verts,
+                     float* joints, void* stream_) {
+  if (!ctx || !R || !betas) return fail("ehb_smpl_forward: null argument");
+  if (!ctx->smpl_loaded) return fail("ehb_smpl_forward: call ehb_smpl_load first");
+  if (n <= 0) return fail("ehb_smpl_forward: n must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  return smpl_run(ctx, n, R, betas, nullptr, transl, verts, joints, static_cast<cudaStream_t>(stream_));
+}
+
+int ehb_decode(ehb_ctx* ctx, const float* x0, const float* betas, float* pose6d, float* R, float* verts, float* joints,
+               void* stream_) {
+  if (!ctx || !x0 || !R) return fail("ehb_decode: null argument");
+  if (ctx->n_bodies <= 0) return fail("ehb_decode: call ehb_set_bodies first");
+  if (!ctx->norm_set) return fail("ehb_decode: call ehb_set_norm first");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int n = ctx->n_bodies;
+  if (pose6d) {
+    const size_t tot = static_cast<size_t>(n) * ehb::XDIM;
+    denorm_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, stream>>>(x0, ctx->mean.as<float>(),
+                                                                                ctx->std_.as<float>(), pose6d, tot);
+    EHB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  EHB_CUDA(ehb::launch_rot6d(x0, ctx->mean.as<float>(), ctx->std_.as<float>(), R, n, stream));
+  ctx->launches += 1;
+  if (!verts && !joints) return 0;
+  if (!ctx->smpl_loaded) return fail("ehb_decode: call ehb_smpl_load first");
+  if (!betas) return fail("ehb_decode: betas is NULL");
+  return smpl_run(ctx, n, R, betas, ctx->img_of_body.as<int32_t>(), nullptr, verts, joints, stream);
+}
+
+}  // extern "C"

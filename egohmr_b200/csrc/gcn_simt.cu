@@ -1,0 +1,307 @@
+// SIMT (fp32 FFMA) kernels of the denoise step that are HBM/latency bound rather than contraction bound:
+//   K2  gcn_input_kernel   — the algebraically folded 3718-wide input ModulatedGraphConv + BN + ReLU
+//   K3  gcn_output_kernel  — output ModulatedGraphConv (hid -> 6), cond/uncond fuse-select and the DDIM/DDPM update
+//   sgemm_nn               — plain fp32 GEMM for the once-per-batch conditioning folds and for the fp32 check path
+//   gcn_hidden_epilogue    — check-path twin of the tcgen05 kernel's epilogue (reads H = X.Wcat from global)
+#include "kernels.cuh"
+
+namespace ehb {
+namespace {
+
+// ------------------------------------------------------------------------------------------------ sgemm
+constexpr int GT = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                       float* __restrict__ C, int M, int N, int K, int lda, int ldb,
+                                                       int ldc, int accumulate) {
+  __shared__ float As[GK][GT + 4];
+  __shared__ float Bs[GK][GT + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GK) {
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      const int mm = e / GK, kk = e % GK;
+      const int gm = m0 + mm, gk = k0 + kk;
+      As[kk][mm] = (gm < M && gk < K) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
+    }
+    for (int e = threadIdx.x; e < GT * GK; e += 256) {
+      const int kk = e / GT, nn = e % GT;
+      const int gk = k0 + kk, gn = n0 + nn;
+      Bs[kk][nn] = (gk < K && gn < N) ? B[static_cast<size_t>(gk) * ldb + gn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) b[i] = Bs[kk][tx * 4 + i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(a[i], b[jn], acc[i][jn]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int jn = 0; jn < 4; ++jn) {
+      const int gn = n0 + tx * 4 + jn;
+      if (gn >= N) continue;
+      float* dst = C + static_cast<size_t>(gm) * ldc + gn;
+      *dst = accumulate ? (*dst + acc[i][jn]) : acc[i][jn];
+    }
+  }
+}
+
+// fp16 hi/lo operand split shared by every producer of a GEMM A operand
+__device__ __forceinline__ float store_hl(__half* out_hl, size_t row, int C, int c, float v, float act_scale) {
+  const float sv = v * act_scale;
+  const __half hi = __float2half_rn(sv);
+  const __half lo = __float2half_rn(sv - __half2float(hi));
+  out_hl[row * (2 * static_cast<size_t>(C)) + c] = hi;
+  out_hl[row * (2 * static_cast<size_t>(C)) + C + c] = lo;
+  return fabsf(sv);
+}
+
+__device__ __forceinline__ size_t slot_row0(int slot) {
+  return static_cast<size_t>(slot / SLOTS_PER_TILE) * TILE_ROWS + static_cast<size_t>(slot % SLOTS_PER_TILE) * NJ;
+}
+
+// ------------------------------------------------------------------------------------------------ K2
+// Reference: EgoHMR.forward builds feat = [img*vis | scene | transl | cam | Linear6->512(x_t) | temb] (egohmr.py:190-236)
+// and feeds it to gconv_input (modulated_gcn.py:99-101).  Because the feature is a concatenation and the layer is
+// linear before the joint mix, feat.W_k splits into per-image, per-step and per-joint terms:
+//   h_k[j] = vis[j]*a_k[img] (conditioned pass only) + be_k[img] + ct_k[step] + x_t[j,:].wx_k
+__global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ InputLayerParams p) {
+  __shared__ float xs[NJ][6];
+  __shared__ float visf[NJ];
+  const int slot = blockIdx.x;
+  const int body = p.slot_body[slot];
+  const int img = p.img_of_body[body];
+  const bool cond = p.slot_cond[slot] != 0;
+  if (threadIdx.x < XDIM) xs[threadIdx.x / 6][threadIdx.x % 6] = p.x_t[static_cast<size_t>(body) * XDIM + threadIdx.x];
+  if (threadIdx.x < NJ) visf[threadIdx.x] = (cond && p.vis[img * NJ + threadIdx.x]) ? 1.f : 0.f;
+  __syncthreads();
+  const int C = p.C;
+  const size_t row0 = slot_row0(slot);
+  float amax = 0.f;
+  {
+    const int c = blockIdx.y * 128 + threadIdx.x;  // C % 128 == 0
+    const float a0 = p.a01[(static_cast<size_t>(img) * 2 + 0) * C + c];
+    const float a1 = p.a01[(static_cast<size_t>(img) * 2 + 1) * C + c];
+    const float base0 = p.be01[(static_cast<size_t>(img) * 2 + 0) * C + c] + p.ct01[(static_cast<size_t>(p.step) * 2 + 0) * C + c];
+    const float base1 = p.be01[(static_cast<size_t>(img) * 2 + 1) * C + c] + p.ct01[(static_cast<size_t>(p.step) * 2 + 1) * C + c];
+    float w0[6], w1[6];
+#pragma unroll
+    for (int d = 0; d < 6; ++d) {
+      w0[d] = p.wx01[(0 * 6 + d) * C + c];
+      w1[d] = p.wx01[(1 * 6 + d) * C + c];
+    }
+    float g[NJ], y[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < 6; ++d) {
+        x0 = fmaf(xs[j][d], w0[d], x0);
+        x1 = fmaf(xs[j][d], w1[d], x1);
+      }
+      const float h0 = fmaf(visf[j], a0, base0) + x0;
+      const float h1 = fmaf(visf[j], a1, base1) + x1;
+      const float m = p.mod[j * C + c];
+      g[j] = m * h1;
+      y[j] = p.adj.diag[j] * (m * h0);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float acc = y[j];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[j][i], g[i], acc);
+      y[j] = acc;
+    }
+    const float sc = p.bn_scale[c], sh = p.bn_shift[c];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float v = fmaxf(fmaf(y[j], sc, sh), 0.f);
+      p.res[(row0 + j) * C + c] = v;
+      amax = fmaxf(amax, store_hl(p.out_hl, row0 + j, C, c, v, p.act_scale));
+    }
+  }
+  if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------ K3
+// Output ModulatedGraphConv (no BN/ReLU, modulated_gcn.py:111), the diffuse_fuse select of egohmr.py:239-254
+// (guidance_param == 0: invisible joints take the image-masked pass, visible joints the image-conditioned pass)
+// and one sampler update (gaussian_diffusion.py:298-337 p_sample, :340-388 with gradient, :511-556 ddim_sample).
+// The update replays the reference's fp32 op order with contraction disabled so equal inputs give equal bits.
+__global__ void __launch_bounds__(256) gcn_output_kernel(const __grid_constant__ OutputLayerParams p) {
+  __shared__ float hs[2][NJ][12];
+  const int body = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = p.C;
+  const int slots[2] = {p.body_slot[body * 2 + 0], p.body_slot[body * 2 + 1]};
+  for (int rr = warp; rr < 2 * NJ; rr += 8) {
+    const int pass = rr / NJ, j = rr % NJ;
+    if (slots[pass] < 0) continue;
+    const float* arow = p.act + (slot_row0(slots[pass]) + j) * C;
+    float acc[12] = {};
+    for (int k = lane; k < C; k += 32) {
+      const float a = arow[k];
+      const float4* wp = reinterpret_cast<const float4*>(p.wout + static_cast<size_t>(k) * 12);
+      const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+      acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]);
+      acc[3] = fmaf(a, w0.w, acc[3]); acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
+      acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]); acc[8] = fmaf(a, w2.x, acc[8]);
+      acc[9] = fmaf(a, w2.y, acc[9]); acc[10] = fmaf(a, w2.z, acc[10]); acc[11] = fmaf(a, w2.w, acc[11]);
+    }
+#pragma unroll
+    for (int o = 0; o < 12; ++o) {
+      float v = acc[o];
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+      if (lane == 0) hs[pass][j][o] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= XDIM) return;
+  const int e = threadIdx.x, j = e / 6, d = e % 6;
+  float out[2] = {0.f, 0.f};
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    if (slots[pass] < 0) continue;
+    float acc = p.adj.diag[j] * (p.mod[j * 6 + d] * hs[pass][j][d]);
+    for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[j][i], p.mod[i * 6 + d] * hs[pass][i][6 + d], acc);
+    out[pass] = acc + p.bias[d];
+  }
+  const int img = p.img_of_body[body];
+  float x0;
+  if (p.diffuse_fuse) {
+    x0 = p.vis[img * NJ + j] ? out[0] : out[1];
+  } else {
+    x0 = out[0];
+  }
+  const size_t idx = static_cast<size_t>(body) * XDIM + e;
+  if (p.out_cond) p.out_cond[idx] = out[0];
+  if (p.out_uncond) p.out_uncond[idx] = out[1];
+  const float x = p.x_t[idx];
+  float xp;
+  if (p.kind == SAMPLER_DDIM) {
+    const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(p.coef.c[0], x), x0), p.coef.c[1]);
+    xp = __fadd_rn(__fmul_rn(x0, p.coef.c[2]), __fmul_rn(p.coef.c[3], eps));
+  } else {
+    float mean = __fadd_rn(__fmul_rn(p.coef.c[0], x0), __fmul_rn(p.coef.c[1], x));
+    if (p.grad) mean = __fadd_rn(mean, __fmul_rn(p.coef.c[3], p.grad[idx]));
+    const float nz = p.noise ? __fmul_rn(p.coef.c[2], p.noise[idx]) : 0.f;
+    xp = __fadd_rn(mean, nz);
+  }
+  p.x0[idx] = x0;
+  p.x_prev[idx] = xp;
+}
+
+// ------------------------------------------------------------------------------------------------ check path
+struct HiddenSimtParams {
+  AdjMix adj;
+  const float* H;       // [rows_pad][2C]  h0 | h1
+  const float* mod;     // [24][C] unscaled M
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* res_in;  // may alias out_f32
+  float* out_f32;
+  __half* out_hl;
+  int* overflow_flag;
+  float act_scale;
+  int C, n_slots, add_res, write_hl;
+};
+
+__global__ void __launch_bounds__(128) gcn_hidden_epilogue_kernel(const __grid_constant__ HiddenSimtParams p) {
+  const int slot = blockIdx.x;
+  const int C = p.C;
+  const size_t row0 = slot_row0(slot);
+  float amax = 0.f;
+  {
+    const int c = blockIdx.y * 128 + threadIdx.x;  // C % 128 == 0
+    float g[NJ], y[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const float m = p.mod[j * C + c];
+      const float h0 = p.H[(row0 + j) * (2 * static_cast<size_t>(C)) + c];
+      const float h1 = p.H[(row0 + j) * (2 * static_cast<size_t>(C)) + C + c];
+      g[j] = m * h1;
+      y[j] = p.adj.diag[j] * (m * h0);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float acc = y[j];
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[j][i], g[i], acc);
+      y[j] = acc;
+    }
+    const float sc = p.bn_scale[c], sh = p.bn_shift[c];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float v = fmaxf(fmaf(y[j], sc, sh), 0.f);
+      if (p.add_res) v += p.res_in[(row0 + j) * C + c];
+      p.out_f32[(row0 + j) * C + c] = v;
+      if (p.write_hl) amax = fmaxf(amax, store_hl(p.out_hl, row0 + j, C, c, v, p.act_scale));
+    }
+  }
+  if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
+}
+
+}  // namespace
+
+cudaError_t launch_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                            int accumulate, cudaStream_t stream) {
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
+  sgemm_nn_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream) {
+  if (p.n_slots <= 0) return cudaSuccess;
+  gcn_input_kernel<<<dim3(p.n_slots, p.C / 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gcn_output(const OutputLayerParams& p, cudaStream_t stream) {
+  if (p.n_bodies <= 0) return cudaSuccess;
+  gcn_output_kernel<<<p.n_bodies, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gcn_hidden_simt(const float* x_f32, const float* wcat, float* h_tmp, const HiddenLayerParams& p,
+                                   const float* mod_unscaled, float* out_f32, cudaStream_t stream) {
+  // Check path: x_f32 is the fp32 layer input, p.res the residual source (add_res), out_f32 the fp32 destination
+  // (may alias p.res: every element is read and written by the same thread).
+  const int rows = p.n_mtiles * TILE_ROWS;
+  cudaError_t e = launch_sgemm_nn(x_f32, wcat, h_tmp, rows, 2 * p.C, p.C, p.C, 2 * p.C, 2 * p.C, 0, stream);
+  if (e != cudaSuccess) return e;
+  HiddenSimtParams q;
+  q.adj = p.adj;
+  q.H = h_tmp;
+  q.mod = mod_unscaled;
+  q.bn_scale = p.bn_scale;
+  q.bn_shift = p.bn_shift;
+  q.res_in = p.res;
+  q.out_f32 = out_f32;
+  q.out_hl = p.out_hl;
+  q.overflow_flag = p.overflow_flag;
+  q.act_scale = p.act_scale;
+  q.C = p.C;
+  q.n_slots = p.n_slots;
+  q.add_res = p.add_res;
+  q.write_hl = p.write_hl;
+  if (p.n_slots <= 0) return cudaSuccess;
+  gcn_hidden_epilogue_kernel<<<dim3(p.n_slots, p.C / 128), 128, 0, stream>>>(q);
+  return cudaGetLastError();
+}
+
+}  // namespace ehb

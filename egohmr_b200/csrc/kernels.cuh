@@ -1,0 +1,133 @@
+// Internal (non-ABI) declarations shared by the CUDA translation units.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+namespace ehb {
+
+constexpr int NJ = 24;          // SMPL joints == graph nodes
+constexpr int XDIM = NJ * 6;    // 144-d rot6d body representation
+constexpr int SLOTS_PER_TILE = 5;   // (body,pass) slots per 128-row GEMM tile (5*24 = 120 rows + 8 pad)
+constexpr int TILE_ROWS = 128;
+
+// sym(adj + adj2) of one ModulatedGraphConv, split the way its forward uses it
+// (reference: models/egohmr/modulated_gcn/modulated_gcn_conv.py:42-46): `adj*E` (diagonal) and `adj*(1-E)`.
+struct AdjMix {
+  float diag[NJ];
+  float off[NJ][NJ];  // off[j][i], zero on the diagonal
+};
+
+// Epilogue of one hidden ModulatedGraphConv + BatchNorm1d(eval) + ReLU (+ residual).
+struct HiddenLayerParams {
+  AdjMix adj;
+  const float* mod;       // [24][C]  M[j][c] / (act_scale * w_scale)   (undoes the fp16 operand scaling, exact)
+  const float* bn_scale;  // [C]      gamma / sqrt(var + eps)
+  const float* bn_shift;  // [C]      beta + (bias - mean) * bn_scale
+  float* res;             // [rows_pad][C] fp32 block-boundary activations (read if add_res, written if write_f32)
+  __half* out_hl;         // [rows_pad][2C] next layer's A operand: [hi(C) | lo(C)] of act_scale * value
+  int* overflow_flag;     // set to 1 if a scaled activation leaves the fp16 range
+  float act_scale;
+  int C;                  // channels (== K of the GEMM)
+  int n_mtiles, n_ntiles; // n_ntiles = C / 128
+  int n_slots;            // valid (body,pass) slots; slot s lives in tile s/5 at rows (s%5)*24 ..
+  int add_res, write_f32, write_hl;
+};
+
+// launchers (gcn_umma.cu / gcn_simt.cu / smpl_lbs.cu)
+cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
+                                   int num_sms, cudaStream_t stream);
+size_t gcn_hidden_umma_smem_bytes();
+
+// fp32 SIMT check path for the same layer: H = X * Wcat via sgemm, then the identical epilogue.
+cudaError_t launch_gcn_hidden_simt(const float* x_f32, const float* wcat /*[K][2C] fp32*/, float* h_tmp /*[rows][2C]*/,
+                                   const HiddenLayerParams& p, const float* mod_unscaled, float* out_f32,
+                                   cudaStream_t stream);
+
+// C[M][N] = A[M][K] * B[K][N]  (+ C if accumulate), all row-major fp32, plain FFMA.
+cudaError_t launch_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
+                            int accumulate, cudaStream_t stream);
+
+struct InputLayerParams {
+  AdjMix adj;
+  const float* a01;      // [n_img][2][C]   img_feat . W_k[0:img_dim]
+  const float* be01;     // [n_img][2][C]   rest_feat . W_k[img_dim:cond_dim] + inproc_b . W_k[x rows]
+  const float* ct01;     // [n_steps][2][C] temb(step) . W_k[temb rows]
+  const float* wx01;     // [2][6][C]       inproc_w^T . W_k[x rows]
+  const float* mod;      // [24][C] (unscaled M)
+  const float* bn_scale; // [C]
+  const float* bn_shift; // [C]
+  const uint8_t* vis;    // [n_img][24]
+  const int32_t* slot_body;  // [n_slots]
+  const uint8_t* slot_cond;  // [n_slots] 1 = image-conditioned pass, 0 = image-masked pass
+  const int32_t* img_of_body;
+  const float* x_t;      // [B][144]
+  float* res;            // [rows_pad][C]
+  __half* out_hl;        // [rows_pad][2C]
+  int* overflow_flag;
+  float act_scale;
+  int C, n_slots, step;
+};
+cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream);
+
+// Per-step sampler coefficients (host-computed in fp32 exactly as the reference's torch ops would):
+//  DDIM (eta=0):  c[0]=sqrt_recip_alphas_cumprod, c[1]=sqrt_recipm1_alphas_cumprod, c[2]=sqrt(alpha_bar_prev),
+//                 c[3]=sqrt(1-alpha_bar_prev)
+//  DDPM:          c[0]=posterior_mean_coef1, c[1]=posterior_mean_coef2, c[2]=(t!=0)*exp(0.5*log_var),
+//                 c[3]=gradient scale (cond_grad_weight*variance, or cond_grad_weight*0.01), 0 when unguided
+struct StepCoef {
+  float c[8];
+};
+enum SamplerKind { SAMPLER_DDIM = 0, SAMPLER_DDPM = 1 };
+
+struct OutputLayerParams {
+  AdjMix adj;
+  const float* act;       // [rows_pad][C] fp32 activations of the last block
+  const float* wout;      // [C][12]  (k*6+d)
+  const float* mod;       // [24][6]
+  const float* bias;      // [6]
+  const uint8_t* vis;     // [n_img][24]
+  const int32_t* img_of_body;
+  const int32_t* body_slot;  // [B][2]: slot of the cond pass, slot of the uncond pass (-1 = not evaluated)
+  const float* x_t;       // [B][144]
+  const float* noise;     // [B][144] or null
+  const float* grad;      // [B][144] or null
+  float* x_prev;          // [B][144]
+  float* x0;              // [B][144]
+  float* out_cond;        // optional [B][144] raw image-conditioned denoiser output (tests)
+  float* out_uncond;      // optional [B][144]
+  StepCoef coef;
+  int kind;
+  int C, n_bodies, diffuse_fuse;
+};
+cudaError_t launch_gcn_output(const OutputLayerParams& p, cudaStream_t stream);
+
+// ---- SMPL ----
+struct SmplDevice {
+  const float* v_template;   // [V][3]
+  const float* shapedirs;    // [V][3][NB]
+  const float* posedirs;     // [207][V*3]
+  const float* lbs_weights;  // [V][24]
+  const float* j_template;   // [24][3]    J_regressor . v_template
+  const float* j_shapedirs;  // [24][3][NB] J_regressor . shapedirs
+  const int32_t* extra_vids; // [n_extra]
+  int parents[NJ];
+  int V, NB, n_extra;
+};
+// x (normalised rot6d, [B][144]) -> R [B][24][9]; mean/std may be null (identity).
+cudaError_t launch_rot6d(const float* x, const float* mean, const float* std_, float* R, int n_bodies,
+                         cudaStream_t stream);
+// generic [n][6] -> [n][9] ('diffusion' column order), no normalisation stats
+cudaError_t launch_rot6d_flat(const float* x6, float* R, int n, cudaStream_t stream);
+// R [B][24][9], betas [nb][NB] indexed through beta_index (null = identity) -> A [B][24][12], posed joints [B][24][3],
+// pose feature [B][207]
+cudaError_t launch_smpl_pose(const SmplDevice& m, const float* R, const float* betas, const int32_t* beta_index,
+                             float* A, float* joints24, float* posefeat, int n_bodies, cudaStream_t stream);
+cudaError_t launch_smpl_skin(const SmplDevice& m, const float* betas, const int32_t* beta_index, const float* A,
+                             const float* posefeat, const float* transl /*[B][3] or null*/, float* verts,
+                             int n_bodies, cudaStream_t stream);
+cudaError_t launch_smpl_joints(const SmplDevice& m, const float* joints24, const float* verts, const float* transl,
+                               float* joints /*[B][24+n_extra][3]*/, int n_bodies, cudaStream_t stream);
+
+}  // namespace ehb

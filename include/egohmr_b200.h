@@ -1,0 +1,141 @@
+/*
+ * egohmr_b200 — C ABI of the B200-native EgoHMR diffusion-sampling hot path.
+ *
+ * Every entry point replaces one piece of the reference's Python hot path (citations are into the reference tree,
+ * sanweiliti/EgoHMR @ dc4e0a0).  Plain pointers and sizes only: no torch / C++ types cross this boundary.
+ * Unless marked HOST, pointers are DEVICE pointers on the context's device; `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  All calls return 0 on success; on failure they return non-zero and
+ * ehb_last_error() describes why.  No hot call allocates, synchronises the host, or touches the CPU for math.
+ * There is no CPU fallback: without a CUDA device ehb_ctx_create fails.
+ */
+#ifndef EGOHMR_B200_H_
+#define EGOHMR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EHB_NUM_JOINTS 24
+#define EHB_XDIM 144 /* 24 joints x 6-D rotation */
+
+typedef struct ehb_ctx ehb_ctx;
+
+/* One ModulatedGraphConv (+ its BatchNorm1d when it is wrapped in a _GraphConv), parameters in the reference's
+ * state_dict layout (models/egohmr/modulated_gcn/modulated_gcn_conv.py:16-36, modulated_gcn.py:9-19).  HOST. */
+typedef struct {
+  int32_t in_dim, out_dim;
+  const float* W;    /* [2][in_dim][out_dim]   "...gconv.W"    */
+  const float* M;    /* [24][out_dim]          "...gconv.M"    */
+  const float* adj2; /* [24][24]               "...gconv.adj2" */
+  const float* bias; /* [out_dim]              "...gconv.bias" */
+  const float* bn_weight; /* [out_dim] or NULL (gconv_output has no BN) "...bn.weight"       */
+  const float* bn_bias;   /* "...bn.bias"         */
+  const float* bn_mean;   /* "...bn.running_mean" */
+  const float* bn_var;    /* "...bn.running_var"  */
+  float bn_eps;
+} ehb_gconv;
+
+/* The denoiser: ModulatedGCN (modulated_gcn.py:61-116) + InputProcess (egohmr.py:646-655) + the feature layout of
+ * EgoHMR.forward's 3718-wide input (egohmr.py:220-236): [img(img_dim) | rest(cond_dim-img_dim) | x_feat | temb]. HOST. */
+typedef struct {
+  int32_t hid;       /* gcn_hid_dim, multiple of 128 */
+  int32_t n_blocks;  /* diffusion_blk */
+  int32_t img_dim;   /* 2048 */
+  int32_t cond_dim;  /* 2694 = img + scene 512 + transl 128 + cam 6 */
+  int32_t xfeat_dim; /* 512 */
+  int32_t temb_dim;  /* 512 */
+  int32_t diffuse_fuse; /* egohmr.py:239 */
+  const float* adj;      /* [24][24] normalised skeleton adjacency built in egohmr.py:86-94 */
+  const float* inproc_w; /* [xfeat_dim][6]  "input_process.poseEmbedding.weight" */
+  const float* inproc_b; /* [xfeat_dim]     "input_process.poseEmbedding.bias"   */
+  const ehb_gconv* layers; /* [0] gconv_input, [1 .. 2*n_blocks] gconv_layers.{b}.gconv{1,2}, [last] gconv_output */
+  int32_t n_layers;        /* 2*n_blocks + 2 */
+} ehb_gcn_weights;
+
+/* SMPL model tensors as smplx stores them (smplx/body_models.py::SMPL.__init__).  HOST. */
+typedef struct {
+  int32_t n_verts;       /* 6890 */
+  int32_t n_betas;       /* 10   */
+  int32_t n_extra;       /* 21 vertex-picked joints appended by VertexJointSelector */
+  const float* v_template;  /* [V][3] */
+  const float* shapedirs;   /* [V][3][n_betas] */
+  const float* posedirs;    /* [207][V*3] */
+  const float* J_regressor; /* [24][V] */
+  const float* lbs_weights; /* [V][24] */
+  const int32_t* parents;   /* [24], parents[0] = -1 */
+  const int32_t* extra_vertex_ids; /* [n_extra] */
+} ehb_smpl_model;
+
+const char* ehb_last_error(void);
+/* number of kernels this library has launched on `ctx` since creation (bench.py's gpu_launches) */
+int64_t ehb_launch_count(const ehb_ctx* ctx);
+
+int ehb_ctx_create(int device, ehb_ctx** out);
+void ehb_ctx_destroy(ehb_ctx* ctx);
+
+/* models/egohmr/egohmr.py:95-99 (ModulatedGCN construction) + load_state_dict (test_egohmr.py:125-126):
+ * ingest the denoiser weights and repack them into kernel layouts (fp16 hi/lo split, folded BN, folded input layer). */
+int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w);
+/* smplx.create('data/smpl', model_type='smpl', ...) (egohmr.py:105-107, test_egohmr.py:143-145) */
+int ehb_smpl_load(ehb_ctx* ctx, const ehb_smpl_model* m);
+/* body_rep_mean / body_rep_std (test_egohmr.py:109-111; used at egohmr.py:258,528).  HOST [144] each. */
+int ehb_set_norm(ehb_ctx* ctx, const float* mean, const float* std);
+
+/* GaussianDiffusion.__init__ tables (diffusion/gaussian_diffusion.py:122-169) reduced to what one sampler update
+ * needs.  kind 0 = ddim_sample (:511-556, eta = 0), 1 = p_sample / p_sample_with_grad (:298-388).
+ * coef is HOST [n_steps][8] floats, row i = coefficients of respaced timestep i (see DESIGN.md "sampler update"). */
+int ehb_set_schedule(ehb_ctx* ctx, int kind, int n_steps, const float* coef);
+
+/* Step-invariant conditioning of EgoHMR.forward (egohmr.py:178-223) for n_img images:
+ *   img_feat  [n_img][img_dim]            backbone output (:183)
+ *   rest_feat [n_img][cond_dim-img_dim]   [scene_feats | transl_feat | cam_feats] (:214-221)
+ *   vis       [n_img][24] uint8           vis_mask_smpl (:186-189)
+ *   temb      [n_steps][temb_dim]         embed_timestep(timestep_map[i]) for every respaced step i (:178)
+ * Folds them through the input ModulatedGraphConv's weight rows (one fp32 GEMM each). */
+int ehb_set_cond(ehb_ctx* ctx, int n_img, const float* img_feat, const float* rest_feat, const uint8_t* vis,
+                 int n_steps, const float* temb, void* stream);
+
+/* The chains to sample: body b is conditioned on image img_of_body[b] (HOST int32 [n_bodies]).
+ * The reference runs `num_samples` sequential chains per image (test_egohmr.py:251-255); here they are one batch. */
+int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body);
+
+/* One reverse-diffusion step = p_mean_variance (gaussian_diffusion.py:233-276: model call, i.e. the denoiser of
+ * egohmr.py:232-257) + p_sample / p_sample_with_grad / ddim_sample.
+ *   step   respaced timestep index i (the reference's `t`, uniform over the batch, :495)
+ *   x_t    [n_bodies][144] in;  noise [n_bodies][144] or NULL (ignored by DDIM, eta=0);
+ *   grad   [n_bodies][144] or NULL (model.guide_coll output, :379);
+ *   x_prev [n_bodies][144] out ('sample');  x0 [n_bodies][144] out ('pred_xstart' == 'pred_x_start'). */
+int ehb_denoise_step(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad, float* x_prev,
+                     float* x0, void* stream);
+/* Same, but also returns the raw image-conditioned / image-masked denoiser outputs (egohmr.py:237,246). Tests only. */
+int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
+                           float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream);
+
+/* utils/geometry.py:47-66 rot6d_to_rotmat(x, 'diffusion'): x6 [n][6] -> R [n][3][3]. */
+int ehb_rot6d_to_rotmat(ehb_ctx* ctx, const float* x6, int n, float* R, void* stream);
+
+/* egohmr.py:258-260 + :276: x0 (normalised) -> pose_6d = x0*std+mean -> R [n_bodies][24][3][3] -> SMPL.
+ * betas [n_img][n_betas] indexed through img_of_body.  verts [n_bodies][V][3] (may be NULL to skip skinning, then
+ * the 21 vertex-picked joints are skipped too and joints must be NULL), joints [n_bodies][45][3]. */
+int ehb_decode(ehb_ctx* ctx, const float* x0, const float* betas, float* pose6d, float* R, float* verts, float* joints,
+               void* stream);
+
+/* smplx SMPL.forward(betas, body_pose, global_orient, transl, pose2rot=False) (call sites egohmr.py:276,492,537,
+ * test_egohmr.py:291-292): R [n][24][3][3] (global_orient first), betas [n][n_betas], transl [n][3] or NULL. */
+int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, const float* transl, float* verts,
+                     float* joints, void* stream);
+
+/* Diagnostics.  gemm_mode 0 = tcgen05 fp16x3 kernel (product path), 1 = fp32 FFMA check path (tests only). */
+int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);
+/* Returns 1 (and clears it) if any fp16 operand overflowed since the last call; synchronises `stream`. */
+int ehb_check_overflow(ehb_ctx* ctx, void* stream);
+/* Runs only hidden layer `layer` (1-based index into ehb_gcn_weights.layers) `iters` times on the current
+ * activations and returns the average device time in ms through *ms (bench.py's roofline leg). */
+int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGOHMR_B200_H_ */
