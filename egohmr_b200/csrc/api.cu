@@ -575,6 +575,15 @@ int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* s
   return 0;
 }
 
+int ehb_debug_get_buffer(ehb_ctx* ctx, int which, void** ptr, uint64_t* bytes) {
+  if (!ctx || !ptr || !bytes) return fail("ehb_debug_get_buffer: null argument");
+  const DevBuf* b = which == 0 ? &ctx->res : (which == 1 ? &ctx->act_hl[0] : (which == 2 ? &ctx->act_hl[1] : nullptr));
+  if (!b) return fail("ehb_debug_get_buffer: which must be 0, 1 or 2");
+  *ptr = b->p;
+  *bytes = b->bytes;
+  return 0;
+}
+
 int ehb_rot6d_to_rotmat(ehb_ctx* ctx, const float* x6, int n, float* R, void* stream_) {
   if (!ctx || !x6 || !R) return fail("ehb_rot6d_to_rotmat: null argument");
   if (n < 0) return fail("ehb_rot6d_to_rotmat: negative n");

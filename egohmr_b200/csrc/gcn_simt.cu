@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ 
   const int body = p.slot_body[slot];
   const int img = p.img_of_body[body];
   const bool cond = p.slot_cond[slot] != 0;
-  if (threadIdx.x < XDIM) xs[threadIdx.x / 6][threadIdx.x % 6] = p.x_t[static_cast<size_t>(body) * XDIM + threadIdx.x];
+  for (int e = threadIdx.x; e < XDIM; e += blockDim.x) xs[e / 6][e % 6] = p.x_t[static_cast<size_t>(body) * XDIM + e];
   if (threadIdx.x < NJ) visf[threadIdx.x] = (cond && p.vis[img * NJ + threadIdx.x]) ? 1.f : 0.f;
   __syncthreads();
   const int C = p.C;

@@ -12,10 +12,10 @@
 // (3 tcgen05.mma kind::f16 per 16-wide k slice).  The dropped lo*lo term and the fp16 rounding of lo are ~2^-22
 // relative, i.e. fp32 SGEMM territory.
 //
-// Pipeline.  warp 0: TMA producer (A_hi, A_lo, B_hi, B_lo tiles, 64B swizzle, 4-stage mbarrier ring);
-// warp 1: single-thread tcgen05.mma issuer, fp32 accumulator double-buffered in TMEM (2 x 256 columns);
-// warps 4-7: tcgen05.ld the accumulator (one TMEM lane quadrant each), apply the modulation M and stage
-// (M o h1), diag(A)(M o h0) transposed in shared memory; warps 8-12: one (body,pass) slot each, lane = channel:
+// Pipeline.  warp 4: TMA producer (A_hi, A_lo, B_hi, B_lo tiles, 64B swizzle, 4-stage mbarrier ring);
+// warp 5: single-thread tcgen05.mma issuer, fp32 accumulator double-buffered in TMEM (2 x 256 columns);
+// warps 0-3: tcgen05.ld the accumulator (one TMEM lane quadrant each), apply the modulation M and stage
+// (M o h1), diag(A)(M o h0) transposed in shared memory; warps 6-10: one (body,pass) slot each, lane = channel:
 // 24x24 joint mix with the adjacency taken straight from the kernel-parameter constant bank, BN scale/shift, ReLU,
 // residual, then write the next layer's operand (hi|lo fp16) and/or the fp32 block-boundary activations.
 #include "kernels.cuh"
@@ -37,9 +37,11 @@ constexpr int GT_LD = 132;        // padded row length (floats) of the transpose
 constexpr int EPI_BYTES = 2 * CHUNK * GT_LD * 4;
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
-constexpr int NUM_WARPS = 13;
+// warp roles: 0-3 tcgen05.ld (warp index == TMEM lane quadrant), 4 TMA producer (+ TMEM alloc/dealloc),
+// 5 MMA issuer, 6-10 joint-mix/store.  11 warps keep the per-thread register budget at 168.
+constexpr int NUM_WARPS = 11;
 constexpr int NUM_THREADS = NUM_WARPS * 32;
-constexpr int LD_WARP0 = 4, MIX_WARP0 = 8;
+constexpr int LD_WARP0 = 0, TMA_WARP = 4, MMA_WARP = 5, MIX_WARP0 = 6;
 constexpr int TMEM_COLS = 512;
 
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
@@ -71,11 +73,11 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int KB = p.C / BK;
   const int total_tiles = p.n_mtiles * p.n_ntiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == TMA_WARP && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&bars->full[s], 1);
       ptx::mbar_init(&bars->empty[s], 1);
@@ -84,11 +86,11 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       ptx::mbar_init(&bars->tfull[s], 1);
       ptx::mbar_init(&bars->tempty[s], 4);   // one elected lane of each tcgen05.ld warp
     }
-    ptx::mbar_init(&bars->cfull, 4 * 32);    // every thread of warps 4-7
-    ptx::mbar_init(&bars->cempty, 5 * 32);   // every thread of warps 8-12
+    ptx::mbar_init(&bars->cfull, 4 * 32);    // every thread of the tcgen05.ld warps
+    ptx::mbar_init(&bars->cempty, 5 * 32);   // every thread of the mix warps
     ptx::fence_mbar_init();
   }
-  if (warp == 2) {
+  if (warp == TMA_WARP) {
     ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
     ptx::tmem_relinquish();
   }
@@ -97,7 +99,7 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
-  if (warp == 0) {
+  if (warp == TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
@@ -121,7 +123,7 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BM, BN);
     int stage = 0;
@@ -162,7 +164,7 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         aphase ^= 1;
       }
     }
-  } else if (warp >= LD_WARP0 && warp < MIX_WARP0) {
+  } else if (warp < LD_WARP0 + 4) {
     // ------------------------------------------------------------------ TMEM -> modulate -> shared (transposed)
     const int q = warp - LD_WARP0;  // == warp % 4: the TMEM lane quadrant this warp may read
     const int r = q * 32 + lane;    // tile row
@@ -225,7 +227,17 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool valid = (m_tile * SLOTS_PER_TILE + w) < p.n_slots;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 2 / CHUNK; ++ch, ++chunk_it) {
-        float g[NJ], y[NJ];
+        float g[NJ], y[NJ], rsd[NJ];
+        const int c = n_tile * (BN / 2) + ch * CHUNK + lane;
+        const size_t row0 = static_cast<size_t>(m_tile) * BM + NJ * w;
+        // residual rows are fetched before the hand-off wait: independent loads in flight, latency hidden
+        if (p.add_res && valid) {
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) rsd[jj] = __ldcg(p.res + (row0 + jj) * p.C + c);
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < NJ; ++jj) rsd[jj] = 0.f;
+        }
         ptx::mbar_wait(&bars->cfull, chunk_it & 1);
         {
           const float4* gp = reinterpret_cast<const float4*>(G_T + lane * GT_LD + NJ * w);
@@ -247,15 +259,12 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[jj][i], g[i], acc);
           y[jj] = acc;
         }
-        const int c = n_tile * (BN / 2) + ch * CHUNK + lane;
         const float sc = __ldg(p.bn_scale + c);
         const float sh = __ldg(p.bn_shift + c);
-        const size_t row0 = static_cast<size_t>(m_tile) * BM + NJ * w;
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) {
           const size_t row = row0 + jj;
-          float v = fmaxf(fmaf(y[jj], sc, sh), 0.f);
-          if (p.add_res) v += p.res[row * p.C + c];
+          const float v = fmaxf(fmaf(y[jj], sc, sh), 0.f) + rsd[jj];
           if (p.write_f32) p.res[row * p.C + c] = v;
           if (p.write_hl) {
             const float sv = v * p.act_scale;
@@ -273,7 +282,7 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == TMA_WARP) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }

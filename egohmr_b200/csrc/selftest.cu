@@ -27,6 +27,78 @@
     }                                                                            \
   } while (0)
 
+
+#include <cuda_fp16.h>
+// CPU double-precision evaluation of hidden layer `which_layer` (1 = gconv1 of block 0, 2 = gconv2 of block 0 with
+// the residual) at sampled (slot, channel) pairs, from the layer's actual fp16 hi/lo input operand.
+static int g_only_slot = -1, g_only_c = -1;
+static void spot_check_layer(ehb_ctx* ctx, int which_layer, const ehb_gconv& g, const float* adj, int C, int n_slots,
+                             float act_scale, const char* tag) {
+  void *p0 = nullptr, *p1 = nullptr, *pr = nullptr;
+  uint64_t b0 = 0, b1 = 0, br = 0;
+  ehb_debug_get_buffer(ctx, 1, &p0, &b0);
+  ehb_debug_get_buffer(ctx, 2, &p1, &b1);
+  ehb_debug_get_buffer(ctx, 0, &pr, &br);
+  std::vector<__half> h_a(b0 / 2), h_b(b1 / 2);
+  std::vector<float> res(br / 4);
+  cudaMemcpy(h_a.data(), p0, b0, cudaMemcpyDeviceToHost);
+  cudaMemcpy(h_b.data(), p1, b1, cudaMemcpyDeviceToHost);
+  cudaMemcpy(res.data(), pr, br, cudaMemcpyDeviceToHost);
+  const std::vector<__half>& in = which_layer == 1 ? h_a : h_b;
+  auto hl = [&](const std::vector<__half>& v, size_t row, int c) {
+    return (double(__half2float(v[row * 2 * C + c])) + double(__half2float(v[row * 2 * C + C + c]))) / act_scale;
+  };
+  float a[24][24];
+  for (int i = 0; i < 24; ++i)
+    for (int j = 0; j < 24; ++j) a[i][j] = adj[i * 24 + j] + g.adj2[i * 24 + j];
+  double worst = 0, worst_ref = 0;
+  int wslot = -1, wc = -1, wj = -1;
+  double by_j[24] = {0};
+  for (int slot = 0; slot < n_slots; ++slot)
+    for (int c = (g_only_c >= 0 ? g_only_c : (C <= 256 ? 0 : (slot * 37) % 64)); c < C; c += (g_only_c >= 0 ? C : (C <= 256 ? 1 : 61))) {
+      if (g_only_slot >= 0 && slot != g_only_slot) continue;
+      const size_t row0 = size_t(slot / 5) * 128 + size_t(slot % 5) * 24;
+      double h0[24], h1[24];
+      for (int j = 0; j < 24; ++j) {
+        double s0 = 0, s1 = 0;
+        for (int kk = 0; kk < C; ++kk) {
+          const double av = hl(in, row0 + j, kk);
+          s0 += av * g.W[(size_t(0) * C + kk) * C + c];
+          s1 += av * g.W[(size_t(1) * C + kk) * C + c];
+        }
+        h0[j] = s0;
+        h1[j] = s1;
+      }
+      const double sc = double(g.bn_weight[c]) / std::sqrt(double(g.bn_var[c]) + double(g.bn_eps));
+      const double sh = double(g.bn_bias[c]) + (double(g.bias[c]) - double(g.bn_mean[c])) * sc;
+      for (int j = 0; j < 24; ++j) {
+        double y = 0;
+        for (int i = 0; i < 24; ++i) {
+          const double s = (double(a[i][j]) + double(a[j][i])) / 2.0;
+          y += s * g.M[i * C + c] * (i == j ? h0[i] : h1[i]);
+        }
+        double ref = std::fmax(y * sc + sh, 0.0);
+        double got;
+        if (which_layer == 1) {
+          got = hl(h_b, row0 + j, c);
+        } else {
+          ref += hl(h_a, row0 + j, c);  // residual = block input = input-layer output
+          got = res[(row0 + j) * C + c];
+        }
+        const double d = std::fabs(got - ref);
+        if (g_only_c >= 0) std::printf("      j=%d ref=%.6f got=%.6f\n", j, ref, got);
+        by_j[j] = std::fmax(by_j[j], d);
+        if (d > worst) {
+          worst = d; worst_ref = ref; wslot = slot; wc = c; wj = j;
+        }
+      }
+    }
+  std::printf("[%s] layer-%d vs CPU fp64: max err %.3e (ref %.4f at slot %d ch %d joint %d)\n   by joint:", tag,
+              which_layer, worst, worst_ref, wslot, wc, wj);
+  for (int j = 0; j < 24; ++j) std::printf(" %.0e", by_j[j]);
+  std::printf("\n");
+}
+
 static std::mt19937 rng(1234);
 static std::vector<float> randn(size_t n, float s) {
   std::normal_distribution<float> d(0.f, s);
@@ -148,6 +220,10 @@ int main(int argc, char** argv) {
   CU(cudaMalloc(&d_ou, nx * 4));
 
   std::vector<float> ref_c(nx), ref_u(nx), ref_x0(nx), ref_xp(nx), got_c(nx), got_u(nx), got_x0(nx), got_xp(nx);
+  void* res_ptr = nullptr;
+  uint64_t res_bytes = 0;
+  CK(ehb_debug_get_buffer(ctx, 0, &res_ptr, &res_bytes));
+  std::vector<float> res_ref(res_bytes / 4), res_got(res_bytes / 4);
   // fp32 check path
   CK(ehb_debug_set_gemm_mode(ctx, 1));
   CK(ehb_denoise_step_debug(ctx, 2, d_x, nullptr, nullptr, d_xp, d_x0, d_oc, d_ou, nullptr));
@@ -156,6 +232,9 @@ int main(int argc, char** argv) {
   CU(cudaMemcpy(ref_u.data(), d_ou, nx * 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(ref_x0.data(), d_x0, nx * 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(ref_xp.data(), d_xp, nx * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(res_ref.data(), res_ptr, res_bytes, cudaMemcpyDeviceToHost));
+  spot_check_layer(ctx, 1, layers[1], adj.data(), C, 2 * B, 8.f, "fp32 check path");
+  if (nblk == 1) spot_check_layer(ctx, 2, layers[2], adj.data(), C, 2 * B, 8.f, "fp32 check path");
   std::printf("check path: overflow=%d  x0[0..3] = %g %g %g %g\n", ehb_check_overflow(ctx, nullptr), ref_x0[0],
               ref_x0[1], ref_x0[2], ref_x0[3]);
   // tcgen05 path
@@ -172,6 +251,43 @@ int main(int argc, char** argv) {
   CU(cudaMemcpy(got_u.data(), d_ou, nx * 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(got_x0.data(), d_x0, nx * 4, cudaMemcpyDeviceToHost));
   CU(cudaMemcpy(got_xp.data(), d_xp, nx * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(res_got.data(), res_ptr, res_bytes, cudaMemcpyDeviceToHost));
+  spot_check_layer(ctx, 1, layers[1], adj.data(), C, 2 * B, 8.f, "tcgen05 path");
+  if (nblk == 1) spot_check_layer(ctx, 2, layers[2], adj.data(), C, 2 * B, 8.f, "tcgen05 path");
+  {
+    // error map of the last block's fp32 activations: by row-in-tile (groups of 8) and by channel (groups of 32)
+    const size_t rows = res_ref.size() / C;
+    std::vector<double> by_row(16, 0.0), by_col(C / 32, 0.0), by_tile(rows / 128, 0.0);
+    double mx = 0, mr = 0;
+    size_t wr = 0;
+    int wcc = 0;
+    for (size_t r = 0; r < rows; ++r)
+      for (int c = 0; c < C; ++c) {
+        const double d = std::fabs(double(res_got[r * C + c]) - double(res_ref[r * C + c]));
+        if (d > mx) { wr = r; wcc = c; }
+        mr = std::fmax(mr, std::fabs(double(res_ref[r * C + c])));
+        if (!(d <= mx)) mx = d;
+        by_row[(r % 128) / 8] = std::fmax(by_row[(r % 128) / 8], d);
+        by_col[c / 32] = std::fmax(by_col[c / 32], d);
+        by_tile[r / 128] = std::fmax(by_tile[r / 128], d);
+      }
+    std::printf("worst res location: row %zu (tile %zu, slot-in-tile %zu, joint %zu) channel %d: check=%.6f umma=%.6f\n", wr,
+                wr / 128, (wr % 128) / 24, (wr % 128) % 24, wcc, res_ref[wr * C + wcc], res_got[wr * C + wcc]);
+    if (nblk == 1) {
+      g_only_slot = int((wr / 128) * 5 + (wr % 128) / 24);
+      g_only_c = wcc;
+      spot_check_layer(ctx, 1, layers[1], adj.data(), C, 2 * B, 8.f, "tcgen05 path @worst");
+      spot_check_layer(ctx, 2, layers[2], adj.data(), C, 2 * B, 8.f, "tcgen05 path @worst");
+      g_only_slot = g_only_c = -1;
+    }
+    std::printf("res (last block fp32 activations): max err %.3e (max|ref| %.3e)\n  by row-in-tile/8:", mx, mr);
+    for (double v : by_row) std::printf(" %.1e", v);
+    std::printf("\n  by channel/32:");
+    for (double v : by_col) std::printf(" %.1e", v);
+    std::printf("\n  by m-tile:");
+    for (size_t i = 0; i < by_tile.size() && i < 12; ++i) std::printf(" %.1e", by_tile[i]);
+    std::printf("\n");
+  }
   std::printf("tcgen05 path: overflow=%d  x0[0..3] = %g %g %g %g\n", ehb_check_overflow(ctx, nullptr), got_x0[0],
               got_x0[1], got_x0[2], got_x0[3]);
   double r;

@@ -135,6 +135,10 @@ int ehb_check_overflow(ehb_ctx* ctx, void* stream);
  * activations and returns the average device time in ms through *ms (bench.py's roofline leg). */
 int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* stream);
 
+/* Device pointer + size of an internal activation buffer (tests / bring-up only):
+ * which 0 = fp32 block-boundary activations [rows_pad][hid], 1/2 = fp16 [hi|lo] operand ping/pong [rows_pad][2*hid]. */
+int ehb_debug_get_buffer(ehb_ctx* ctx, int which, void** ptr, uint64_t* bytes);
+
 #ifdef __cplusplus
 }
 #endif
