@@ -1,0 +1,97 @@
+"""ctypes binding of libegohmr_b200.so (include/egohmr_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (``egohmr_b200/lib/libegohmr_b200.so``).  There is no
+fallback: if the shared object is missing, or a context cannot be created because there is no sm_100 GPU, the caller
+gets an exception — never a silent CPU / eager-PyTorch path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libegohmr_b200.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class EhbError(RuntimeError):
+    pass
+
+
+class GConv(C.Structure):
+    _fields_ = [("in_dim", C.c_int32), ("out_dim", C.c_int32), ("W", c_float_p), ("M", c_float_p), ("adj2", c_float_p),
+                ("bias", c_float_p), ("bn_weight", c_float_p), ("bn_bias", c_float_p), ("bn_mean", c_float_p),
+                ("bn_var", c_float_p), ("bn_eps", C.c_float)]
+
+
+class GcnWeights(C.Structure):
+    _fields_ = [("hid", C.c_int32), ("n_blocks", C.c_int32), ("img_dim", C.c_int32), ("cond_dim", C.c_int32),
+                ("xfeat_dim", C.c_int32), ("temb_dim", C.c_int32), ("diffuse_fuse", C.c_int32), ("adj", c_float_p),
+                ("inproc_w", c_float_p), ("inproc_b", c_float_p), ("layers", C.POINTER(GConv)), ("n_layers", C.c_int32)]
+
+
+class SmplModel(C.Structure):
+    _fields_ = [("n_verts", C.c_int32), ("n_betas", C.c_int32), ("n_extra", C.c_int32), ("v_template", c_float_p),
+                ("shapedirs", c_float_p), ("posedirs", c_float_p), ("J_regressor", c_float_p),
+                ("lbs_weights", c_float_p), ("parents", c_int32_p), ("extra_vertex_ids", c_int32_p)]
+
+
+# every symbol include/egohmr_b200.h declares: name -> (restype, argtypes)
+_vp = C.c_void_p
+SIGNATURES = {
+    "ehb_last_error": (C.c_char_p, []),
+    "ehb_launch_count": (C.c_int64, [_vp]),
+    "ehb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "ehb_ctx_destroy": (None, [_vp]),
+    "ehb_gcn_load": (C.c_int, [_vp, C.POINTER(GcnWeights)]),
+    "ehb_smpl_load": (C.c_int, [_vp, C.POINTER(SmplModel)]),
+    "ehb_set_norm": (C.c_int, [_vp, c_float_p, c_float_p]),
+    "ehb_set_schedule": (C.c_int, [_vp, C.c_int, C.c_int, c_float_p]),
+    "ehb_set_cond": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp]),
+    "ehb_set_temb": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "ehb_set_bodies": (C.c_int, [_vp, C.c_int, c_int32_p]),
+    "ehb_denoise_step": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_denoise_step_debug": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_sampler_update": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_rot6d_to_rotmat": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
+    "ehb_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_smpl_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_debug_set_gemm_mode": (C.c_int, [_vp, C.c_int]),
+    "ehb_check_overflow": (C.c_int, [_vp, _vp]),
+    "ehb_time_hidden_layer": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), _vp]),
+    "ehb_debug_get_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_uint64)]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree library and type every exported entry point.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EhbError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` first "
+                       "(there is no CPU / PyTorch fallback for the sampling hot path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise EhbError(load().ehb_last_error().decode("utf-8", "replace"))
+
+
+def f32(a):
+    """Contiguous float32 numpy view/copy (kept alive by the caller for the duration of the call)."""
+    return np.ascontiguousarray(np.asarray(a), dtype=np.float32)
+
+
+def fptr(a):
+    return a.ctypes.data_as(c_float_p)

@@ -367,16 +367,15 @@ int ehb_set_schedule(ehb_ctx* ctx, int kind, int n_steps, const float* coef) {
 }
 
 int ehb_set_cond(ehb_ctx* ctx, int n_img, const float* img_feat, const float* rest_feat, const uint8_t* vis,
-                 int n_steps, const float* temb, void* stream_) {
-  if (!ctx || !img_feat || !rest_feat || !vis || !temb) return fail("ehb_set_cond: null argument");
+                 void* stream_) {
+  if (!ctx || !img_feat || !rest_feat || !vis) return fail("ehb_set_cond: null argument");
   if (!ctx->gcn_loaded) return fail("ehb_set_cond: call ehb_gcn_load first");
-  if (n_img <= 0 || n_steps <= 0) return fail("ehb_set_cond: n_img and n_steps must be positive");
+  if (n_img <= 0) return fail("ehb_set_cond: n_img must be positive");
   EHB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int C = ctx->hid, C2 = 2 * C, rest = ctx->cond_dim - ctx->img_dim;
   EHB_CUDA(ctx->a01.ensure(sizeof(float) * n_img * C2));
   EHB_CUDA(ctx->be01.ensure(sizeof(float) * n_img * C2));
-  EHB_CUDA(ctx->ct01.ensure(sizeof(float) * n_steps * C2));
   EHB_CUDA(ctx->vis.ensure(static_cast<size_t>(n_img) * ehb::NJ));
   EHB_CUDA(cudaMemcpyAsync(ctx->vis.p, vis, static_cast<size_t>(n_img) * ehb::NJ, cudaMemcpyDeviceToDevice, stream));
   EHB_CUDA(ehb::launch_sgemm_nn(img_feat, ctx->w_img.as<float>(), ctx->a01.as<float>(), n_img, C2, ctx->img_dim,
@@ -389,10 +388,22 @@ int ehb_set_cond(ehb_ctx* ctx, int n_img, const float* img_feat, const float* re
   }
   EHB_CUDA(ehb::launch_sgemm_nn(rest_feat, ctx->w_rest.as<float>(), ctx->be01.as<float>(), n_img, C2, rest, rest, C2,
                                 C2, 1, stream));
+  ctx->launches += 3;
+  ctx->n_img = n_img;
+  return 0;
+}
+
+int ehb_set_temb(ehb_ctx* ctx, int n_steps, const float* temb, void* stream_) {
+  if (!ctx || !temb) return fail("ehb_set_temb: null argument");
+  if (!ctx->gcn_loaded) return fail("ehb_set_temb: call ehb_gcn_load first");
+  if (n_steps <= 0) return fail("ehb_set_temb: n_steps must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int C2 = 2 * ctx->hid;
+  EHB_CUDA(ctx->ct01.ensure(sizeof(float) * n_steps * C2));
   EHB_CUDA(ehb::launch_sgemm_nn(temb, ctx->w_temb.as<float>(), ctx->ct01.as<float>(), n_steps, C2, ctx->temb_dim,
                                 ctx->temb_dim, C2, C2, 0, stream));
-  ctx->launches += 4;
-  ctx->n_img = n_img;
+  ctx->launches += 1;
   ctx->n_steps_cond = n_steps;
   return 0;
 }
@@ -572,6 +583,18 @@ int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* s
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *ms = t / iters;
+  return 0;
+}
+
+int ehb_sampler_update(ehb_ctx* ctx, int step, int n, const float* x_t, const float* x0, const float* noise,
+                       const float* grad, float* x_prev, void* stream_) {
+  if (!ctx || !x_t || !x0 || !x_prev) return fail("ehb_sampler_update: null argument");
+  if (step < 0 || step >= static_cast<int>(ctx->coef.size())) return fail("ehb_sampler_update: step out of range");
+  if (n <= 0) return fail("ehb_sampler_update: n must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_sampler_update(ctx->coef[step], ctx->kind, x_t, x0, noise, grad, x_prev,
+                                      static_cast<size_t>(n) * ehb::XDIM, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += 1;
   return 0;
 }
 

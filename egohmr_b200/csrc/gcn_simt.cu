@@ -136,6 +136,26 @@ __global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ 
   if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
 }
 
+// One element of the reverse-diffusion update, in the reference's fp32 op order with contraction disabled.
+__device__ __forceinline__ float sampler_update_one(const StepCoef& coef, int kind, float x, float x0, const float* noise,
+                                                    const float* grad, size_t idx) {
+  if (kind == SAMPLER_DDIM) {
+    const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(coef.c[0], x), x0), coef.c[1]);
+    return __fadd_rn(__fmul_rn(x0, coef.c[2]), __fmul_rn(coef.c[3], eps));
+  }
+  float mean = __fadd_rn(__fmul_rn(coef.c[0], x0), __fmul_rn(coef.c[1], x));
+  if (grad) mean = __fadd_rn(mean, __fmul_rn(coef.c[3], grad[idx]));
+  const float nz = noise ? __fmul_rn(coef.c[2], noise[idx]) : 0.f;
+  return __fadd_rn(mean, nz);
+}
+
+__global__ void sampler_update_kernel(const StepCoef coef, int kind, const float* __restrict__ x_t,
+                                      const float* __restrict__ x0, const float* __restrict__ noise,
+                                      const float* __restrict__ grad, float* __restrict__ x_prev, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x_prev[i] = sampler_update_one(coef, kind, x_t[i], x0[i], noise, grad, i);
+}
+
 // ------------------------------------------------------------------------------------------------ K3
 // Output ModulatedGraphConv (no BN/ReLU, modulated_gcn.py:111), the diffuse_fuse select of egohmr.py:239-254
 // (guidance_param == 0: invisible joints take the image-masked pass, visible joints the image-conditioned pass)
@@ -190,19 +210,8 @@ __global__ void __launch_bounds__(256) gcn_output_kernel(const __grid_constant__
   const size_t idx = static_cast<size_t>(body) * XDIM + e;
   if (p.out_cond) p.out_cond[idx] = out[0];
   if (p.out_uncond) p.out_uncond[idx] = out[1];
-  const float x = p.x_t[idx];
-  float xp;
-  if (p.kind == SAMPLER_DDIM) {
-    const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(p.coef.c[0], x), x0), p.coef.c[1]);
-    xp = __fadd_rn(__fmul_rn(x0, p.coef.c[2]), __fmul_rn(p.coef.c[3], eps));
-  } else {
-    float mean = __fadd_rn(__fmul_rn(p.coef.c[0], x0), __fmul_rn(p.coef.c[1], x));
-    if (p.grad) mean = __fadd_rn(mean, __fmul_rn(p.coef.c[3], p.grad[idx]));
-    const float nz = p.noise ? __fmul_rn(p.coef.c[2], p.noise[idx]) : 0.f;
-    xp = __fadd_rn(mean, nz);
-  }
   p.x0[idx] = x0;
-  p.x_prev[idx] = xp;
+  p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
 }
 
 // ------------------------------------------------------------------------------------------------ check path
@@ -268,6 +277,15 @@ cudaError_t launch_sgemm_nn(const float* A, const float* B, float* C, int M, int
 cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream) {
   if (p.n_slots <= 0) return cudaSuccess;
   gcn_input_kernel<<<dim3(p.n_slots, p.C / 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sampler_update(const StepCoef& coef, int kind, const float* x_t, const float* x0,
+                                  const float* noise, const float* grad, float* x_prev, size_t n,
+                                  cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  sampler_update_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(coef, kind, x_t, x0, noise, grad,
+                                                                                    x_prev, n);
   return cudaGetLastError();
 }
 

@@ -206,7 +206,8 @@ int main(int argc, char** argv) {
   std::vector<uint8_t> vis(size_t(n_img) * 24);
   for (auto& v : vis) v = (rng() % 10) < 6;
   uint8_t* d_vis = to_dev(vis);
-  CK(ehb_set_cond(ctx, n_img, d_img, d_rest, d_vis, n_steps, d_temb, nullptr));
+  CK(ehb_set_cond(ctx, n_img, d_img, d_rest, d_vis, nullptr));
+  CK(ehb_set_temb(ctx, n_steps, d_temb, nullptr));
   std::vector<int32_t> iob(B);
   for (int b = 0; b < B; ++b) iob[b] = b / S;
   CK(ehb_set_bodies(ctx, B, iob.data()));

@@ -1,0 +1,340 @@
+"""diffusion/gaussian_diffusion.py of the reference, sampling side, behind the same call signatures.
+
+The float64 schedule tables are computed exactly as the reference does (same numpy calls, same order).  What changes
+is where a reverse step executes: when `model` is an `egohmr_b200` EgoHMR, one step = ONE C-ABI call
+(`ehb_denoise_step`: folded input layer -> 8 tcgen05 GCN layers x 2 passes -> output layer + fuse-select + sampler
+update) and the SMPL / projection work of `EgoHMR.forward` happens once, for the final x0, instead of on every step.
+Any other `model(batch, t) -> {'pred_x_start': ...}` callable still works through the generic path, whose sampler
+update is the same CUDA kernel (`ehb_sampler_update`).
+"""
+import math
+
+import numpy as np
+import torch as th
+
+from ..engine import Engine
+
+
+def betas_for_alpha_bar(num_diffusion_timesteps, alpha_bar, max_beta=0.999):
+    """gaussian_diffusion.py:49-66."""
+    out = []
+    for i in range(num_diffusion_timesteps):
+        lo, hi = i / num_diffusion_timesteps, (i + 1) / num_diffusion_timesteps
+        out.append(min(1 - alpha_bar(hi) / alpha_bar(lo), max_beta))
+    return np.array(out)
+
+
+def get_named_beta_schedule(schedule_name, num_diffusion_timesteps, scale_betas=1.0):
+    """gaussian_diffusion.py:22-46."""
+    if schedule_name == "linear":
+        scale = scale_betas * 1000 / num_diffusion_timesteps
+        return np.linspace(scale * 0.0001, scale * 0.02, num_diffusion_timesteps, dtype=np.float64)
+    if schedule_name == "cosine":
+        return betas_for_alpha_bar(num_diffusion_timesteps, lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2)
+    raise NotImplementedError(f"unknown beta schedule: {schedule_name}")
+
+
+def _extract_into_tensor(arr, timesteps, broadcast_shape):
+    """gaussian_diffusion.py:784-797."""
+    res = th.from_numpy(arr).to(device=timesteps.device)[timesteps].float()
+    while len(res.shape) < len(broadcast_shape):
+        res = res[..., None]
+    return res.expand(broadcast_shape)
+
+
+_generic_engines = {}
+
+
+def _generic_engine(device):
+    idx = device.index or 0
+    if idx not in _generic_engines:
+        _generic_engines[idx] = Engine(idx)
+    return _generic_engines[idx]
+
+
+class GaussianDiffusion:
+    """gaussian_diffusion.py:105-169 (tables) and :233-780 (sampling)."""
+
+    DDIM, DDPM = 0, 1
+
+    def __init__(self, *, betas, rescale_timesteps=False, body_rep_mean=None, body_rep_std=None):
+        self.rescale_timesteps = rescale_timesteps
+        self.body_rep_mean, self.body_rep_std = body_rep_mean, body_rep_std
+        betas = np.array(betas, dtype=np.float64)
+        self.betas = betas
+        assert len(betas.shape) == 1, "betas must be 1-D"
+        assert (betas > 0).all() and (betas <= 1).all()
+        self.num_timesteps = int(betas.shape[0])
+        alphas = 1.0 - betas
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.alphas_cumprod_next = np.append(self.alphas_cumprod[1:], 0.0)
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.log_one_minus_alphas_cumprod = np.log(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_log_variance_clipped = np.log(np.append(self.posterior_variance[1], self.posterior_variance[1:]))
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        if not hasattr(self, "timestep_map"):
+            self.timestep_map = list(range(self.num_timesteps))
+
+    # ------------------------------------------------------------------ per-step scalar coefficients
+    def step_coefficients(self, kind, guided=False, cond_grad_weight=1.0, ddim_guided=False):
+        """[num_timesteps, 8] fp32 rows for `ehb_set_schedule`.  Every scalar is produced by the same fp32 torch ops the
+        reference applies to its [bs,144]-expanded coefficient tensors, so the device update is bit-compatible."""
+        f = lambda a: th.from_numpy(np.asarray(a)).float()
+        T = self.num_timesteps
+        c = th.zeros(T, 8)
+        if kind == self.DDIM:
+            ab, abp = f(self.alphas_cumprod), f(self.alphas_cumprod_prev)
+            sigma = 0.0 * th.sqrt((1 - abp) / (1 - ab)) * th.sqrt(1 - ab / abp)  # eta = 0  (:541-545)
+            c[:, 0] = f(self.sqrt_recip_alphas_cumprod)
+            c[:, 1] = f(self.sqrt_recipm1_alphas_cumprod)
+            c[:, 2] = th.sqrt(abp)
+            c[:, 3] = th.sqrt(1 - abp - sigma ** 2)
+        else:
+            t = th.arange(T)
+            c[:, 0] = f(self.posterior_mean_coef1)
+            c[:, 1] = f(self.posterior_mean_coef2)
+            c[:, 2] = (t != 0).float() * th.exp(0.5 * f(self.posterior_log_variance_clipped))  # :333-336
+            if guided:  # :378-385, thresholds are on the respaced index
+                var = f(self.posterior_variance)
+                g = th.zeros(T)
+                g[t <= 10] = cond_grad_weight * 0.01
+                mid = (t <= 10) & (t >= 5)
+                g[mid] = (cond_grad_weight * var)[mid]
+                c[:, 3] = g
+        return c.numpy()
+
+    # ------------------------------------------------------------------ forward process (used for init_data)
+    def q_sample(self, x_start, t, noise=None):
+        """gaussian_diffusion.py:188-207."""
+        if noise is None:
+            noise = th.randn_like(x_start)
+        assert noise.shape == x_start.shape
+        return (_extract_into_tensor(self.sqrt_alphas_cumprod, t, x_start.shape) * x_start
+                + _extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
+
+    def _scale_timesteps(self, t):
+        return t.float() * (1000.0 / self.num_timesteps) if self.rescale_timesteps else t
+
+    def _map_timesteps(self, t):
+        return t
+
+    # ------------------------------------------------------------------ model evaluation
+    @staticmethod
+    def _is_fused(model):
+        return hasattr(model, "engine") and hasattr(model, "prepare") and hasattr(model, "assemble_outputs")
+
+    def p_mean_variance(self, model, batch, x, t, clip_denoised=True, denoised_fn=None):
+        """gaussian_diffusion.py:233-276 (generic path: any model honouring the `model(batch, t)` protocol)."""
+        B = x.shape[0]
+        assert t.shape == (B,)
+        batch["x_t"] = x
+        output_dict = model(batch, self._map_timesteps(self._scale_timesteps(t)))
+        pred_xstart = output_dict["pred_x_start"]
+        var = _extract_into_tensor(self.posterior_variance, t, x.shape)
+        logvar = _extract_into_tensor(self.posterior_log_variance_clipped, t, x.shape)
+        mean = (_extract_into_tensor(self.posterior_mean_coef1, t, x.shape) * pred_xstart
+                + _extract_into_tensor(self.posterior_mean_coef2, t, x.shape) * x)
+        return {"mean": mean, "variance": var, "log_variance": logvar, "pred_xstart": pred_xstart,
+                "other_outputs": output_dict}
+
+    def _generic_step(self, kind, model, batch, x, t, guided, cond_grad_weight):
+        """One reverse step for a foreign model: model call + CUDA sampler update."""
+        if not x.is_cuda:
+            raise RuntimeError("egohmr_b200 samplers run on CUDA tensors only (no CPU fallback)")
+        i = int(t[0])
+        out = self.p_mean_variance(model, batch, x, t)
+        noise = th.randn_like(x)
+        grad = None
+        if guided and kind == self.DDPM and i <= 10:
+            grad = model.guide_coll(batch, out["other_outputs"], t, compute_grad="x_t").float().contiguous()
+        eng = _generic_engine(x.device)
+        eng.set_schedule(kind, self.step_coefficients(kind, guided, cond_grad_weight))
+        x_prev = th.empty_like(x, dtype=th.float32)
+        eng.sampler_update(i, x.float().contiguous(), out["pred_xstart"].float().contiguous(),
+                           noise.float().contiguous() if kind == self.DDPM else None, grad, x_prev)
+        return {"sample": x_prev, "pred_xstart": out["pred_xstart"], "other_outputs": out["other_outputs"]}
+
+    def p_sample(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, cond_grad_weight=0.0):
+        """gaussian_diffusion.py:298-337."""
+        return self._generic_step(self.DDPM, model, batch, x, t, False, cond_grad_weight)
+
+    def p_sample_with_grad(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, cond_grad_weight=1.0):
+        """gaussian_diffusion.py:340-388."""
+        return self._generic_step(self.DDPM, model, batch, x, t, True, cond_grad_weight)
+
+    def ddim_sample(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, eta=0.0):
+        """gaussian_diffusion.py:511-556 (eta = 0, the only value the reference passes, :770)."""
+        if eta != 0.0:
+            raise NotImplementedError("eta != 0 is never used by the reference (val_losses passes eta=0.0)")
+        return self._generic_step(self.DDIM, model, batch, x, t, False, 0.0)
+
+    # ------------------------------------------------------------------ loops
+    def _loop(self, kind, model, batch, shape, noise, device, progress, skip_timesteps, init_data, cond_fn_with_grad,
+              cond_grad_weight):
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        data = noise if noise is not None else th.randn(*shape, device=device)
+        if skip_timesteps and init_data is None:
+            init_data = th.zeros_like(data)
+        indices = list(range(self.num_timesteps - skip_timesteps))[::-1]
+        if init_data is not None:
+            my_t = th.ones([shape[0]], device=device, dtype=th.long) * indices[0]
+            data = self.q_sample(init_data, my_t, data)
+        if progress:
+            from tqdm.auto import tqdm
+            indices = tqdm(indices)
+        guided = bool(cond_fn_with_grad)
+        if kind == self.DDIM and guided:
+            raise NotImplementedError("ddim_sample_with_grad: the reference documents DDIM as incompatible with the "
+                                      "collision guidance (README.md:145-148)")
+        if not self._is_fused(model):
+            for i in indices:
+                t = th.tensor([i] * shape[0], device=device)
+                with th.no_grad():
+                    out = self._generic_step(kind, model, batch, data, t, guided, cond_grad_weight)
+                    yield out
+                    data = out["sample"]
+            return
+        # ---- fused path
+        with th.no_grad():
+            eng = model.engine
+            cond = model.prepare(batch, num_samples=getattr(self, "_num_samples", 1))
+            model.set_timesteps(self.timestep_map)
+            eng.set_schedule(kind, self.step_coefficients(kind, guided, cond_grad_weight))
+            x = data.float().contiguous()
+            assert x.shape[0] == eng.n_bodies, (x.shape, eng.n_bodies)
+            x_next, x0 = th.empty_like(x), th.empty_like(x)
+            batch["vis_mask_smpl"] = cond["vis"]
+            last = indices[-1] if not progress else 0
+            for i in indices:
+                batch["x_t"] = x  # p_mean_variance mutates the caller's dict (:256)
+                step_noise = th.randn_like(x)  # drawn on every step, like the reference (:331, :547): same RNG stream
+                grad = None
+                if guided and i <= 10:
+                    t = th.full((x.shape[0],), i, device=device, dtype=th.long)
+                    grad = model.guide_coll(batch, {"pred_smpl_params": {"betas": cond["betas_img"][cond["img_of_body"]]}},
+                                            t, compute_grad="x_t").float().contiguous()
+                eng.denoise_step(i, x, step_noise if kind == self.DDPM else None, grad, x_next, x0)
+                is_last = i == last
+                other = model.assemble_outputs(batch, x0, cond) if is_last else {"pred_x_start": x0}
+                yield {"sample": x_next, "pred_xstart": x0, "other_outputs": other}
+                if not is_last:
+                    x, x_next = x_next, th.empty_like(x)
+                    x0 = th.empty_like(x)
+
+    def p_sample_loop_progressive(self, model, batch, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                  device=None, progress=False, skip_timesteps=0, init_data=None,
+                                  cond_fn_with_grad=False, cond_grad_weight=1.0):
+        """gaussian_diffusion.py:449-508."""
+        yield from self._loop(self.DDPM, model, batch, shape, noise, device, progress, skip_timesteps, init_data,
+                              cond_fn_with_grad, cond_grad_weight)
+
+    def p_sample_loop(self, model, batch, shape, noise=None, clip_denoised=True, denoised_fn=None, device=None,
+                      progress=False, skip_timesteps=0, init_data=None, cond_fn_with_grad=False, cond_grad_weight=1.0,
+                      dump_steps=None):
+        """gaussian_diffusion.py:391-446."""
+        final, dump = None, []
+        for i, sample in enumerate(self.p_sample_loop_progressive(
+                model, batch, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, device=device,
+                progress=progress, skip_timesteps=skip_timesteps, init_data=init_data,
+                cond_fn_with_grad=cond_fn_with_grad, cond_grad_weight=cond_grad_weight)):
+            if dump_steps is not None and i in dump_steps:
+                dump.append(sample["sample"].clone())
+            final = sample
+        return dump if dump_steps is not None else final
+
+    def ddim_sample_loop_progressive(self, model, batch, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                     device=None, progress=False, eta=0.0, skip_timesteps=0, init_data=None,
+                                     cond_fn_with_grad=False):
+        """gaussian_diffusion.py:670-718."""
+        if eta != 0.0:
+            raise NotImplementedError("eta != 0 is never used by the reference (val_losses passes eta=0.0)")
+        yield from self._loop(self.DDIM, model, batch, shape, noise, device, progress, skip_timesteps, init_data,
+                              cond_fn_with_grad, 1.0)
+
+    def ddim_sample_loop(self, model, batch, shape, noise=None, clip_denoised=True, denoised_fn=None, device=None,
+                         progress=False, eta=0.0, skip_timesteps=0, init_data=None, cond_fn_with_grad=False):
+        """gaussian_diffusion.py:618-667."""
+        final = None
+        for sample in self.ddim_sample_loop_progressive(
+                model, batch, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, device=device,
+                progress=progress, eta=eta, skip_timesteps=skip_timesteps, init_data=init_data,
+                cond_fn_with_grad=cond_fn_with_grad):
+            final = sample
+        return final
+
+    def val_losses(self, model, batch, shape, clip_denoised=True, progress=False, cond_fn_with_grad=False,
+                   cond_grad_weight=1.0, cur_epoch=0, timestep_respacing="", compute_loss=True):
+        """gaussian_diffusion.py:749-780."""
+        model.validation_setup()
+        if timestep_respacing == "":
+            val_output = self.p_sample_loop(model=model, batch=batch, shape=shape, progress=progress,
+                                            clip_denoised=clip_denoised, cond_fn_with_grad=cond_fn_with_grad,
+                                            cond_grad_weight=cond_grad_weight)
+        elif timestep_respacing[0:4] == "ddim":
+            val_output = self.ddim_sample_loop(model=model, batch=batch, shape=shape, progress=progress,
+                                               clip_denoised=clip_denoised, eta=0.0,
+                                               cond_fn_with_grad=cond_fn_with_grad)
+        else:
+            print("timestep_respacing_eval not setup correctly")
+            raise SystemExit()
+        if compute_loss:
+            model.compute_loss(batch, val_output["other_outputs"], cur_epoch=cur_epoch)
+        return val_output["other_outputs"]
+
+    # ------------------------------------------------------------------ batched multi-sample entry (new)
+    def sample_many(self, model, batch, num_samples, timestep_respacing="", noise=None, cond_fn_with_grad=False,
+                    cond_grad_weight=1.0):
+        """All `num_samples` chains of every image as ONE batch of bs*num_samples bodies (body = img*S + n), instead of
+        the reference driver's sequential loop (test_egohmr.py:251-255).  Returns the final output dict with a leading
+        [bs*num_samples] axis.  `noise`: optional [n_steps+1, bs*S, 144] pre-drawn noise (index 0 = initial x_T)."""
+        model.validation_setup()
+        bs = batch["img"].shape[0]
+        shape = [bs * num_samples, 144]
+        kind = self.DDPM if timestep_respacing == "" else self.DDIM
+        self._num_samples = num_samples
+        try:
+            if noise is not None:
+                feed = _NoiseFeed(noise)
+                old = th.randn_like
+                th.randn_like = feed.randn_like
+                try:
+                    final = None
+                    for final in self._loop(kind, model, batch, shape, feed.initial(), None, False, 0, None,
+                                            cond_fn_with_grad, cond_grad_weight):
+                        pass
+                finally:
+                    th.randn_like = old
+            else:
+                final = None
+                for final in self._loop(kind, model, batch, shape, None, None, False, 0, None, cond_fn_with_grad,
+                                        cond_grad_weight):
+                    pass
+        finally:
+            self._num_samples = 1
+        out = final["other_outputs"]
+        out["sample"] = final["sample"]
+        return out
+
+
+class _NoiseFeed:
+    """Feeds pre-drawn noise to the loop in the reference's draw order (tests / reproducible multi-GPU sharding)."""
+
+    def __init__(self, noise):
+        self.noise = noise
+        self.i = 1
+
+    def initial(self):
+        return self.noise[0]
+
+    def randn_like(self, x, **kw):
+        n = self.noise[self.i]
+        self.i += 1
+        return n

@@ -1,0 +1,195 @@
+"""Thin Python handle on one ``ehb_ctx`` (one per process / GPU).  PyTorch is only the owner of device memory and of
+the CUDA stream here; all arithmetic of the hot path happens inside libegohmr_b200.so."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, f32, fptr
+
+
+def _dev_ptr(t, dtype=torch.float32, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("tensor required")
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f"expected a contiguous CUDA {dtype} tensor, got "
+                         f"{type(t).__name__} {getattr(t, 'dtype', None)} cuda={getattr(t, 'is_cuda', None)}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.EhbError("egohmr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = C.c_void_p()
+        check(self.lib.ehb_ctx_create(self.device.index, C.byref(h)))
+        self._h = h
+        self.n_bodies = 0
+        self.n_img = 0
+        self.n_verts = 0
+        self.n_extra = 0
+        self.n_betas = 0
+        self.hid = 0
+        self.smpl_loaded = False
+        self.gcn_loaded = False
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ehb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ loading
+    def load_gcn(self, sd, adj, hid, n_blocks, diffuse_fuse=True, img_dim=2048, cond_dim=2694, xfeat_dim=512,
+                 temb_dim=512, prefix="diffusion_model", bn_eps=1e-5):
+        """`sd`: mapping reference-state_dict-name -> array (numpy or torch), see include/egohmr_b200.h::ehb_gconv."""
+        keep = []
+
+        def arr(name):
+            v = sd[name]
+            if isinstance(v, torch.Tensor):
+                v = v.detach().cpu().numpy()
+            a = f32(v)
+            keep.append(a)
+            return a
+
+        def gconv(gname, bnname, in_dim, out_dim):
+            g = _lib.GConv()
+            g.in_dim, g.out_dim = in_dim, out_dim
+            W = arr(gname + ".W")
+            assert W.shape == (2, in_dim, out_dim), (gname, W.shape)
+            g.W, g.M, g.adj2, g.bias = fptr(W), fptr(arr(gname + ".M")), fptr(arr(gname + ".adj2")), fptr(arr(gname + ".bias"))
+            if bnname is not None:
+                g.bn_weight, g.bn_bias = fptr(arr(bnname + ".weight")), fptr(arr(bnname + ".bias"))
+                g.bn_mean, g.bn_var = fptr(arr(bnname + ".running_mean")), fptr(arr(bnname + ".running_var"))
+            g.bn_eps = bn_eps
+            return g
+
+        in_dim = cond_dim + xfeat_dim + temb_dim
+        layers = [gconv(f"{prefix}.gconv_input.0.gconv", f"{prefix}.gconv_input.0.bn", in_dim, hid)]
+        for b in range(n_blocks):
+            for k in (1, 2):
+                layers.append(gconv(f"{prefix}.gconv_layers.{b}.gconv{k}.gconv", f"{prefix}.gconv_layers.{b}.gconv{k}.bn",
+                                    hid, hid))
+        layers.append(gconv(f"{prefix}.gconv_output", None, hid, 6))
+        arr_t = (_lib.GConv * len(layers))(*layers)
+        w = _lib.GcnWeights()
+        w.hid, w.n_blocks, w.img_dim, w.cond_dim, w.xfeat_dim, w.temb_dim = hid, n_blocks, img_dim, cond_dim, xfeat_dim, temb_dim
+        w.diffuse_fuse = 1 if diffuse_fuse else 0
+        adj_a = f32(adj.detach().cpu().numpy() if isinstance(adj, torch.Tensor) else adj)
+        w.adj = fptr(adj_a)
+        w.inproc_w, w.inproc_b = fptr(arr("input_process.poseEmbedding.weight")), fptr(arr("input_process.poseEmbedding.bias"))
+        w.layers, w.n_layers = arr_t, len(layers)
+        check(self.lib.ehb_gcn_load(self._h, C.byref(w)))
+        self.hid, self.gcn_loaded, self.n_bodies = hid, True, 0
+
+    def load_smpl(self, model):
+        a = {k: f32(model[k]) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")}
+        parents = np.ascontiguousarray(model["parents"], dtype=np.int32)
+        extra = np.ascontiguousarray(model["extra_vertex_ids"], dtype=np.int32)
+        m = _lib.SmplModel()
+        m.n_verts, m.n_betas, m.n_extra = a["v_template"].shape[0], a["shapedirs"].shape[-1], extra.shape[0]
+        assert a["shapedirs"].shape == (m.n_verts, 3, m.n_betas) and a["posedirs"].shape == (207, m.n_verts * 3)
+        m.v_template, m.shapedirs, m.posedirs = fptr(a["v_template"]), fptr(a["shapedirs"]), fptr(a["posedirs"])
+        m.J_regressor, m.lbs_weights = fptr(a["J_regressor"]), fptr(a["lbs_weights"])
+        m.parents = parents.ctypes.data_as(_lib.c_int32_p)
+        m.extra_vertex_ids = extra.ctypes.data_as(_lib.c_int32_p)
+        check(self.lib.ehb_smpl_load(self._h, C.byref(m)))
+        self.n_verts, self.n_extra, self.n_betas, self.smpl_loaded = m.n_verts, m.n_extra, m.n_betas, True
+
+    def set_norm(self, mean, std):
+        m, s = f32(mean).reshape(144), f32(std).reshape(144)
+        check(self.lib.ehb_set_norm(self._h, fptr(m), fptr(s)))
+
+    def set_schedule(self, kind, coef):
+        coef = f32(coef).reshape(-1, 8)
+        check(self.lib.ehb_set_schedule(self._h, int(kind), coef.shape[0], fptr(coef)))
+
+    # ------------------------------------------------------------------ per batch
+    def set_cond(self, img_feat, rest_feat, vis):
+        n = img_feat.shape[0]
+        check(self.lib.ehb_set_cond(self._h, n, _dev_ptr(img_feat), _dev_ptr(rest_feat), _dev_ptr(vis, torch.uint8),
+                                    _stream()))
+        self.n_img = n
+
+    def set_temb(self, temb):
+        check(self.lib.ehb_set_temb(self._h, temb.shape[0], _dev_ptr(temb), _stream()))
+
+    def set_bodies(self, img_of_body):
+        iob = np.ascontiguousarray(img_of_body, dtype=np.int32)
+        check(self.lib.ehb_set_bodies(self._h, iob.shape[0], iob.ctypes.data_as(_lib.c_int32_p)))
+        self.n_bodies = iob.shape[0]
+
+    # ------------------------------------------------------------------ hot calls
+    def denoise_step(self, step, x_t, noise, grad, x_prev, x0, out_cond=None, out_uncond=None):
+        if out_cond is None and out_uncond is None:
+            check(self.lib.ehb_denoise_step(self._h, int(step), _dev_ptr(x_t), _dev_ptr(noise, allow_none=True),
+                                            _dev_ptr(grad, allow_none=True), _dev_ptr(x_prev), _dev_ptr(x0), _stream()))
+        else:
+            check(self.lib.ehb_denoise_step_debug(self._h, int(step), _dev_ptr(x_t), _dev_ptr(noise, allow_none=True),
+                                                  _dev_ptr(grad, allow_none=True), _dev_ptr(x_prev), _dev_ptr(x0),
+                                                  _dev_ptr(out_cond, allow_none=True),
+                                                  _dev_ptr(out_uncond, allow_none=True), _stream()))
+
+    def sampler_update(self, step, x_t, x0, noise, grad, x_prev):
+        check(self.lib.ehb_sampler_update(self._h, int(step), x_t.shape[0], _dev_ptr(x_t), _dev_ptr(x0),
+                                          _dev_ptr(noise, allow_none=True), _dev_ptr(grad, allow_none=True),
+                                          _dev_ptr(x_prev), _stream()))
+
+    def decode(self, x0, betas, want_smpl=True):
+        """x0 [B,144] (normalised) -> pose6d [B,144], R [B,24,3,3], verts [B,V,3] | None, joints [B,24+E,3] | None."""
+        B = x0.shape[0]
+        assert B == self.n_bodies
+        pose6d = torch.empty(B, 144, device=x0.device, dtype=torch.float32)
+        R = torch.empty(B, 24, 3, 3, device=x0.device, dtype=torch.float32)
+        verts = joints = None
+        if want_smpl:
+            verts = torch.empty(B, self.n_verts, 3, device=x0.device, dtype=torch.float32)
+            joints = torch.empty(B, 24 + self.n_extra, 3, device=x0.device, dtype=torch.float32)
+        check(self.lib.ehb_decode(self._h, _dev_ptr(x0), _dev_ptr(betas, allow_none=not want_smpl), _dev_ptr(pose6d),
+                                  _dev_ptr(R), _dev_ptr(verts, allow_none=True), _dev_ptr(joints, allow_none=True),
+                                  _stream()))
+        return pose6d, R, verts, joints
+
+    def smpl_forward(self, R, betas, transl=None):
+        n = R.shape[0]
+        verts = torch.empty(n, self.n_verts, 3, device=R.device, dtype=torch.float32)
+        joints = torch.empty(n, 24 + self.n_extra, 3, device=R.device, dtype=torch.float32)
+        check(self.lib.ehb_smpl_forward(self._h, n, _dev_ptr(R), _dev_ptr(betas), _dev_ptr(transl, allow_none=True),
+                                        _dev_ptr(verts), _dev_ptr(joints), _stream()))
+        return verts, joints
+
+    def rot6d_to_rotmat(self, x6):
+        n = x6.numel() // 6
+        R = torch.empty(n, 3, 3, device=x6.device, dtype=torch.float32)
+        check(self.lib.ehb_rot6d_to_rotmat(self._h, _dev_ptr(x6), n, _dev_ptr(R), _stream()))
+        return R
+
+    # ------------------------------------------------------------------ diagnostics
+    def launch_count(self):
+        return int(self.lib.ehb_launch_count(self._h))
+
+    def set_gemm_mode(self, mode):
+        check(self.lib.ehb_debug_set_gemm_mode(self._h, int(mode)))
+
+    def check_overflow(self):
+        return bool(self.lib.ehb_check_overflow(self._h, _stream()))
+
+    def time_hidden_layer(self, layer, iters):
+        ms = C.c_float()
+        check(self.lib.ehb_time_hidden_layer(self._h, int(layer), int(iters), C.byref(ms), _stream()))
+        return float(ms.value)

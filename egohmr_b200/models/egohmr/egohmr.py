@@ -1,0 +1,329 @@
+"""`EgoHMR` with the reference's constructor / forward / state_dict interface (models/egohmr/egohmr.py:29-303),
+re-architected for the sampling hot path:
+
+* the step-invariant part of `forward` (image / scene / translation / camera encoders, visibility, beta head,
+  egohmr.py:181-223,262-265) runs once per batch in PyTorch and is cached (`prepare`);
+* everything that depends on x_t / t — the 10-layer Modulated GCN evaluated twice (image-conditioned and image-masked,
+  :236-246), the fuse-select (:248-254), de-normalisation + rot6d (:258-260), SMPL (:276) — runs in
+  libegohmr_b200.so through `self.engine`.
+
+Parameters keep the reference's names, so `load_state_dict(torch.load(ckpt)['state_dict'], strict=False)`
+(test_egohmr.py:125-126) ingests a reference checkpoint unchanged.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ... import smpl as smpl_mod
+from ... import synth
+from ...engine import Engine
+from ...utils.geometry import perspective_projection
+from ..resnet import ResNet50Features
+from ..respointnet import ResnetPointnet
+
+OPENPOSE_TO_SMPL = [8, 12, 9, 8, 13, 10, 8, 14, 11, 8, 14, 11, 0, 5, 2, 0, 5, 2, 6, 3, 7, 4, 7, 4]          # :111
+OPENPOSE_TO_SMPL_LOOSEN = [8, 13, 10, 8, 13, 10, 8, 14, 11, 8, 14, 11, 1, 5, 2, 0, 5, 2, 6, 3, 7, 4, 7, 4]   # :114
+
+
+class _GConvParams(nn.Module):
+    """Parameter container for one ModulatedGraphConv (modulated_gcn_conv.py:16-36); the math lives in the kernels."""
+
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.W = nn.Parameter(torch.empty(2, in_dim, out_dim))
+        self.M = nn.Parameter(torch.empty(24, out_dim))
+        self.adj2 = nn.Parameter(torch.full((24, 24), 1e-6))
+        self.bias = nn.Parameter(torch.empty(out_dim))
+        nn.init.xavier_uniform_(self.W.data, gain=1.414)
+        nn.init.xavier_uniform_(self.M.data, gain=1.414)
+        stdv = 1.0 / np.sqrt(out_dim)
+        self.bias.data.uniform_(-stdv, stdv)
+
+
+class _GraphConvParams(nn.Module):
+    def __init__(self, in_dim, out_dim):
+        super().__init__()
+        self.gconv = _GConvParams(in_dim, out_dim)
+        self.bn = nn.BatchNorm1d(out_dim)
+
+
+class _ResGraphConvParams(nn.Module):
+    def __init__(self, hid):
+        super().__init__()
+        self.gconv1 = _GraphConvParams(hid, hid)
+        self.gconv2 = _GraphConvParams(hid, hid)
+
+
+class ModulatedGCNParams(nn.Module):
+    """state_dict-compatible skeleton of ModulatedGCN (modulated_gcn.py:61-94)."""
+
+    def __init__(self, in_dim, hid_dim, out_dim, num_layers):
+        super().__init__()
+        self.gconv_input = nn.Sequential(_GraphConvParams(in_dim, hid_dim))
+        self.gconv_layers = nn.Sequential(*[_ResGraphConvParams(hid_dim) for _ in range(num_layers)])
+        self.gconv_output = _GConvParams(hid_dim, out_dim)
+
+
+class PositionalEncoding(nn.Module):
+    def __init__(self, d_model, max_len=5000):
+        super().__init__()
+        self.register_buffer("pe", torch.from_numpy(synth.positional_encoding_table(d_model, max_len)))
+
+
+class TimestepEmbedder(nn.Module):
+    def __init__(self, latent_dim, sequence_pos_encoder):
+        super().__init__()
+        self.sequence_pos_encoder = sequence_pos_encoder
+        self.time_embed = nn.Sequential(nn.Linear(latent_dim, latent_dim), nn.SiLU(), nn.Linear(latent_dim, latent_dim))
+
+    def forward(self, timesteps):
+        return self.time_embed(self.sequence_pos_encoder.pe[timesteps]).permute(1, 0, 2)
+
+
+class InputProcess(nn.Module):
+    def __init__(self, input_dim, latent_dim):
+        super().__init__()
+        self.poseEmbedding = nn.Linear(input_dim, latent_dim)
+
+
+class FCHeadBeta(nn.Module):
+    def __init__(self, in_dim, init_betas=None):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Linear(in_dim, 1024), nn.ReLU(inplace=False), nn.Linear(1024, 10))
+        nn.init.xavier_uniform_(self.layers[2].weight, gain=0.02)
+        if init_betas is None:
+            try:  # egohmr.py:669 reads the mean shape from CWD
+                init_betas = np.load("data/smpl_mean_params.npz")["shape"].astype(np.float32)
+            except (FileNotFoundError, OSError):
+                init_betas = np.zeros(10, np.float32)
+        self.register_buffer("init_betas", torch.from_numpy(np.asarray(init_betas, np.float32).reshape(1, 10)))
+
+    def forward(self, feats, pred_pose=None):
+        return self.layers(feats) + self.init_betas
+
+
+class TranslEnc(nn.Module):
+    def __init__(self, in_dim=3, out_dim=128):
+        super().__init__()
+        self.layers = nn.Sequential(nn.Linear(in_dim, 64), nn.ReLU(inplace=False), nn.Linear(64, out_dim))
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+class EgoHMR(nn.Module):
+    def __init__(self, cfg, device=None, body_rep_mean=None, body_rep_std=None,
+                 with_focal_length=False, with_bbox_info=False, with_cam_center=False,
+                 scene_feat_dim=512, scene_type="whole_scene", scene_cano=False,
+                 weight_loss_v2v=0, weight_loss_keypoints_3d=0, weight_loss_keypoints_3d_full=0,
+                 weight_loss_keypoints_2d_full=0, weight_loss_betas=0, weight_loss_body_pose=0,
+                 weight_loss_global_orient=0, weight_loss_pose_6d_ortho=0, weight_coap_penetration=0,
+                 start_coap_epoch=0, cond_mask_prob=0, only_mask_img_cond=False, diffusion_blk=4, gcn_dropout=0.0,
+                 gcn_nonlocal_layer=False, gcn_hid_dim=1024, pelvis_vis_loosen=False, diffuse_fuse=False,
+                 smpl_model=None, collision_model=None):
+        super().__init__()
+        if gcn_nonlocal_layer:
+            raise NotImplementedError("gcn_nonlocal_layer=True is never enabled by the reference's drivers "
+                                      "(egohmr.py:37, test_egohmr.py:112-118) and is not on the accelerated path")
+        if diffuse_fuse and not only_mask_img_cond:
+            raise NotImplementedError("diffuse_fuse with only_mask_img_cond=False (mask every condition) is not "
+                                      "implemented; the reference's test default is only_mask_img_cond=True")
+        self.cfg = cfg
+        self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
+        self.with_focal_length, self.with_bbox_info, self.with_cam_center = with_focal_length, with_bbox_info, with_cam_center
+        self.body_rep_mean, self.body_rep_std = body_rep_mean, body_rep_std
+        self.diffuse_feat_dim = 6
+        self.cond_mask_prob, self.only_mask_img_cond, self.diffuse_fuse = cond_mask_prob, only_mask_img_cond, diffuse_fuse
+        self.scene_type, self.scene_cano = scene_type, scene_cano
+        self.hid, self.n_blocks = gcn_hid_dim, diffusion_blk
+
+        self.input_process_out_dim = 512
+        self.input_process = InputProcess(6, 512)
+        self.timestep_embed_dim = 512
+        self.sequence_pos_encoder = PositionalEncoding(512)
+        self.embed_timestep = TimestepEmbedder(512, self.sequence_pos_encoder)
+        self.backbone = ResNet50Features()
+        self.scene_enc = ResnetPointnet(out_dim=scene_feat_dim, hidden_dim=256)
+        self.transl_enc = TranslEnc(3, 128)
+        self.img_dim = cfg.MODEL.BACKBONE.OUT_CHANNELS
+        ctx_dim = self.img_dim + (1 if with_focal_length else 0) + (3 if with_bbox_info else 0) + \
+            (2 if with_cam_center else 0) + scene_feat_dim + 128  # egohmr.py:76-83
+        self.cond_dim = ctx_dim
+        self.register_buffer("adj", torch.from_numpy(synth.skeleton_adjacency()), persistent=False)  # :86-94
+        self.diffusion_model = ModulatedGCNParams(ctx_dim + 512 + 512, gcn_hid_dim, 6, diffusion_blk)
+        init_betas = None if smpl_model is None else smpl_model.get("init_betas")
+        self.beta_layer = FCHeadBeta(ctx_dim, init_betas)
+
+        self.engine = Engine(self.device.index or 0)
+        self.smpl = smpl_mod.create("data/smpl", model_type="smpl", gender="neutral", smpl_model=smpl_model,
+                                    engine=self.engine)  # :105
+        self.smpl_male = self.smpl if smpl_model is not None else smpl_mod.create("data/smpl", gender="male")
+        self.smpl_female = self.smpl if smpl_model is not None else smpl_mod.create("data/smpl", gender="female")
+        self.openpose_to_smpl = OPENPOSE_TO_SMPL_LOOSEN if pelvis_vis_loosen else OPENPOSE_TO_SMPL
+        # collision guidance is a pluggable callable with COAP's signature: `attach_coap` upstream
+        self.collision_model = collision_model
+        self.weight_coap_penetration, self.start_coap_epoch = weight_coap_penetration, start_coap_epoch
+        self.to(self.device)
+        self._weights_dirty = True
+        self._cond_key = None
+        self._cond = None
+        self._temb_key = None
+
+    # ------------------------------------------------------------------ weight ingestion
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        own = self.state_dict()
+        filtered = {k: v for k, v in state_dict.items() if k in own}  # smpl.* / coap.* buffers live elsewhere here
+        res = super().load_state_dict(filtered, strict=False, **kw)
+        self._weights_dirty = True
+        self._cond_key = None
+        if strict:
+            missing = [k for k in own if k not in state_dict]
+            if missing:
+                raise RuntimeError(f"missing keys in state_dict: {missing[:5]}...")
+        return res
+
+    def _sync_engine(self):
+        if not self._weights_dirty:
+            return
+        sd = {k: v for k, v in self.state_dict().items()
+              if k.startswith("diffusion_model.") or k.startswith("input_process.")}
+        bn_eps = self.diffusion_model.gconv_input[0].bn.eps
+        self.engine.load_gcn(sd, self.adj, self.hid, self.n_blocks, self.diffuse_fuse, self.img_dim, self.cond_dim,
+                             512, 512, bn_eps=bn_eps)
+        if not self.engine.smpl_loaded:
+            self.engine.load_smpl(self.smpl.model)
+        mean = self.body_rep_mean if self.body_rep_mean is not None else torch.zeros(144)
+        std = self.body_rep_std if self.body_rep_std is not None else torch.ones(144)
+        self.engine.set_norm(torch.as_tensor(mean).detach().float().cpu().numpy(),
+                             torch.as_tensor(std).detach().float().cpu().numpy())
+        self._weights_dirty = False
+        self._cond_key = None
+        self._temb_key = None
+
+    def validation_setup(self):  # egohmr.py:475-484
+        self.training = False
+        self.eval()
+
+    # ------------------------------------------------------------------ step-invariant conditioning
+    @staticmethod
+    def _tkey(t):
+        return (t.data_ptr(), tuple(t.shape), t._version)
+
+    def _cam_feats(self, batch):  # egohmr.py:195-205
+        feats = []
+        if self.with_focal_length:
+            feats = [batch["fx"].unsqueeze(1)] + feats
+        if self.with_bbox_info:
+            orig_fx = batch["fx"] * self.cfg.CAM.FX_NORM_COEFF
+            feats = [torch.stack([batch["box_center"][:, 0] / orig_fx, batch["box_center"][:, 1] / orig_fx,
+                                  batch["box_size"] / orig_fx], dim=-1)] + feats
+        if self.with_cam_center:
+            orig_fx = batch["fx"] * self.cfg.CAM.FX_NORM_COEFF
+            feats = [torch.stack([batch["cam_cx"] / orig_fx, batch["cam_cy"] / orig_fx], dim=-1)] + feats
+        return feats
+
+    @torch.no_grad()
+    def prepare(self, batch, num_samples=1, features=None):
+        """Compute (or reuse) everything in `forward` that does not depend on x_t / t and hand it to the engine.
+        `features`: optional dict(img_feats, scene_feats, transl_feat) to bypass the encoders (tests)."""
+        self._sync_engine()
+        transl = batch["smpl_params"]["transl"]
+        key = (self._tkey(batch["img"]), self._tkey(batch["scene_pcd_verts_full"]), self._tkey(transl),
+               self._tkey(batch["orig_keypoints_2d"]), self._tkey(batch["fx"]), num_samples, id(features))
+        if key == self._cond_key:
+            return self._cond
+        was_training = self.training
+        self.eval()
+        bs = batch["img"].shape[0]
+        vis_op = batch["orig_keypoints_2d"][:, :, -1] > 0  # egohmr.py:186-189
+        vis_op[:, 8] = True
+        vis = vis_op[:, self.openpose_to_smpl]
+        pts = batch["scene_pcd_verts_full"] - transl.unsqueeze(1) if self.scene_cano else batch["scene_pcd_verts_full"]
+        if features is None:
+            img_feats = self.backbone(batch["img"])
+            scene_feats = self.scene_enc(pts)
+            transl_feat = self.transl_enc(transl)
+        else:
+            img_feats, scene_feats, transl_feat = features["img_feats"], features["scene_feats"], features["transl_feat"]
+        rest = torch.cat([scene_feats, transl_feat] + self._cam_feats(batch), dim=1).float().contiguous()
+        img_feats = img_feats.float().contiguous()
+        betas = self.beta_layer(torch.cat([img_feats, rest], dim=1))  # :263-265
+        self.engine.set_cond(img_feats, rest, vis.to(torch.uint8).contiguous())
+        iob = np.repeat(np.arange(bs, dtype=np.int32), num_samples)
+        self.engine.set_bodies(iob)
+        idx = torch.from_numpy(iob.astype(np.int64)).to(img_feats.device)
+        self._cond = {"vis": vis, "betas_img": betas.float().contiguous(), "scene_pts": pts, "transl": transl,
+                      "img_of_body": idx, "num_samples": num_samples, "bs": bs}
+        self.scene_pcd_verts = pts
+        self.input_transl = transl
+        self._cond_key = key
+        if was_training:
+            self.train()
+        return self._cond
+
+    @torch.no_grad()
+    def set_timesteps(self, t_orig_list):
+        """Upload embed_timestep(t) for the original timesteps the sampler will visit (row i <-> respaced step i)."""
+        self._sync_engine()
+        key = tuple(int(t) for t in t_orig_list)
+        if key == self._temb_key:
+            return
+        t = torch.tensor(key, device=self.device, dtype=torch.long)
+        temb = self.embed_timestep(t).squeeze(0) if len(key) > 1 else self.embed_timestep(t).reshape(1, -1)
+        self.engine.set_temb(temb.reshape(len(key), -1).float().contiguous())
+        self._temb_key = key
+
+    # ------------------------------------------------------------------ outputs
+    def assemble_outputs(self, batch, x0, cond=None):
+        """egohmr.py:256-303 for the final x0: de-normalise, rot6d, SMPL, global joints, 2-D projection."""
+        cond = cond or self._cond
+        idx = cond["img_of_body"]
+        pose6d, R, verts, joints = self.engine.decode(x0, cond["betas_img"], want_smpl=True)
+        betas = cond["betas_img"][idx]
+        transl = cond["transl"][idx]
+        out = {"pred_x_start": x0, "pred_pose_6d": pose6d,
+               "pred_smpl_params": {"global_orient": R[:, [0]].clone(), "body_pose": R[:, 1:].clone(), "betas": betas.clone()},
+               "pred_keypoints_3d": joints, "pred_vertices": verts}
+        if self.with_focal_length:
+            focal = (batch["fx"].unsqueeze(-1).repeat(1, 2) * self.cfg.CAM.FX_NORM_COEFF)[idx]
+            center = torch.stack([batch["cam_cx"], batch["cam_cy"]], dim=-1)[idx]
+        else:
+            focal = self.cfg.EXTRA.FOCAL_LENGTH * torch.ones(x0.shape[0], 2, device=x0.device)
+            center = torch.tensor([[960.0, 540.0]], device=x0.device).repeat(x0.shape[0], 1)
+        self.camera_center_full, self.focal_length = center, focal
+        out["pred_keypoints_3d_full"] = joints + transl.unsqueeze(1)
+        kp2d = perspective_projection(joints, transl, focal, center)
+        kp2d = torch.stack([kp2d[:, :, 0] / 1920 - 0.5, kp2d[:, :, 1] / 1080 - 0.5], dim=-1)
+        out["pred_keypoints_2d_full"] = kp2d
+        return out
+
+    @torch.no_grad()
+    def forward(self, batch, timesteps, eval_with_uncond=True):
+        """EgoHMR.forward(batch, timesteps) (egohmr.py:173-303).  `timesteps` are ORIGINAL diffusion timesteps and must
+        be uniform over the batch, as they always are while sampling (gaussian_diffusion.py:495)."""
+        if self.diffuse_fuse and not eval_with_uncond:
+            raise NotImplementedError("eval_with_uncond=False is the training-time path (egohmr.py:465)")
+        t0 = int(timesteps[0])
+        if not bool((timesteps == t0).all()):
+            raise NotImplementedError("non-uniform timesteps only occur in training (out of scope)")
+        cond = self.prepare(batch, num_samples=1)
+        self.set_timesteps([t0])
+        x_t = batch["x_t"].reshape(-1, 144).float().contiguous()
+        batch["vis_mask_smpl"] = cond["vis"]  # egohmr.py:189 mutates the caller's dict
+        x0 = torch.empty_like(x_t)
+        scratch = torch.empty_like(x_t)
+        self.engine.set_schedule(0, np.array([[1, 1, 1, 0, 0, 0, 0, 0]], np.float32))
+        self.engine.denoise_step(0, x_t, None, None, scratch, x0)
+        self._temb_key = None  # the sampler's table must be re-uploaded after a stand-alone forward
+        return self.assemble_outputs(batch, x0, cond)
+
+    # ------------------------------------------------------------------ collision hooks (boundary only)
+    def guide_coll(self, batch, output, t, compute_grad="x_t"):
+        raise NotImplementedError("collision-guided sampling: native LBS backward (K6) is scheduled after K1-K5")
+
+    def eval_coll(self, output):
+        raise NotImplementedError("eval_coll needs a collision model with COAP's query() (SURVEY.md 2 #10)")
+
+    def compute_loss(self, batch, output, cur_epoch=0):
+        raise NotImplementedError("validation losses need ground-truth keys and are outside the sampling hot path; "
+                                  "call val_losses(..., compute_loss=False)")

@@ -88,14 +88,16 @@ int ehb_set_norm(ehb_ctx* ctx, const float* mean, const float* std);
  * coef is HOST [n_steps][8] floats, row i = coefficients of respaced timestep i (see DESIGN.md "sampler update"). */
 int ehb_set_schedule(ehb_ctx* ctx, int kind, int n_steps, const float* coef);
 
-/* Step-invariant conditioning of EgoHMR.forward (egohmr.py:178-223) for n_img images:
+/* Step-invariant conditioning of EgoHMR.forward (egohmr.py:181-223) for n_img images:
  *   img_feat  [n_img][img_dim]            backbone output (:183)
  *   rest_feat [n_img][cond_dim-img_dim]   [scene_feats | transl_feat | cam_feats] (:214-221)
  *   vis       [n_img][24] uint8           vis_mask_smpl (:186-189)
- *   temb      [n_steps][temb_dim]         embed_timestep(timestep_map[i]) for every respaced step i (:178)
  * Folds them through the input ModulatedGraphConv's weight rows (one fp32 GEMM each). */
 int ehb_set_cond(ehb_ctx* ctx, int n_img, const float* img_feat, const float* rest_feat, const uint8_t* vis,
-                 int n_steps, const float* temb, void* stream);
+                 void* stream);
+/* Timestep embeddings (egohmr.py:178, TimestepEmbedder :642-643): temb [n_steps][temb_dim], row i =
+ * embed_timestep(timestep_map[i]) for respaced step i; folded through the input layer's temb rows. */
+int ehb_set_temb(ehb_ctx* ctx, int n_steps, const float* temb, void* stream);
 
 /* The chains to sample: body b is conditioned on image img_of_body[b] (HOST int32 [n_bodies]).
  * The reference runs `num_samples` sequential chains per image (test_egohmr.py:251-255); here they are one batch. */
@@ -112,6 +114,12 @@ int ehb_denoise_step(ehb_ctx* ctx, int step, const float* x_t, const float* nois
 /* Same, but also returns the raw image-conditioned / image-masked denoiser outputs (egohmr.py:237,246). Tests only. */
 int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
                            float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream);
+
+/* The sampler update alone (gaussian_diffusion.py:331-336 / :373-387 / :537-555) for a caller-supplied pred_xstart:
+ * the generic `p_sample(model, ...)` / `ddim_sample(model, ...)` entry points use it when `model` is not the fused
+ * denoiser.  All pointers [n][144]; noise / grad may be NULL. */
+int ehb_sampler_update(ehb_ctx* ctx, int step, int n, const float* x_t, const float* x0, const float* noise,
+                       const float* grad, float* x_prev, void* stream);
 
 /* utils/geometry.py:47-66 rot6d_to_rotmat(x, 'diffusion'): x6 [n][6] -> R [n][3][3]. */
 int ehb_rot6d_to_rotmat(ehb_ctx* ctx, const float* x6, int n, float* R, void* stream);

@@ -94,30 +94,49 @@ class Schedule:
         self.posterior_mean_coef2 = (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
 
 
-def _ex(arr, t, dtype):
-    """_extract_into_tensor (gaussian_diffusion.py:784-797): float64 table entry, cast with .float()."""
-    return np.asarray(arr[t], dtype=np.float64).astype(dtype)
+def _ex(arr, t):
+    """_extract_into_tensor (gaussian_diffusion.py:784-797): the float64 table entry cast with .float().  The
+    coefficient tensors are fp32 whatever dtype the sampler state has; torch promotes them only when they meet a
+    float64 tensor, so every coefficient-only expression below is evaluated in fp32 first."""
+    return np.float32(arr[t])
+
+
+def ddim_coefficients(sch, t):
+    """The four per-step scalars of ddim_sample with eta = 0 (gaussian_diffusion.py:537-551), fp32 like torch."""
+    one = np.float32(1.0)
+    alpha_bar = _ex(sch.alphas_cumprod, t)
+    alpha_bar_prev = _ex(sch.alphas_cumprod_prev, t)
+    sigma = np.float32(0.0) * np.sqrt((one - alpha_bar_prev) / (one - alpha_bar)) * np.sqrt(one - alpha_bar / alpha_bar_prev)
+    return (_ex(sch.sqrt_recip_alphas_cumprod, t), _ex(sch.sqrt_recipm1_alphas_cumprod, t), np.sqrt(alpha_bar_prev),
+            np.sqrt(one - alpha_bar_prev - sigma ** 2))
 
 
 def ddim_update(sch, x, x0, t, dtype=np.float32):
     """ddim_sample with eta = 0 (gaussian_diffusion.py:511-556) given pred_xstart = x0; t is the respaced index."""
-    one = dtype(1.0)
-    eps = (_ex(sch.sqrt_recip_alphas_cumprod, t, dtype) * x - x0) / _ex(sch.sqrt_recipm1_alphas_cumprod, t, dtype)  # :286-290
-    alpha_bar = _ex(sch.alphas_cumprod, t, dtype)
-    alpha_bar_prev = _ex(sch.alphas_cumprod_prev, t, dtype)
-    sigma = dtype(0.0) * np.sqrt((one - alpha_bar_prev) / (one - alpha_bar)) * np.sqrt(one - alpha_bar / alpha_bar_prev)
-    mean_pred = x0 * np.sqrt(alpha_bar_prev) + np.sqrt(one - alpha_bar_prev - sigma ** 2) * eps
+    c_recip, c_recipm1, s_abp, s_1mabp = (dtype(c) for c in ddim_coefficients(sch, t))
+    eps = (c_recip * x - x0) / c_recipm1  # :286-290
+    mean_pred = x0 * s_abp + s_1mabp * eps
     return mean_pred.astype(dtype)  # + nonzero_mask * sigma * noise == + 0
+
+
+def ddpm_coefficients(sch, t, guided=False, cond_grad_weight=1.0):
+    """coef1, coef2, (t != 0) * exp(0.5 * log_var), gradient scale — fp32 like torch (gaussian_diffusion.py:220-223,
+    260-262, 336, 378-385)."""
+    nonzero = np.float32(1.0 if t != 0 else 0.0)
+    std = np.exp(np.float32(0.5) * _ex(sch.posterior_log_variance_clipped, t))
+    gscale = np.float32(0.0)
+    if guided and t <= 10:
+        if t >= 5:
+            gscale = np.float32(cond_grad_weight) * _ex(sch.posterior_variance, t)
+        else:
+            gscale = np.float32(cond_grad_weight * 0.01)
+    return _ex(sch.posterior_mean_coef1, t), _ex(sch.posterior_mean_coef2, t), np.float32(nonzero * std), gscale
 
 
 def ddpm_update(sch, x, x0, t, noise, grad=None, cond_grad_weight=1.0, dtype=np.float32):
     """p_sample / p_sample_with_grad (gaussian_diffusion.py:298-388) given pred_xstart = x0."""
-    mean = _ex(sch.posterior_mean_coef1, t, dtype) * x0 + _ex(sch.posterior_mean_coef2, t, dtype) * x  # :220-223
+    c1, c2, nz_std, gscale = (dtype(c) for c in ddpm_coefficients(sch, t, grad is not None, cond_grad_weight))
+    mean = c1 * x0 + c2 * x  # :220-223
     if grad is not None and t <= 10:  # :378-385
-        if t >= 5:
-            mean = mean + (dtype(cond_grad_weight) * _ex(sch.posterior_variance, t, dtype)) * grad
-        else:
-            mean = mean + dtype(dtype(cond_grad_weight) * dtype(0.01)) * grad
-    nonzero = dtype(1.0 if t != 0 else 0.0)
-    std = np.exp(dtype(0.5) * _ex(sch.posterior_log_variance_clipped, t, dtype))
-    return (mean + (nonzero * std) * noise).astype(dtype)
+        mean = mean + gscale * grad
+    return (mean + nz_std * noise).astype(dtype)

@@ -1,0 +1,191 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference (/root/reference).
+
+Run once in the build container (`python tests/golden/make_golden.py`); the GPU box never runs this.  Inputs, weights
+and the SMPL model come from `egohmr_b200.synth` (seeded, regenerable), so only the reference's OUTPUTS are stored.
+The reference's RNG draws (`th.randn`, `th.randn_like`) are fed from `synth.make_noise` so every implementation sees
+the same noise; nothing inside /root/reference is edited.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+from egohmr_b200 import synth  # noqa: E402
+import ref_standins  # noqa: E402
+
+
+def to_torch(batch, dtype):
+    out = {}
+    for k, v in batch.items():
+        if isinstance(v, dict):
+            out[k] = to_torch(v, dtype)
+        else:
+            out[k] = torch.from_numpy(np.asarray(v)).to(dtype)
+    return out
+
+
+class NoiseFeed:
+    """Replaces torch.randn / torch.randn_like while the reference sampler runs."""
+
+    def __init__(self, noise, dtype):
+        self.noise = [torch.from_numpy(n).to(dtype) for n in noise]
+        self.i = 0
+
+    def _next(self, shape):
+        n = self.noise[self.i]
+        self.i += 1
+        assert tuple(n.shape) == tuple(shape), (n.shape, shape)
+        return n.clone()
+
+    def randn(self, *shape, **kw):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return self._next(shape)
+
+    def randn_like(self, x, **kw):
+        return self._next(x.shape)
+
+
+def build_reference(hid, n_blocks, dtype, seed=0):
+    smpl_model = synth.make_smpl_model(seed)
+    ref_standins.install(smpl_model, smpl_model["init_betas"])
+    from models.egohmr.egohmr import EgoHMR
+    mean, std = synth.body_rep_stats(seed)
+    model = EgoHMR(cfg=ref_standins.make_cfg(), device="cpu",
+                   body_rep_mean=torch.from_numpy(mean).to(dtype), body_rep_std=torch.from_numpy(std).to(dtype),
+                   with_focal_length=True, with_bbox_info=True, with_cam_center=True, scene_feat_dim=512,
+                   scene_type="cube", scene_cano=True, cond_mask_prob=0.0, only_mask_img_cond=True,
+                   pelvis_vis_loosen=True, diffuse_fuse=True, diffusion_blk=n_blocks, gcn_hid_dim=hid)
+    sd = synth.make_state_dict(seed, hid=hid, n_blocks=n_blocks, init_betas=smpl_model["init_betas"])
+    res = model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+    assert not res.unexpected_keys and all(k.startswith("smpl") for k in res.missing_keys), res
+    # randomised adj2 must survive: the reference keeps `adj` as a plain attribute, adj2 as a parameter
+    model = model.to(dtype)
+    for m in model.modules():
+        if hasattr(m, "adj") and isinstance(getattr(m, "adj"), torch.Tensor):
+            m.adj = m.adj.to(dtype)
+    model.eval()
+    if dtype == torch.float64:
+        model.smpl.out_dtype = torch.float64
+    return model, mean, std
+
+
+def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0):
+    from diffusion.model_util import create_gaussian_diffusion
+    import diffusion.gaussian_diffusion as gd
+    model, mean, std = build_reference(hid, n_blocks, dtype, seed)
+    diffusion = create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=respacing,
+                                          body_rep_mean=torch.from_numpy(mean).to(dtype),
+                                          body_rep_std=torch.from_numpy(std).to(dtype))
+    n_steps = diffusion.num_timesteps
+    batch = to_torch(synth.make_batch(seed, n_img), dtype)
+    noise = synth.make_noise(seed, 1, n_img, n_steps)[0]
+    feed = NoiseFeed(noise, dtype)
+    trace = []
+    orig_pmv = diffusion.p_mean_variance.__func__ if hasattr(diffusion.p_mean_variance, "__func__") else None
+
+    # record per-step x_t / pred_xstart by wrapping the model call (does not alter the reference's arithmetic)
+    class Wrapped(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m = m
+
+        def forward(self, b, t, **kw):
+            o = self.m(b, t, **kw)
+            trace.append((int(t[0]), b["x_t"].detach().clone().numpy(), o["pred_x_start"].detach().clone().numpy()))
+            return o
+
+        def __getattr__(self, k):
+            try:
+                return super().__getattr__(k)
+            except AttributeError:
+                return getattr(self.m, k)
+
+    old_randn, old_randn_like = torch.randn, torch.randn_like
+    torch.randn, torch.randn_like = feed.randn, feed.randn_like
+    try:
+        with torch.no_grad():
+            out = diffusion.val_losses(model=Wrapped(model), batch=batch, shape=[n_img, 144], progress=False,
+                                       clip_denoised=False, cur_epoch=0, timestep_respacing=respacing,
+                                       cond_fn_with_grad=False, cond_grad_weight=2.0, compute_loss=False)
+    finally:
+        torch.randn, torch.randn_like = old_randn, old_randn_like
+    g = lambda t: t.detach().numpy()
+    rec = {
+        "T": T, "respacing": respacing, "hid": hid, "n_blocks": n_blocks, "n_img": n_img, "seed": seed,
+        "timestep_map": np.array(diffusion.timestep_map), "trace_t_orig": np.array([t for t, _, _ in trace]),
+        "trace_x_t": np.stack([x for _, x, _ in trace]), "trace_x0": np.stack([x for _, _, x in trace]),
+        "pred_x_start": g(out["pred_x_start"]), "pred_pose_6d": g(out["pred_pose_6d"]),
+        "global_orient": g(out["pred_smpl_params"]["global_orient"]), "body_pose": g(out["pred_smpl_params"]["body_pose"]),
+        "betas": g(out["pred_smpl_params"]["betas"]), "pred_keypoints_3d": g(out["pred_keypoints_3d"]),
+        "pred_vertices": g(out["pred_vertices"]), "pred_keypoints_2d_full": g(out["pred_keypoints_2d_full"]),
+        "vis_mask_smpl": batch["vis_mask_smpl"].numpy(),
+    }
+    # step-invariant features of the reference's own encoders (inputs for feature-level parity tests)
+    with torch.no_grad():
+        rec["img_feats"] = g(model.backbone(batch["img"]))
+        pts = batch["scene_pcd_verts_full"] - batch["smpl_params"]["transl"].unsqueeze(1)
+        rec["scene_feats"] = g(model.scene_enc(pts))
+        rec["transl_feat"] = g(model.transl_enc(batch["smpl_params"]["transl"]))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, {k: getattr(v, "shape", v) for k, v in rec.items() if k in ("trace_x0", "pred_vertices")})
+
+
+def schedule_tables():
+    from diffusion.model_util import create_gaussian_diffusion
+    rec = {}
+    for T in (50, 100, 1000):
+        for resp in ("", "ddim5"):
+            d = create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=resp)
+            tag = f"T{T}_{resp or 'ddpm'}"
+            rec[tag + "_timestep_map"] = np.array(d.timestep_map)
+            for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+                      "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+                      "posterior_mean_coef1", "posterior_mean_coef2"):
+                rec[tag + "_" + k] = getattr(d, k)
+    np.savez_compressed(os.path.join(HERE, "schedule_tables.npz"), **rec)
+    print("wrote schedule_tables", len(rec))
+
+
+def small_ops():
+    """rot6d_to_rotmat and one ModulatedGraphConv straight from the reference's modules."""
+    from utils.geometry import rot6d_to_rotmat
+    from models.egohmr.modulated_gcn.modulated_gcn_conv import ModulatedGraphConv
+    rng = np.random.default_rng(77)
+    x = rng.normal(0, 1, (64, 144)).astype(np.float32)
+    x[0, :6] = 0  # degenerate input exercises the eps clamp
+    R32 = rot6d_to_rotmat(torch.from_numpy(x), "diffusion").numpy()
+    R64 = rot6d_to_rotmat(torch.from_numpy(x).double(), "diffusion").numpy()
+    adj = torch.from_numpy(synth.skeleton_adjacency())
+    conv = ModulatedGraphConv(96, 128, adj)
+    sdc = {k: rng.normal(0, 0.3, tuple(v.shape)).astype(np.float32) for k, v in conv.state_dict().items()}
+    conv.load_state_dict({k: torch.from_numpy(v) for k, v in sdc.items()})
+    xin = rng.normal(0, 1, (3, 24, 96)).astype(np.float32)
+    with torch.no_grad():
+        y32 = conv(torch.from_numpy(xin)).numpy()
+        conv64 = conv.double()
+        conv64.adj = adj.double()
+        y64 = conv64(torch.from_numpy(xin).double()).numpy()
+    np.savez_compressed(os.path.join(HERE, "small_ops.npz"), rot6d_x=x, rot6d_R32=R32, rot6d_R64=R64, gconv_x=xin,
+                        gconv_y32=y32, gconv_y64=y64, **{"gconv_" + k: v for k, v in sdc.items()})
+    print("wrote small_ops")
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    # the stand-ins must be installed before importing reference modules
+    smpl_model = synth.make_smpl_model(0)
+    ref_standins.install(smpl_model, smpl_model["init_betas"])
+    schedule_tables()
+    small_ops()
+    run_case("ddim5_T50_hid1024_f32", 50, "ddim5", 1024, 4, 2, torch.float32)
+    run_case("ddim5_T50_hid1024_f64", 50, "ddim5", 1024, 4, 2, torch.float64)
+    run_case("ddpm_T50_hid256_f32", 50, "", 256, 2, 3, torch.float32)
+    run_case("ddpm_T50_hid256_f64", 50, "", 256, 2, 3, torch.float64)

@@ -1,0 +1,275 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the oracle and the reference's golden vectors.
+
+Tolerances (all absolute, stated where used):
+* the denoiser runs its 8 hidden GEMMs on the fp16 tensor pipe with an error-compensated hi/lo split (~2^-22 relative
+  operand error, DESIGN.md "numerics"); against the float64 reference trace that is a few 1e-6 on pred_x_start
+  (|x0| ~ 1), against 5e-7 for the reference's own fp32-vs-fp64 noise;
+* SMPL LBS is plain fp32 FFMA: a few 1e-7 m on vertices for a fixed pose;
+* the sampler update is bit-exact given equal inputs.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from egohmr_b200 import synth
+from oracle import egohmr as o_egohmr, encoders, gcn, geometry, schedule, smpl as o_smpl
+
+pytestmark = pytest.mark.gpu
+
+X0_TOL = 2e-5          # max |pred_x_start - float64 reference| (normalised rot6d units, |x0| ~ 1)
+VERT_TOL_M = 2e-5      # max per-vertex error in metres vs the float64 oracle = 0.02 mm
+
+
+@pytest.fixture(scope="module")
+def full():
+    from egohmr_b200.testing import build_model
+    return build_model(1024, 4, T=50, respacing="ddim5")
+
+
+@pytest.fixture(scope="module")
+def small():
+    from egohmr_b200.testing import build_model
+    return build_model(256, 2, T=50, respacing="")
+
+
+def _tb(batch_np):
+    from egohmr_b200.testing import torch_batch
+    return torch_batch(batch_np, "cuda:0")
+
+
+def test_context_on_sm100(full):
+    assert torch.cuda.get_device_capability(0)[0] == 10
+    assert full[0].engine.lib is not None
+
+
+def test_rot6d_golden(golden_dir):
+    from egohmr_b200.utils.geometry import rot6d_to_rotmat
+    so = np.load(os.path.join(golden_dir, "small_ops.npz"))
+    R = rot6d_to_rotmat(torch.from_numpy(so["rot6d_x"]).cuda(), "diffusion").cpu().numpy()
+    assert R.shape == (64 * 24, 3, 3)
+    assert np.abs(R - so["rot6d_R64"]).max() < 5e-7
+    RtR = np.einsum("nij,nik->njk", R[1:], R[1:])
+    assert np.abs(RtR - np.eye(3)).max() < 1e-5 and np.abs(np.linalg.det(R[1:].astype(np.float64)) - 1).max() < 1e-5
+    assert np.isnan(R[0]).sum() == 0   # all-zero 6-D input: eps clamp, no NaN (F.normalize semantics)
+
+
+def test_rot6d_empty_input():
+    from egohmr_b200.utils.geometry import rot6d_to_rotmat
+    assert rot6d_to_rotmat(torch.zeros(0, 144, device="cuda")).shape == (0, 3, 3)
+
+
+def test_smpl_forward_matches_oracle(full):
+    model, _, _, smpl_model, _, _ = full
+    rng = np.random.default_rng(3)
+    n = 37   # ragged vs the 8-body skinning tile
+    R = geometry.rot6d_to_rotmat(rng.normal(0, 1, (n, 144))).reshape(n, 24, 3, 3)
+    betas = rng.normal(0, 1, (n, 10))
+    transl = rng.normal(0, 1, (n, 3))
+    ref = o_smpl.smpl_forward(smpl_model, R, betas, transl)
+    Rt = torch.from_numpy(R.astype(np.float32)).cuda()
+    out = model.smpl(betas=torch.from_numpy(betas.astype(np.float32)).cuda(), body_pose=Rt[:, 1:], global_orient=Rt[:, [0]],
+                     transl=torch.from_numpy(transl.astype(np.float32)).cuda(), pose2rot=False, return_full_pose=True)
+    assert out.vertices.shape == (n, 6890, 3) and out.joints.shape == (n, 45, 3)
+    assert np.abs(out.vertices.cpu().numpy() - ref["vertices"]).max() < 3e-6
+    assert np.abs(out.joints.cpu().numpy() - ref["joints"]).max() < 3e-6
+    assert torch.equal(out.full_pose, Rt)
+
+
+def test_smpl_known_answers(full):
+    model, _, _, smpl_model, _, _ = full
+    eye = torch.eye(3, device="cuda").repeat(2, 24, 1, 1)
+    out = model.smpl(betas=torch.zeros(2, 10, device="cuda"), body_pose=eye[:, 1:], global_orient=eye[:, [0]], pose2rot=False)
+    assert np.abs(out.vertices.cpu().numpy() - smpl_model["v_template"][None]).max() < 1e-6   # identity pose -> template
+
+
+def _oracle_denoise(sd, n_blocks, x_t, t_orig, g, dtype=np.float64):
+    cam = encoders.cam_feats(synth.make_batch(0, x_t.shape[0]), np.dtype(dtype).type)
+    rest = np.concatenate([g["scene_feats"], g["transl_feat"], cam], axis=1)
+    return gcn.denoise(sd, synth.skeleton_adjacency(), n_blocks, x_t.astype(dtype), np.full(x_t.shape[0], t_orig),
+                       g["img_feats"].astype(dtype), rest.astype(dtype), g["vis_mask_smpl"].astype(bool), True)
+
+
+def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
+    """One EgoHMR.forward at t=30 on the reference's own encoder features: tcgen05 path vs float64 oracle, and the
+    tcgen05 path vs the fp32 FFMA check path (isolates the tensor-core numerics)."""
+    model, diffusion, sd, _, _, _ = full
+    g = np.load(os.path.join(golden_dir, "ddim5_T50_hid1024_f64.npz"))
+    batch = _tb(synth.make_batch(0, 2))
+    feats = {k: torch.from_numpy(g[k].astype(np.float32)).cuda() for k in ("img_feats", "scene_feats", "transl_feat")}
+    x_t = g["trace_x_t"][1]  # the reference's x_t entering original timestep 30
+    ref_x0, ref_c, ref_u = _oracle_denoise(sd, 4, x_t, 30, g)
+    assert np.abs(ref_x0 - g["trace_x0"][1]).max() < 1e-12  # the oracle reproduces the reference here
+    model.prepare(batch, 1, features=feats)
+    model.set_timesteps([30])
+    model.engine.set_schedule(0, np.array([[1, 1, 1, 0, 0, 0, 0, 0]], np.float32))
+    xt = torch.from_numpy(x_t.astype(np.float32)).cuda()
+    outs = {}
+    for mode in (1, 0):
+        model.engine.set_gemm_mode(mode)
+        x0, xp, oc, ou = (torch.empty_like(xt) for _ in range(4))
+        model.engine.denoise_step(0, xt, None, None, xp, x0, oc, ou)
+        torch.cuda.synchronize()
+        outs[mode] = (x0.cpu().numpy(), oc.cpu().numpy(), ou.cpu().numpy())
+    model.engine.set_gemm_mode(0)
+    model._temb_key = None
+    model._cond_key = None
+    assert not model.engine.check_overflow()
+    print(f"fp32-FFMA path vs f64: {np.abs(outs[1][0] - ref_x0).max():.3e}; tcgen05 path vs f64: "
+          f"{np.abs(outs[0][0] - ref_x0).max():.3e}")
+    assert np.abs(outs[1][0] - ref_x0).max() < 3e-6        # fp32 FFMA path vs float64
+    assert np.abs(outs[0][1] - ref_c).max() < X0_TOL       # image-conditioned pass
+    assert np.abs(outs[0][2] - ref_u).max() < X0_TOL       # image-masked pass
+    assert np.abs(outs[0][0] - ref_x0).max() < X0_TOL      # fused select
+    assert np.abs(outs[0][0] - outs[1][0]).max() < X0_TOL
+
+
+def test_forward_signature_and_outputs(full):
+    """model(batch, t) returns the reference's dict (egohmr.py:256-303) and mutates batch like the reference."""
+    model, diffusion, sd, smpl_model, mean, std = full
+    batch_np = synth.make_batch(0, 2)
+    batch = _tb(batch_np)
+    x_t = np.random.default_rng(5).normal(0, 1, (2, 144)).astype(np.float32)
+    batch["x_t"] = torch.from_numpy(x_t).cuda()
+    out = model(batch, torch.tensor([20, 20], device="cuda"))
+    ref = o_egohmr.forward(sd, synth.skeleton_adjacency(), 4, smpl_model, batch_np, x_t, np.array([20, 20]), mean, std,
+                           dtype=np.float64)
+    for k in ("pred_x_start", "pred_pose_6d", "pred_keypoints_3d", "pred_vertices", "pred_keypoints_3d_full",
+              "pred_keypoints_2d_full"):
+        assert tuple(out[k].shape) == ref[k].shape, k
+        assert np.abs(out[k].cpu().numpy() - ref[k]).max() < 5e-5, k
+    assert out["pred_smpl_params"]["global_orient"].shape == (2, 1, 3, 3)
+    assert out["pred_smpl_params"]["body_pose"].shape == (2, 23, 3, 3)
+    assert np.abs(out["pred_smpl_params"]["betas"].cpu().numpy() - ref["pred_smpl_params"]["betas"]).max() < 1e-5
+    assert "vis_mask_smpl" in batch and batch["vis_mask_smpl"].shape == (2, 24)
+
+
+def test_ddim5_sampling_vs_reference_golden(full, golden_dir):
+    """configs[0]: test_egohmr.py's sampling block, DDIM-5 of T=50, through create_gaussian_diffusion and the sampler
+    loops, with the noise the golden run used; compared with the reference's float64 and float32 runs."""
+    model, diffusion, sd, smpl_model, mean, std = full
+    g64 = np.load(os.path.join(golden_dir, "ddim5_T50_hid1024_f64.npz"))
+    g32 = np.load(os.path.join(golden_dir, "ddim5_T50_hid1024_f32.npz"))
+    batch = _tb(synth.make_batch(0, 2))
+    noise = synth.make_noise(0, 1, 2, 5)[0]
+    x0s = []
+    final = None
+    for out in diffusion.ddim_sample_loop_progressive(model, batch, [2, 144], noise=torch.from_numpy(noise[0]).cuda()):
+        x0s.append(out["pred_xstart"].cpu().numpy())
+        final = out
+    x0s = np.stack(x0s)
+    noise_floor = np.abs(g32["trace_x0"] - g64["trace_x0"]).max()   # the reference's own fp32 vs fp64
+    print(f"max|x0 - ref_f64| = {np.abs(x0s - g64['trace_x0']).max():.3e}; reference fp32-vs-fp64 = {noise_floor:.3e}")
+    assert np.abs(x0s - g64["trace_x0"]).max() < X0_TOL
+    oo = final["other_outputs"]
+    assert torch.equal(final["sample"], final["pred_xstart"])  # DDIM's last step returns pred_xstart exactly
+    # vertices vs a float64 SMPL on the float64 reference rotations
+    R64 = np.concatenate([g64["global_orient"], g64["body_pose"]], axis=1)
+    v64 = o_smpl.smpl_forward(smpl_model, R64, g64["betas"])["vertices"]
+    dv = np.abs(oo["pred_vertices"].cpu().numpy() - v64).max()
+    print(f"max vertex error vs float64 = {dv * 1e3:.3e} mm")
+    assert dv < VERT_TOL_M
+    assert np.abs(oo["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < VERT_TOL_M
+    assert np.abs(oo["pred_keypoints_2d_full"].cpu().numpy() - g64["pred_keypoints_2d_full"]).max() < 1e-4
+    assert np.abs(oo["pred_smpl_params"]["betas"].cpu().numpy() - g64["betas"]).max() < 1e-5
+
+
+def test_val_losses_dropin_and_rng_parity(full):
+    """val_losses(...) draws its noise from torch's global generator exactly like the reference (randn(shape), then one
+    randn_like per step — DDIM included), so a seeded call equals a call fed the same first draw explicitly."""
+    model, diffusion, *_ = full
+    batch = _tb(synth.make_batch(1, 3))
+    torch.manual_seed(123)
+    a = diffusion.val_losses(model=model, batch=batch, shape=[3, 144], progress=False, clip_denoised=False, cur_epoch=0,
+                             timestep_respacing="ddim5", cond_fn_with_grad=False, cond_grad_weight=2.0, compute_loss=False)
+    after = torch.randn(1, device="cuda")
+    torch.manual_seed(123)
+    first = torch.randn(3, 144, device="cuda")
+    b = diffusion.ddim_sample_loop(model, batch, [3, 144], noise=first)["other_outputs"]
+    assert torch.equal(a["pred_x_start"], b["pred_x_start"]) and torch.equal(a["pred_vertices"], b["pred_vertices"])
+    torch.manual_seed(123)
+    for _ in range(6):   # randn(shape) + 5 x randn_like, as gaussian_diffusion.py:478,547 would consume
+        torch.randn(3, 144, device="cuda")
+    assert torch.equal(after, torch.randn(1, device="cuda"))
+
+
+def test_ddpm50_sampling_vs_reference_golden(small, golden_dir):
+    """Full 50-step DDPM chain (p_sample, no guidance), hid 256 x 2 blocks."""
+    model, diffusion, sd, smpl_model, mean, std = small
+    g64 = np.load(os.path.join(golden_dir, "ddpm_T50_hid256_f64.npz"))
+    g32 = np.load(os.path.join(golden_dir, "ddpm_T50_hid256_f32.npz"))
+    batch = _tb(synth.make_batch(0, 3))
+    noise = torch.from_numpy(synth.make_noise(0, 1, 3, 50)[0]).cuda()
+    out = diffusion.sample_many(model, batch, 1, "", noise=noise)
+    d64 = np.abs(out["pred_x_start"].cpu().numpy() - g64["pred_x_start"]).max()
+    floor = np.abs(g32["pred_x_start"] - g64["pred_x_start"]).max()
+    print(f"DDPM-50 final max|x0 - ref_f64| = {d64:.3e}; reference fp32-vs-fp64 = {floor:.3e}")
+    assert d64 < 5e-5    # 50 chained steps
+    assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < 1e-4
+
+
+def test_sample_many_equals_sequential_chains(full):
+    """Flattening the num_samples loop (test_egohmr.py:251-255) into one batch changes nothing: chain (img i, sample n)
+    of the flattened run equals the n-th sequential call when both see the same noise."""
+    model, diffusion, *_ = full
+    n_img, S = 3, 4
+    batch = _tb(synth.make_batch(2, n_img))
+    noise = synth.make_noise(7, S, n_img, 5)            # [S, 6, n_img, 144]
+    flat = np.ascontiguousarray(np.transpose(noise, (1, 2, 0, 3))).reshape(6, n_img * S, 144)   # body = img*S + n
+    many = diffusion.sample_many(model, batch, S, "ddim5", noise=torch.from_numpy(flat).cuda())
+    for n in range(S):
+        one = diffusion.sample_many(model, batch, 1, "ddim5", noise=torch.from_numpy(noise[n]).cuda())
+        assert torch.equal(many["pred_x_start"][n::S], one["pred_x_start"])
+        assert torch.equal(many["pred_vertices"][n::S], one["pred_vertices"])
+
+
+def test_full_size_properties_cfg2(full):
+    """configs[1] size (64 images x 10 samples = 640 bodies, DDIM-5) through size-independent properties:
+    determinism, replicated inputs give replicated outputs, orthonormal rotations, no fp16 overflow, and agreement of
+    the tcgen05 path with the fp32 FFMA check path."""
+    model, diffusion, *_ = full
+    n_img, S = 64, 10
+    base = synth.make_batch(3, 8)
+    rep = lambda a: np.concatenate([a] * (n_img // 8), axis=0)  # 8 distinct images, each appearing 8 times
+    batch_np = {k: (rep(v) if not isinstance(v, dict) else {kk: rep(vv) for kk, vv in v.items()}) for k, v in base.items()}
+    batch = _tb(batch_np)
+    n8 = synth.make_noise(11, 1, 8 * S, 5)[0].reshape(6, 8, S, 144)
+    noise = np.concatenate([n8] * (n_img // 8), axis=1).reshape(6, n_img * S, 144)
+    nz = torch.from_numpy(noise).cuda()
+    a = diffusion.sample_many(model, batch, S, "ddim5", noise=nz)
+    b = diffusion.sample_many(model, batch, S, "ddim5", noise=nz)
+    assert torch.equal(a["pred_x_start"], b["pred_x_start"]) and torch.equal(a["pred_vertices"], b["pred_vertices"])
+    assert not model.engine.check_overflow()
+    x0 = a["pred_x_start"].reshape(n_img, S, 144)
+    assert torch.equal(x0[:8], x0[8:16]) and torch.equal(x0[:8], x0[56:64])   # replicas agree bit for bit
+    R = torch.cat([a["pred_smpl_params"]["global_orient"], a["pred_smpl_params"]["body_pose"]], dim=1).reshape(-1, 3, 3)
+    assert (R.transpose(1, 2) @ R - torch.eye(3, device="cuda")).abs().max() < 1e-5
+    assert torch.isfinite(a["pred_vertices"]).all()
+    model.engine.set_gemm_mode(1)
+    try:
+        c = diffusion.sample_many(model, batch, S, "ddim5", noise=nz)
+    finally:
+        model.engine.set_gemm_mode(0)
+    d = (a["pred_x_start"] - c["pred_x_start"]).abs().max().item()
+    dv = (a["pred_vertices"] - c["pred_vertices"]).abs().max().item()
+    print(f"cfg2: tcgen05 vs fp32-FFMA path: max|dx0| = {d:.3e}, max vertex diff = {dv * 1e3:.3e} mm")
+    assert d < X0_TOL and dv < VERT_TOL_M
+
+
+def test_generic_path_with_foreign_model(full):
+    """p_sample / ddim_sample keep the reference's `model(batch, t)` protocol: a foreign callable returning
+    pred_x_start is stepped with the CUDA sampler update, bit-identical to the oracle's fp32 update."""
+    _, diffusion, *_ = full
+    sch = schedule.Schedule(50, "ddim5")
+    rng = np.random.default_rng(9)
+    x = rng.normal(0, 1, (4, 144)).astype(np.float32)
+    x0 = rng.normal(0, 1, (4, 144)).astype(np.float32)
+
+    class Foreign(torch.nn.Module):
+        def forward(self, batch, t):
+            assert t.tolist() == [30] * 4          # respaced index 3 -> original timestep 30
+            return {"pred_x_start": torch.from_numpy(x0).cuda()}
+
+    out = diffusion.ddim_sample(Foreign(), {}, torch.from_numpy(x).cuda(), torch.full((4,), 3, device="cuda"))
+    assert np.array_equal(out["sample"].cpu().numpy(), schedule.ddim_update(sch, x, x0, 3))

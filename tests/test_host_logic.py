@@ -1,0 +1,77 @@
+"""Host-side logic that needs no GPU: schedule tables and per-step coefficients of the product sampler, the C-ABI
+library's exported symbols, and the image-sharding plan."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from egohmr_b200 import _lib
+from egohmr_b200.diffusion.model_util import create_gaussian_diffusion
+from egohmr_b200.diffusion.respace import space_timesteps
+from oracle import schedule
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("T,resp", [(50, ""), (50, "ddim5"), (100, ""), (1000, "ddim5"), (1000, "")])
+def test_product_tables_match_reference_golden(golden_dir, T, resp):
+    tab = np.load(os.path.join(golden_dir, "schedule_tables.npz"))
+    d = create_gaussian_diffusion(T, resp)
+    tag = f"T{T}_{resp or 'ddpm'}"
+    assert d.timestep_map == list(tab[tag + "_timestep_map"])
+    for k in ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod",
+              "sqrt_recipm1_alphas_cumprod", "posterior_variance", "posterior_log_variance_clipped",
+              "posterior_mean_coef1", "posterior_mean_coef2"):
+        assert np.array_equal(getattr(d, k), tab[f"{tag}_{k}"]), k
+
+
+def test_space_timesteps_matches_oracle_and_errors():
+    for T in (50, 100, 1000):
+        for s in ("ddim5", "ddim10", [T], "10,15,16", "3", "1", "7,9"):
+            assert space_timesteps(T, s) == schedule.space_timesteps(T, s)
+    with pytest.raises(ValueError):
+        space_timesteps(50, "ddim11")     # no integer stride gives 11 steps of 50
+    with pytest.raises(ValueError):
+        space_timesteps(10, "20")         # cannot take 20 steps out of 10
+
+
+def test_step_coefficients_match_oracle():
+    d = create_gaussian_diffusion(50, "ddim5")
+    s = schedule.Schedule(50, "ddim5")
+    c = d.step_coefficients(d.DDIM)
+    for t in range(5):
+        ref = np.array(schedule.ddim_coefficients(s, t), np.float32)
+        assert np.array_equal(c[t, :4], ref), (t, c[t, :4], ref)
+    assert c[0, 2] == 1.0 and c[0, 3] == 0.0   # last DDIM step returns pred_xstart exactly
+    d = create_gaussian_diffusion(100, "")
+    s = schedule.Schedule(100, "")
+    c = d.step_coefficients(d.DDPM, guided=True, cond_grad_weight=2.0)
+    for t in range(100):
+        ref = np.array(schedule.ddpm_coefficients(s, t, True, 2.0), np.float32)
+        assert np.allclose(c[t, :4], ref, rtol=2e-7, atol=0), (t, c[t, :4], ref)  # expf may differ by 1 ulp
+        assert c[t, 0] == ref[0] and c[t, 1] == ref[1]
+    assert c[0, 2] == 0.0                      # no noise at t == 0
+    assert (c[11:, 3] == 0).all() and (c[:11, 3] > 0).all()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "egohmr_b200.h")).read()
+    declared = set(re.findall(r"\b(ehb_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("ehb_ctx")
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert os.path.exists(_lib.LIB_PATH), "run __graft_entry__.build() first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    _lib.load()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from egohmr_b200.engine import Engine
+    with pytest.raises(_lib.EhbError):
+        Engine(0)

@@ -1,0 +1,107 @@
+"""The oracle (oracle/, numpy) against the vectors produced by the UNMODIFIED reference (tests/golden/make_golden.py).
+This is what pins the oracle: every later CUDA-vs-oracle comparison inherits its meaning from these checks."""
+import os
+
+import numpy as np
+import pytest
+
+from egohmr_b200 import synth
+from oracle import egohmr as o_egohmr, encoders, gcn, geometry, schedule
+
+TABLES = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+          "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2")
+
+
+@pytest.mark.parametrize("T", [50, 100, 1000])
+@pytest.mark.parametrize("resp", ["", "ddim5"])
+def test_schedule_tables_bit_identical(golden_dir, T, resp):
+    tab = np.load(os.path.join(golden_dir, "schedule_tables.npz"))
+    s = schedule.Schedule(T, resp)
+    tag = f"T{T}_{resp or 'ddpm'}"
+    assert list(tab[tag + "_timestep_map"]) == s.timestep_map
+    for k in TABLES:
+        assert np.array_equal(tab[f"{tag}_{k}"], getattr(s, k)), k  # float64, bit for bit
+
+
+def test_ddim5_timestep_maps():
+    # T=50/100/1000 'ddim5' -> strides 10/20/200
+    assert schedule.Schedule(50, "ddim5").timestep_map == [0, 10, 20, 30, 40]
+    assert schedule.Schedule(100, "ddim5").timestep_map == [0, 20, 40, 60, 80]
+    assert schedule.Schedule(1000, "ddim5").timestep_map == [0, 200, 400, 600, 800]
+
+
+def test_rot6d_golden(golden_dir):
+    so = np.load(os.path.join(golden_dir, "small_ops.npz"))
+    R64 = geometry.rot6d_to_rotmat(so["rot6d_x"].astype(np.float64))
+    assert np.abs(R64 - so["rot6d_R64"]).max() < 1e-14
+    assert np.abs(geometry.rot6d_to_rotmat(so["rot6d_x"]) - so["rot6d_R32"]).max() < 5e-7
+
+
+def test_modulated_graph_conv_golden(golden_dir):
+    so = np.load(os.path.join(golden_dir, "small_ops.npz"))
+    y = gcn.modulated_graph_conv(so["gconv_x"].astype(np.float64), so["gconv_W"], so["gconv_M"],
+                                 synth.skeleton_adjacency(), so["gconv_adj2"], so["gconv_bias"])
+    assert np.abs(y - so["gconv_y64"]).max() < 1e-12
+    y32 = gcn.modulated_graph_conv(so["gconv_x"], so["gconv_W"], so["gconv_M"], synth.skeleton_adjacency(),
+                                   so["gconv_adj2"], so["gconv_bias"])
+    assert np.abs(y32 - so["gconv_y32"]).max() < 2e-5
+
+
+def _run_case(golden_dir, case, dtype):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    hid, nb, n_img, T, resp = int(g["hid"]), int(g["n_blocks"]), int(g["n_img"]), int(g["T"]), str(g["respacing"])
+    smpl = synth.make_smpl_model(0)
+    sd = synth.make_state_dict(0, hid=hid, n_blocks=nb, init_betas=smpl["init_betas"])
+    b = synth.make_batch(0, n_img)
+    mean, std = synth.body_rep_stats(0)
+    sch = schedule.Schedule(T, resp)
+    assert sch.timestep_map == list(g["timestep_map"])
+    noise = synth.make_noise(0, 1, n_img, sch.num_timesteps)[0]
+    trace = []
+    out = o_egohmr.sample(sd, synth.skeleton_adjacency(), nb, smpl, b, sch, noise, mean, std,
+                          "ddim" if resp else "ddpm", dtype=dtype, trace=trace)
+    return g, out, np.stack([t["pred_x_start"] for t in trace]), np.stack([t["x_t"] for t in trace])
+
+
+def test_ddim5_full_size_fp64_trace(golden_dir):
+    """T=50 ddim5, hid 1024 x 4 blocks, 2 images: every step's x_t and pred_x_start, float64."""
+    g, out, x0s, xts = _run_case(golden_dir, "ddim5_T50_hid1024_f64", np.float64)
+    assert list(g["trace_t_orig"]) == [40, 30, 20, 10, 0]
+    assert np.abs(x0s - g["trace_x0"]).max() < 1e-12
+    assert np.abs(xts - g["trace_x_t"]).max() < 1e-12
+    assert np.abs(out["pred_pose_6d"] - g["pred_pose_6d"]).max() < 1e-12
+    R = np.concatenate([g["global_orient"], g["body_pose"]], axis=1)
+    Ro = np.concatenate([out["pred_smpl_params"]["global_orient"], out["pred_smpl_params"]["body_pose"]], axis=1)
+    assert np.abs(R - Ro).max() < 1e-12
+    assert np.abs(out["pred_smpl_params"]["betas"] - g["betas"]).max() < 1e-12
+    # the reference casts SMPL inputs to fp32 (egohmr.py:276) even in a float64 run
+    assert np.abs(out["pred_vertices"] - g["pred_vertices"]).max() < 5e-6
+    assert np.abs(out["pred_keypoints_2d_full"] - g["pred_keypoints_2d_full"]).max() < 5e-6
+    assert np.array_equal(encoders.vis_mask_smpl(synth.make_batch(0, 2)["orig_keypoints_2d"]),
+                          g["vis_mask_smpl"].astype(bool))
+
+
+def test_ddim5_full_size_fp32(golden_dir):
+    g, out, x0s, xts = _run_case(golden_dir, "ddim5_T50_hid1024_f32", np.float32)
+    assert np.abs(x0s - g["trace_x0"]).max() < 5e-6      # fp32 summation-order noise
+    assert np.abs(out["pred_vertices"] - g["pred_vertices"]).max() < 2e-5
+    assert np.abs(out["pred_keypoints_3d"] - g["pred_keypoints_3d"]).max() < 2e-5
+
+
+def test_ddpm50_fp64_trace(golden_dir):
+    """Full 50-step DDPM chain (p_sample, no guidance), hid 256 x 2 blocks, 3 images."""
+    g, out, x0s, xts = _run_case(golden_dir, "ddpm_T50_hid256_f64", np.float64)
+    assert list(g["trace_t_orig"]) == list(range(49, -1, -1))
+    # exp(0.5*log_var) is evaluated in fp32 by torch and by numpy: 1-ulp libm differences times the noise
+    assert np.abs(x0s - g["trace_x0"]).max() < 1e-6
+    assert np.abs(xts - g["trace_x_t"]).max() < 2e-6
+
+
+def test_encoders_match_reference_features(golden_dir):
+    g = np.load(os.path.join(golden_dir, "ddim5_T50_hid1024_f64.npz"))
+    smpl = synth.make_smpl_model(0)
+    sd = synth.make_state_dict(0, init_betas=smpl["init_betas"])
+    c = encoders.conditioning(sd, synth.make_batch(0, 2), np.float64)
+    assert np.abs(c["img_feats"] - g["img_feats"]).max() < 1e-10
+    assert np.abs(c["rest_feats"][:, :512] - g["scene_feats"]).max() < 1e-10
+    assert np.abs(c["rest_feats"][:, 512:640] - g["transl_feat"]).max() < 1e-10
