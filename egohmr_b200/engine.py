@@ -176,6 +176,8 @@ class Engine:
     def rot6d_to_rotmat(self, x6):
         n = x6.numel() // 6
         R = torch.empty(n, 3, 3, device=x6.device, dtype=torch.float32)
+        if n == 0:
+            return R
         check(self.lib.ehb_rot6d_to_rotmat(self._h, _dev_ptr(x6), n, _dev_ptr(R), _stream()))
         return R
 

@@ -2,8 +2,9 @@
 
 Tolerances (all absolute, stated where used):
 * the denoiser runs its 8 hidden GEMMs on the fp16 tensor pipe with an error-compensated hi/lo split (~2^-22 relative
-  operand error, DESIGN.md "numerics"); against the float64 reference trace that is a few 1e-6 on pred_x_start
-  (|x0| ~ 1), against 5e-7 for the reference's own fp32-vs-fp64 noise;
+  operand error, DESIGN.md "numerics"); measured against the float64 reference trace: 3.3e-7 on pred_x_start
+  (|x0| ~ 1) after DDIM-5, 2.8e-7 after DDPM-50 — the reference's own fp32-vs-fp64 difference is 4.4e-7 / 4.2e-7;
+  max vertex error 1.8e-3 mm vs float64 (reference fp32: 3.0e-3 mm);
 * SMPL LBS is plain fp32 FFMA: a few 1e-7 m on vertices for a fixed pose;
 * the sampler update is bit-exact given equal inputs.
 """
@@ -18,8 +19,20 @@ from oracle import egohmr as o_egohmr, encoders, gcn, geometry, schedule, smpl a
 
 pytestmark = pytest.mark.gpu
 
-X0_TOL = 2e-5          # max |pred_x_start - float64 reference| (normalised rot6d units, |x0| ~ 1)
-VERT_TOL_M = 2e-5      # max per-vertex error in metres vs the float64 oracle = 0.02 mm
+
+@pytest.fixture(autouse=True, scope="module")
+def _strict_fp32_encoders():
+    """The image encoder is a PyTorch/cuDNN feature provider; torch's default lets cuDNN use TF32 for its
+    convolutions (as it would for the reference on a GPU), which moves pred_x_start by ~1e-5.  Parity against the
+    float64 reference is measured with that switched off."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+X0_TOL = 2e-6          # max |pred_x_start - float64 reference| (normalised rot6d units, |x0| ~ 1); measured 3e-7
+VERT_TOL_M = 2e-5      # max per-vertex error in metres = 0.02 mm; measured 1.8e-3 mm vs float64 (reference fp32: 3.0e-3 mm)
 
 
 @pytest.fixture(scope="module")
@@ -49,7 +62,10 @@ def test_rot6d_golden(golden_dir):
     so = np.load(os.path.join(golden_dir, "small_ops.npz"))
     R = rot6d_to_rotmat(torch.from_numpy(so["rot6d_x"]).cuda(), "diffusion").cpu().numpy()
     assert R.shape == (64 * 24, 3, 3)
-    assert np.abs(R - so["rot6d_R64"]).max() < 5e-7
+    # Gram-Schmidt amplifies fp32 rounding for nearly parallel (a1, a2); the reference's own fp32 run is the yardstick
+    ref_noise = np.abs(so["rot6d_R32"] - so["rot6d_R64"]).max()
+    print(f"rot6d: max|R - ref_f64| = {np.abs(R - so['rot6d_R64']).max():.3e}; reference fp32-vs-fp64 = {ref_noise:.3e}")
+    assert np.abs(R - so["rot6d_R64"]).max() < max(5e-6, 4 * ref_noise)
     RtR = np.einsum("nij,nik->njk", R[1:], R[1:])
     assert np.abs(RtR - np.eye(3)).max() < 1e-5 and np.abs(np.linalg.det(R[1:].astype(np.float64)) - 1).max() < 1e-5
     assert np.isnan(R[0]).sum() == 0   # all-zero 6-D input: eps clamp, no NaN (F.normalize semantics)
@@ -205,8 +221,8 @@ def test_ddpm50_sampling_vs_reference_golden(small, golden_dir):
     d64 = np.abs(out["pred_x_start"].cpu().numpy() - g64["pred_x_start"]).max()
     floor = np.abs(g32["pred_x_start"] - g64["pred_x_start"]).max()
     print(f"DDPM-50 final max|x0 - ref_f64| = {d64:.3e}; reference fp32-vs-fp64 = {floor:.3e}")
-    assert d64 < 5e-5    # 50 chained steps
-    assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < 1e-4
+    assert d64 < 5e-6    # 50 chained steps; measured 2.8e-7
+    assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < 2e-5
 
 
 def test_sample_many_equals_sequential_chains(full):
