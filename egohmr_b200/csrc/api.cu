@@ -134,7 +134,7 @@ struct ehb_ctx {
   int device = 0;
   int num_sms = 0;
   int64_t launches = 0;
-  int gemm_mode = 0;
+  int gemm_mode = 0;   // 0 = tcgen05 CTA-pair kernel, 1 = fp32 FFMA check path, 2 = tcgen05 one-CTA kernel
   float act_scale = 8.f;
 
   // ---- denoiser
@@ -144,7 +144,8 @@ struct ehb_ctx {
     ehb::AdjMix adj;
     DevBuf mod_scaled, mod, bn_scale, bn_shift, w_hl, wcat;
     float w_scale = 1.f;
-    CUtensorMap tmB;
+    CUtensorMap tmB;    // box 256 rows (one-CTA kernel)
+    CUtensorMap tmB2;   // box 128 rows (CTA-pair kernel: each CTA stages half of the B tile)
   };
   std::vector<Hidden*> hidden;
   ehb::AdjMix adj_in, adj_out;
@@ -221,7 +222,8 @@ void ehb_ctx_destroy(ehb_ctx* ctx) {
 
 int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode) {
   if (!ctx) return fail("null ctx");
-  if (gemm_mode != 0 && gemm_mode != 1) return fail("gemm_mode must be 0 (tcgen05) or 1 (fp32 check)");
+  if (gemm_mode < 0 || gemm_mode > 2)
+    return fail("gemm_mode must be 0 (tcgen05 CTA pairs), 1 (fp32 check) or 2 (tcgen05 single CTA)");
   ctx->gemm_mode = gemm_mode;
   return 0;
 }
@@ -327,6 +329,7 @@ int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w) {
     EHB_CUDA(h->bn_scale.upload(sc));
     EHB_CUDA(h->bn_shift.upload(sh));
     if (make_tmap_f16(&h->tmB, h->w_hl.p, C2, C2, 256)) return 1;
+    if (make_tmap_f16(&h->tmB2, h->w_hl.p, C2, C2, 128)) return 1;
   }
 
   // ---- output layer
@@ -430,7 +433,8 @@ int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body) {
   EHB_CUDA(ctx->slot_body.upload(sb));
   EHB_CUDA(ctx->slot_cond.upload(scnd));
   EHB_CUDA(ctx->body_slot.upload(bs));
-  const int n_mtiles = (n_slots + ehb::SLOTS_PER_TILE - 1) / ehb::SLOTS_PER_TILE;
+  // whole CTA-pair tiles: an even number of 128-row tiles (pad tiles hold zeros and are never stored)
+  const int n_mtiles = ((n_slots + ehb::SLOTS_PER_TILE - 1) / ehb::SLOTS_PER_TILE + 1) / 2 * 2;
   const size_t rows = static_cast<size_t>(n_mtiles) * ehb::TILE_ROWS;
   const size_t C = ctx->hid;
   if (n_mtiles != ctx->n_mtiles || !ctx->res.p) {
@@ -470,7 +474,10 @@ static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
   p.write_f32 = second ? 1 : 0;
   p.write_hl = (l != L - 1) ? 1 : 0;
   if (ctx->gemm_mode == 0) {
-    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB, p, ctx->num_sms, stream));
+    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB2, p, ctx->num_sms, 2, stream));
+    ctx->launches += 1;
+  } else if (ctx->gemm_mode == 2) {
+    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB, p, ctx->num_sms, 1, stream));
     ctx->launches += 1;
   } else {
     const size_t rows = static_cast<size_t>(ctx->n_mtiles) * ehb::TILE_ROWS;

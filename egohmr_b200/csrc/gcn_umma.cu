@@ -24,31 +24,43 @@
 namespace ehb {
 namespace {
 
-constexpr int BM = 128;           // rows per tile (5 slots x 24 joints + 8 pad)
+constexpr int BM = 128;           // rows per CTA tile (5 slots x 24 joints + 8 pad)
 constexpr int BN = 256;           // 128 channels of h0 | the same 128 channels of h1
 constexpr int BK = 32;            // fp16 elements per k block = 64 bytes = one SWIZZLE_64B span
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi+lo of both operands = 48 KiB
 constexpr int CHUNK = 32;         // channels per epilogue hand-off
 constexpr int GT_LD = 132;        // padded row length (floats) of the transposed staging tiles
 constexpr int EPI_BYTES = 2 * CHUNK * GT_LD * 4;
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+constexpr int MAX_STAGES = 6;
 // warp roles: 0-3 tcgen05.ld (warp index == TMEM lane quadrant), 4 TMA producer (+ TMEM alloc/dealloc),
-// 5 MMA issuer, 6-10 joint-mix/store.  11 warps keep the per-thread register budget at 168.
-constexpr int NUM_WARPS = 11;
+// 5 MMA issuer, 6-15 joint-mix/store: mix warp w owns slot w%5 and output joints 12*(w/5) .. +11 (lane = channel).
+// Ten mixers (2-3 per SM sub-partition) are what keeps the epilogue faster than the MMAs of the next tile; 16 warps
+// cap the register budget at 128/thread.
+constexpr int NUM_WARPS = 16;
+constexpr int NUM_MIX_WARPS = 10;
+constexpr int NJH = NJ / 2;       // output joints per mix warp
 constexpr int NUM_THREADS = NUM_WARPS * 32;
 constexpr int LD_WARP0 = 0, TMA_WARP = 4, MMA_WARP = 5, MIX_WARP0 = 6;
 constexpr int TMEM_COLS = 512;
 
-static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
+// CTAS = 1: one CTA per 128x256 tile, 4 stages of 48 KiB.
+// CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per 256x256 tile: each CTA stages its own 128 rows of A
+//           and HALF of the B tile, so per-CTA shared-memory fill and L2 traffic drop by a third and the ring is 6
+//           stages of 32 KiB; the leader CTA issues the M=256 MMAs for both, each CTA drains its own TMEM.
+template <int CTAS>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2 / CTAS;            // per CTA
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // hi+lo of both operands
+  static constexpr int STAGES = CTAS == 1 ? 4 : 6;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
+};
 
 struct Barriers {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t tfull[2];
   uint64_t tempty[2];
   uint64_t cfull;
@@ -57,9 +69,14 @@ struct Barriers {
 };
 static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
 
+template <int CTAS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ HiddenLayerParams p) {
+  using C = Cfg<CTAS>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int STAGE_BYTES = C::STAGE_BYTES;
+  constexpr int B_BYTES = C::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -71,7 +88,13 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int KB = p.C / BK;
-  const int total_tiles = p.n_mtiles * p.n_ntiles;
+  const uint32_t rank = CTAS == 1 ? 0u : ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  // work units: a unit is one 128x256 tile (CTAS=1) or one 256x256 pair-tile (CTAS=2)
+  const int n_munits = (p.n_mtiles + CTAS - 1) / CTAS;
+  const int total_units = n_munits * p.n_ntiles;
+  const int unit0 = blockIdx.x / CTAS;
+  const int unit_step = gridDim.x / CTAS;
 
   if (warp == TMA_WARP && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -79,42 +102,60 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   }
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&bars->full[s], 1);
-      ptx::mbar_init(&bars->empty[s], 1);
+      ptx::mbar_init(&bars->full[s], 1);      // the (leader's) producer arms it; both CTAs' bytes are tracked by expect_tx
+      ptx::mbar_init(&bars->empty[s], 1);     // one (multicast) tcgen05.commit
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&bars->tfull[s], 1);
-      ptx::mbar_init(&bars->tempty[s], 4);   // one elected lane of each tcgen05.ld warp
+      ptx::mbar_init(&bars->tempty[s], 4 * CTAS);   // one elected lane of each tcgen05.ld warp of each CTA
     }
     ptx::mbar_init(&bars->cfull, 4 * 32);    // every thread of the tcgen05.ld warps
-    ptx::mbar_init(&bars->cempty, 5 * 32);   // every thread of the mix warps
+    ptx::mbar_init(&bars->cempty, NUM_MIX_WARPS * 32);   // every thread of the mix warps
     ptx::fence_mbar_init();
   }
   if (warp == TMA_WARP) {
-    ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
-    ptx::tmem_relinquish();
+    if (CTAS == 1) {
+      ptx::tmem_alloc(&bars->tmem_base, TMEM_COLS);
+      ptx::tmem_relinquish();
+    } else {
+      ptx::tmem_alloc_2sm(&bars->tmem_base, TMEM_COLS);
+      ptx::tmem_relinquish_2sm();
+    }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync();   // the peer's barriers must be initialised before anything remote touches them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == TMA_WARP) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_ntiles;
-        const int n_tile = tile % p.n_ntiles;
+      for (int u = unit0; u < total_units; u += unit_step) {
+        const int m_tile = (u / p.n_ntiles) * CTAS + static_cast<int>(rank);
+        const int n_tile = u % p.n_ntiles;
+        const int b_row = n_tile * BN + static_cast<int>(rank) * (BN / CTAS);
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* s = stage_base + stage * STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
-          ptx::tma_load_2d(s, &tmA, &bars->full[stage], kb * BK, m_tile * BM);
-          ptx::tma_load_2d(s + A_BYTES, &tmA, &bars->full[stage], p.C + kb * BK, m_tile * BM);
-          ptx::tma_load_2d(s + 2 * A_BYTES, &tmB, &bars->full[stage], kb * BK, n_tile * BN);
-          ptx::tma_load_2d(s + 2 * A_BYTES + B_BYTES, &tmB, &bars->full[stage], p.C + kb * BK, n_tile * BN);
+          if (CTAS == 1) {
+            ptx::mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
+            ptx::tma_load_2d(s, &tmA, &bars->full[stage], kb * BK, m_tile * BM);
+            ptx::tma_load_2d(s + A_BYTES, &tmA, &bars->full[stage], p.C + kb * BK, m_tile * BM);
+            ptx::tma_load_2d(s + 2 * A_BYTES, &tmB, &bars->full[stage], kb * BK, b_row);
+            ptx::tma_load_2d(s + 2 * A_BYTES + B_BYTES, &tmB, &bars->full[stage], p.C + kb * BK, b_row);
+          } else {
+            const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);  // the leader's barrier
+            // only the leader arrives (no fence-carrying remote arrive in the peer's hot loop); the peer's loads may
+            // complete_tx before the leader has armed this phase — the phase cannot complete until the leader arrives
+            if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
+            ptx::tma_load_2d_2sm(s, &tmA, lfull, kb * BK, m_tile * BM);
+            ptx::tma_load_2d_2sm(s + A_BYTES, &tmA, lfull, p.C + kb * BK, m_tile * BM);
+            ptx::tma_load_2d_2sm(s + 2 * A_BYTES, &tmB, lfull, kb * BK, b_row);
+            ptx::tma_load_2d_2sm(s + 2 * A_BYTES + B_BYTES, &tmB, lfull, p.C + kb * BK, b_row);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -124,44 +165,59 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     __syncwarp();
   } else if (warp == MMA_WARP) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BM, BN);
-    int stage = 0;
-    uint32_t phase = 0;
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(&bars->tempty[as], aphase ^ 1);
-      ptx::tc_fence_after_sync();
-      const uint32_t tacc = tmem_base + as * BN;
-      for (int kb = 0; kb < KB; ++kb) {
-        ptx::mbar_wait(&bars->full[stage], phase);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16_f32(BM * CTAS, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int u = unit0; u < total_units; u += unit_step) {
+        if (CTAS == 1) ptx::mbar_wait(&bars->tempty[as], aphase ^ 1);
+        else ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
         ptx::tc_fence_after_sync();
-        if (lane == 0) {
-          const uint32_t sa = ptx::smem_u32(stage_base + stage * STAGE_BYTES);
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&bars->full[stage], phase);
+          ptx::tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t sa = ptx::smem_u32(stage_base + stage * STAGE_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            const uint32_t koff = ks * UMMA_K * 2;
-            const uint64_t a_hi = ptx::make_kmajor_desc<64>(sa + koff);
-            const uint64_t a_lo = ptx::make_kmajor_desc<64>(sa + A_BYTES + koff);
-            const uint64_t b_hi = ptx::make_kmajor_desc<64>(sa + 2 * A_BYTES + koff);
-            const uint64_t b_lo = ptx::make_kmajor_desc<64>(sa + 2 * A_BYTES + B_BYTES + koff);
-            ptx::umma_f16(tacc, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
-            ptx::umma_f16(tacc, a_hi, b_lo, idesc, 1u);
-            ptx::umma_f16(tacc, a_lo, b_hi, idesc, 1u);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint32_t koff = ks * UMMA_K * 2;
+              const uint64_t a_hi = ptx::make_kmajor_desc<64>(sa + koff);
+              const uint64_t a_lo = ptx::make_kmajor_desc<64>(sa + A_BYTES + koff);
+              const uint64_t b_hi = ptx::make_kmajor_desc<64>(sa + 2 * A_BYTES + koff);
+              const uint64_t b_lo = ptx::make_kmajor_desc<64>(sa + 2 * A_BYTES + B_BYTES + koff);
+              const uint32_t first = (kb | ks) != 0 ? 1u : 0u;
+              if (CTAS == 1) {
+                ptx::umma_f16(tacc, a_hi, b_hi, idesc, first);
+                ptx::umma_f16(tacc, a_hi, b_lo, idesc, 1u);
+                ptx::umma_f16(tacc, a_lo, b_hi, idesc, 1u);
+              } else {
+                ptx::umma_f16_2sm(tacc, a_hi, b_hi, idesc, first);
+                ptx::umma_f16_2sm(tacc, a_hi, b_lo, idesc, 1u);
+                ptx::umma_f16_2sm(tacc, a_lo, b_hi, idesc, 1u);
+              }
+            }
+            if (CTAS == 1) {
+              ptx::umma_commit(&bars->empty[stage]);
+              if (kb == KB - 1) ptx::umma_commit(&bars->tfull[as]);
+            } else {
+              ptx::umma_commit_2sm_mc(&bars->empty[stage], 0b11);
+              if (kb == KB - 1) ptx::umma_commit_2sm_mc(&bars->tfull[as], 0b11);
+            }
           }
-          ptx::umma_commit(&bars->empty[stage]);
-          if (kb == KB - 1) ptx::umma_commit(&bars->tfull[as]);
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
         }
-      }
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
       }
     }
   } else if (warp < LD_WARP0 + 4) {
@@ -174,39 +230,50 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     int as = 0;
     uint32_t aphase = 0;
     uint32_t chunk_it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_ntiles;
+    for (int u = unit0; u < total_units; u += unit_step) {
+      const int n_tile = u % p.n_ntiles;
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after_sync();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 2 / CHUNK; ++ch, ++chunk_it) {
-        float h0[32], h1[32], m[32];
-        ptx::tmem_ld_32x32b_x32(trow + ch * CHUNK, h0);
-        ptx::tmem_ld_32x32b_x32(trow + BN / 2 + ch * CHUNK, h1);
-        const float4* mp = reinterpret_cast<const float4*>(p.mod + static_cast<size_t>(j) * p.C + n_tile * (BN / 2) +
-                                                            ch * CHUNK);
+        const float* mrow = p.mod + static_cast<size_t>(j) * p.C + n_tile * (BN / 2) + ch * CHUNK;
+        float h0[16], h1[16], m[16], h0b[16], h1b[16];
+        ptx::tmem_ld_32x32b_x16(trow + ch * CHUNK, h0);
+        ptx::tmem_ld_32x32b_x16(trow + BN / 2 + ch * CHUNK, h1);
+        ptx::tmem_ld_32x32b_x16(trow + ch * CHUNK + 16, h0b);
+        ptx::tmem_ld_32x32b_x16(trow + BN / 2 + ch * CHUNK + 16, h1b);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const float4 t = __ldg(mp + v);
-          m[4 * v + 0] = t.x;
-          m[4 * v + 1] = t.y;
-          m[4 * v + 2] = t.z;
-          m[4 * v + 3] = t.w;
+        for (int v = 0; v < 4; ++v) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(mrow) + v);
+          m[4 * v + 0] = t.x; m[4 * v + 1] = t.y; m[4 * v + 2] = t.z; m[4 * v + 3] = t.w;
         }
         ptx::tmem_ld_wait();
         if (ch == BN / 2 / CHUNK - 1) {
-          // accumulator fully drained: hand the TMEM stage back to the MMA warp
+          // accumulator fully drained: hand the TMEM stage back to the (leader's) MMA warp
           ptx::tc_fence_before_sync();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars->tempty[as]);
+          if (lane == 0) {
+            if (CTAS == 1 || leader) ptx::mbar_arrive(&bars->tempty[as]);
+            else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tempty[as]), 0));
+          }
         }
         ptx::mbar_wait(&bars->cempty, (chunk_it & 1) ^ 1);
         if (valid_row) {
 #pragma unroll
-          for (int c = 0; c < CHUNK; ++c) {
+          for (int c = 0; c < 16; ++c) {
             G_T[c * GT_LD + r] = m[c] * h1[c];
             D_T[c * GT_LD + r] = adiag * (m[c] * h0[c]);
+          }
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(mrow) + 4 + v);
+            m[4 * v + 0] = t.x; m[4 * v + 1] = t.y; m[4 * v + 2] = t.z; m[4 * v + 3] = t.w;
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            G_T[(16 + c) * GT_LD + r] = m[c] * h1b[c];
+            D_T[(16 + c) * GT_LD + r] = adiag * (m[c] * h0b[c]);
           }
         }
         ptx::mbar_arrive(&bars->cfull);
@@ -218,60 +285,76 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
   } else if (warp >= MIX_WARP0) {
     // ------------------------------------------------------------------ joint mix + BN + ReLU (+res) + store
-    const int w = warp - MIX_WARP0;  // slot within the tile
+    const int w = (warp - MIX_WARP0) % SLOTS_PER_TILE;   // slot within the tile
+    const int j0 = ((warp - MIX_WARP0) / SLOTS_PER_TILE) * NJH;  // first output joint of this warp
     uint32_t chunk_it = 0;
     float amax = 0.f;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_ntiles;
-      const int n_tile = tile % p.n_ntiles;
+    for (int u = unit0; u < total_units; u += unit_step) {
+      const int m_tile = (u / p.n_ntiles) * CTAS + static_cast<int>(rank);
+      const int n_tile = u % p.n_ntiles;
       const bool valid = (m_tile * SLOTS_PER_TILE + w) < p.n_slots;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 2 / CHUNK; ++ch, ++chunk_it) {
-        float g[NJ], y[NJ], rsd[NJ];
+        float g[NJ], y[NJH], rsd[NJH];
         const int c = n_tile * (BN / 2) + ch * CHUNK + lane;
-        const size_t row0 = static_cast<size_t>(m_tile) * BM + NJ * w;
+        const size_t row0 = static_cast<size_t>(m_tile) * BM + NJ * w + j0;
         // residual rows are fetched before the hand-off wait: independent loads in flight, latency hidden
+        const float* rp = p.res + row0 * p.C + c;
         if (p.add_res && valid) {
 #pragma unroll
-          for (int jj = 0; jj < NJ; ++jj) rsd[jj] = __ldcg(p.res + (row0 + jj) * p.C + c);
+          for (int jj = 0; jj < NJH; ++jj) rsd[jj] = __ldcg(rp + static_cast<size_t>(jj) * p.C);
         } else {
 #pragma unroll
-          for (int jj = 0; jj < NJ; ++jj) rsd[jj] = 0.f;
+          for (int jj = 0; jj < NJH; ++jj) rsd[jj] = 0.f;
         }
         ptx::mbar_wait(&bars->cfull, chunk_it & 1);
         {
           const float4* gp = reinterpret_cast<const float4*>(G_T + lane * GT_LD + NJ * w);
-          const float4* dp = reinterpret_cast<const float4*>(D_T + lane * GT_LD + NJ * w);
+          const float4* dp = reinterpret_cast<const float4*>(D_T + lane * GT_LD + NJ * w + j0);
 #pragma unroll
           for (int v = 0; v < NJ / 4; ++v) {
             const float4 a = gp[v];
-            const float4 b = dp[v];
             g[4 * v + 0] = a.x; g[4 * v + 1] = a.y; g[4 * v + 2] = a.z; g[4 * v + 3] = a.w;
+          }
+#pragma unroll
+          for (int v = 0; v < NJH / 4; ++v) {
+            const float4 b = dp[v];
             y[4 * v + 0] = b.x; y[4 * v + 1] = b.y; y[4 * v + 2] = b.z; y[4 * v + 3] = b.w;
           }
         }
         ptx::mbar_arrive(&bars->cempty);
         if (!valid) continue;
+        if (j0 == 0) {
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) {
-          float acc = y[jj];
+          for (int jj = 0; jj < NJH; ++jj) {
+            float acc = y[jj];
 #pragma unroll
-          for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[jj][i], g[i], acc);
-          y[jj] = acc;
+            for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[jj][i], g[i], acc);
+            y[jj] = acc;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < NJH; ++jj) {
+            float acc = y[jj];
+#pragma unroll
+            for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[NJH + jj][i], g[i], acc);
+            y[jj] = acc;
+          }
         }
         const float sc = __ldg(p.bn_scale + c);
         const float sh = __ldg(p.bn_shift + c);
+        float* fp = p.res + row0 * p.C + c;
+        __half* hp = p.out_hl + row0 * (2 * static_cast<size_t>(p.C)) + c;
 #pragma unroll
-        for (int jj = 0; jj < NJ; ++jj) {
-          const size_t row = row0 + jj;
+        for (int jj = 0; jj < NJH; ++jj) {
           const float v = fmaxf(fmaf(y[jj], sc, sh), 0.f) + rsd[jj];
-          if (p.write_f32) p.res[row * p.C + c] = v;
+          if (p.write_f32) fp[static_cast<size_t>(jj) * p.C] = v;
           if (p.write_hl) {
             const float sv = v * p.act_scale;
             const __half hi = __float2half_rn(sv);
             const __half lo = __float2half_rn(sv - __half2float(hi));
-            p.out_hl[row * (2 * p.C) + c] = hi;
-            p.out_hl[row * (2 * p.C) + p.C + c] = lo;
+            hp[static_cast<size_t>(jj) * 2 * p.C] = hi;
+            hp[static_cast<size_t>(jj) * 2 * p.C + p.C] = lo;
             amax = fmaxf(amax, fabsf(sv));
           }
         }
@@ -282,31 +365,54 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync();   // the peer may still be reading this CTA's operands / signalling its barriers
   if (warp == TMA_WARP) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    else ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
 }  // namespace
 
-size_t gcn_hidden_umma_smem_bytes() { return SMEM_BYTES; }
+size_t gcn_hidden_umma_smem_bytes() { return Cfg<2>::SMEM_BYTES; }
 
-cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
-                                   int num_sms, cudaStream_t stream) {
+template <int CTAS>
+static cudaError_t launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p, int num_sms,
+                               cudaStream_t stream) {
   static bool attr_set = false;
+  auto kern = gcn_hidden_umma_kernel<CTAS>;
   if (!attr_set) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gcn_hidden_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<CTAS>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
+  const int units = ((p.n_mtiles + CTAS - 1) / CTAS) * p.n_ntiles;
+  if (units == 0) return cudaSuccess;
+  int grid = units * CTAS < num_sms ? units * CTAS : (num_sms / CTAS) * CTAS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CTAS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
+}
+
+cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
+                                   int num_sms, int ctas, cudaStream_t stream) {
   if (p.C % 128 != 0 || p.n_ntiles != p.C / 128) return cudaErrorInvalidValue;
-  const int total = p.n_mtiles * p.n_ntiles;
-  if (total == 0) return cudaSuccess;
-  const int grid = total < num_sms ? total : num_sms;
-  gcn_hidden_umma_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  if (ctas == 2) {
+    if (p.n_mtiles % 2 != 0) return cudaErrorInvalidValue;  // the activation buffers are padded to whole pair-tiles
+    return launch_impl<2>(tmA, tmB, p, num_sms, stream);
+  }
+  return launch_impl<1>(tmA, tmB, p, num_sms, stream);
 }
 
 }  // namespace ehb

@@ -36,8 +36,10 @@ struct HiddenLayerParams {
 };
 
 // launchers (gcn_umma.cu / gcn_simt.cu / smpl_lbs.cu)
+// ctas = 1: one CTA per 128x256 tile (tmB box = 256 rows); ctas = 2: CTA pairs, tcgen05 cta_group::2 (tmB box = 128
+// rows, n_mtiles even).
 cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
-                                   int num_sms, cudaStream_t stream);
+                                   int num_sms, int ctas, cudaStream_t stream);
 size_t gcn_hidden_umma_smem_bytes();
 
 // fp32 SIMT check path for the same layer: H = X * Wcat via sgemm, then the identical epilogue.

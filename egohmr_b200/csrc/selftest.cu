@@ -238,8 +238,11 @@ int main(int argc, char** argv) {
   if (nblk == 1) spot_check_layer(ctx, 2, layers[2], adj.data(), C, 2 * B, 8.f, "fp32 check path");
   std::printf("check path: overflow=%d  x0[0..3] = %g %g %g %g\n", ehb_check_overflow(ctx, nullptr), ref_x0[0],
               ref_x0[1], ref_x0[2], ref_x0[3]);
+  bool all_ok = true;
+  for (int gm : {2, 0}) {
+  std::printf("---- tcgen05 gemm_mode=%d (%s)\n", gm, gm == 0 ? "CTA pairs, cta_group::2" : "single CTA");
   // tcgen05 path
-  CK(ehb_debug_set_gemm_mode(ctx, 0));
+  CK(ehb_debug_set_gemm_mode(ctx, gm));
   CU(cudaMemset(d_oc, 0, nx * 4));
   CU(cudaMemset(d_ou, 0, nx * 4));
   CK(ehb_denoise_step_debug(ctx, 2, d_x, nullptr, nullptr, d_xp, d_x0, d_oc, d_ou, nullptr));
@@ -301,7 +304,8 @@ int main(int argc, char** argv) {
   const double dp = maxabs_diff(got_xp, ref_xp, &r);
   std::printf("max|umma - fp32| x_prev     = %.3e (max|ref| %.3e)\n", dp, r);
   const bool ok = dc < 2e-4 * (1 + r) && du < 2e-4 * (1 + r) && std::isfinite(dc) && std::isfinite(du);
-  std::printf("SELFTEST %s\n", ok ? "PASS" : "FAIL");
+  std::printf("SELFTEST gemm_mode=%d %s\n", gm, ok ? "PASS" : "FAIL");
+  all_ok = all_ok && ok;
 
   // ---- timing
   for (int layer : {1, 2}) {
@@ -327,6 +331,7 @@ int main(int argc, char** argv) {
     cudaEventElapsedTime(&ms, e0, e1);
     std::printf("full denoise step: %.3f ms  (%.0f bodies/s at 5 steps)\n", ms / it, B / (5.0 * ms / it * 1e-3));
   }
+  }
   ehb_ctx_destroy(ctx);
-  return ok ? 0 : 1;
+  return all_ok ? 0 : 1;
 }

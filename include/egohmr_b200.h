@@ -135,7 +135,8 @@ int ehb_decode(ehb_ctx* ctx, const float* x0, const float* betas, float* pose6d,
 int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, const float* transl, float* verts,
                      float* joints, void* stream);
 
-/* Diagnostics.  gemm_mode 0 = tcgen05 fp16x3 kernel (product path), 1 = fp32 FFMA check path (tests only). */
+/* Diagnostics.  gemm_mode 0 = tcgen05 fp16x3 kernel on CTA pairs (cta_group::2, product path), 1 = fp32 FFMA check
+ * path (tests only), 2 = tcgen05 fp16x3 kernel on single CTAs (cta_group::1, bring-up comparison). */
 int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);
 /* Returns 1 (and clears it) if any fp16 operand overflowed since the last call; synchronises `stream`. */
 int ehb_check_overflow(ehb_ctx* ctx, void* stream);

@@ -12,6 +12,8 @@ from egohmr_b200.testing import build_model, torch_batch  # noqa: E402
 n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 model, diffusion, *_ = build_model(1024, 4, T=50, respacing="ddim5")
+model._sync_engine()
+model.engine.set_gemm_mode(int(os.environ.get("EHB_GEMM_MODE", "0")))
 batch = torch_batch(synth.make_batch(100, n_img), "cuda:0")
 for _ in range(3):
     model._cond_key = None
