@@ -174,14 +174,11 @@ def run_b200(args):
         model._cond_key = None   # a new batch every step: the encoders run every time
         return diffusion.sample_many(model, batch, S, RESPACING)
 
+    from egohmr_b200 import sharding
+
     def gather_results(out):
-        packed = torch.cat([out["pred_smpl_params"]["global_orient"].reshape(B, 9), out["pred_smpl_params"]["body_pose"].reshape(B, 207),
-                            out["pred_smpl_params"]["betas"]], dim=1).contiguous()     # 226 floats = 904 B per body
-        if world == 1:
-            return packed
-        full = torch.empty(world * B, packed.shape[1], device=dev)
-        dist.all_gather_into_tensor(full, packed)
-        return full
+        # 226 floats = 904 B per body; one all_gather per sampling pass, no per-step communication
+        return sharding.gather_results(sharding.pack_results(out), n_img * world, S)
 
     def barrier():
         if world > 1:
