@@ -172,7 +172,7 @@ struct ehb_ctx {
   bool smpl_loaded = false;
   ehb::SmplDevice smpl{};
   DevBuf s_vt, s_sd, s_pd, s_w, s_jt, s_jsd, s_ex;
-  DevBuf sc_R, sc_A, sc_j24, sc_pf, sc_p6;
+  DevBuf sc_R, sc_A, sc_j24, sc_pf, sc_p6, sc_dvp, sc_dA, sc_dpf;
 
   DevBuf overflow;
 
@@ -706,6 +706,44 @@ int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, co
   if (n <= 0) return fail("ehb_smpl_forward: n must be positive");
   EHB_CUDA(cudaSetDevice(ctx->device));
   return smpl_run(ctx, n, R, betas, nullptr, transl, verts, joints, static_cast<cudaStream_t>(stream_));
+}
+
+int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream_) {
+  if (!ctx || !R || !aa) return fail("ehb_rotmat_to_angle_axis: null argument");
+  if (n < 0) return fail("ehb_rotmat_to_angle_axis: negative n");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_rotmat_to_aa(R, aa, n, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += n > 0;
+  return 0;
+}
+
+int ehb_smpl_backward(ehb_ctx* ctx, const float* x_t, const float* betas, const float* g_verts, const float* g_joints,
+                      const float* g_aa, float* grad_x, void* stream_) {
+  if (!ctx || !x_t || !betas || !grad_x) return fail("ehb_smpl_backward: null argument");
+  if (ctx->n_bodies <= 0) return fail("ehb_smpl_backward: call ehb_set_bodies first");
+  if (!ctx->norm_set || !ctx->smpl_loaded) return fail("ehb_smpl_backward: call ehb_set_norm and ehb_smpl_load first");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int n = ctx->n_bodies;
+  const size_t V = ctx->smpl.V;
+  EHB_CUDA(ctx->sc_R.ensure(static_cast<size_t>(n) * ehb::NJ * 9 * sizeof(float)));
+  EHB_CUDA(ctx->sc_A.ensure(static_cast<size_t>(n) * ehb::NJ * 12 * sizeof(float)));
+  EHB_CUDA(ctx->sc_j24.ensure(static_cast<size_t>(n) * ehb::NJ * 3 * sizeof(float)));
+  EHB_CUDA(ctx->sc_pf.ensure(static_cast<size_t>(n) * 207 * sizeof(float)));
+  EHB_CUDA(ctx->sc_dvp.ensure(static_cast<size_t>(n) * V * 3 * sizeof(float)));
+  EHB_CUDA(ctx->sc_dA.ensure(static_cast<size_t>(n) * ehb::NJ * 12 * sizeof(float)));
+  EHB_CUDA(ctx->sc_dpf.ensure(static_cast<size_t>(n) * 207 * sizeof(float)));
+  const int32_t* idx = ctx->img_of_body.as<int32_t>();
+  // forward products for this x (rotations, skinning transforms, pose feature)
+  EHB_CUDA(ehb::launch_rot6d(x_t, ctx->mean.as<float>(), ctx->std_.as<float>(), ctx->sc_R.as<float>(), n, stream));
+  EHB_CUDA(ehb::launch_smpl_pose(ctx->smpl, ctx->sc_R.as<float>(), betas, idx, ctx->sc_A.as<float>(),
+                                 ctx->sc_j24.as<float>(), ctx->sc_pf.as<float>(), n, stream));
+  EHB_CUDA(ehb::launch_smpl_backward(ctx->smpl, x_t, ctx->mean.as<float>(), ctx->std_.as<float>(), betas, idx,
+                                     ctx->sc_A.as<float>(), ctx->sc_pf.as<float>(), g_verts, g_joints, g_aa,
+                                     ctx->sc_dvp.as<float>(), ctx->sc_dA.as<float>(), ctx->sc_dpf.as<float>(), grad_x, n,
+                                     stream));
+  ctx->launches += 5;
+  return 0;
 }
 
 int ehb_decode(ehb_ctx* ctx, const float* x0, const float* betas, float* pose6d, float* R, float* verts, float* joints,

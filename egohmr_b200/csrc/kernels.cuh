@@ -136,4 +136,14 @@ cudaError_t launch_smpl_skin(const SmplDevice& m, const float* betas, const int3
 cudaError_t launch_smpl_joints(const SmplDevice& m, const float* joints24, const float* verts, const float* transl,
                                float* joints /*[B][24+n_extra][3]*/, int n_bodies, cudaStream_t stream);
 
+// ---- guidance backward (smpl_bwd.cu)
+cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, cudaStream_t stream);
+// dL/dx [B][144] from dL/dverts [B][V][3], dL/djoints [B][24+E][3], dL/dfull_pose_aa [B][24][3] (each may be null).
+// A / posefeat: forward products of launch_smpl_pose for the same x; d_vposed [B][V][3], dA [B][24][12], d_pf [B][207]
+// are scratch.
+cudaError_t launch_smpl_backward(const SmplDevice& m, const float* x, const float* mean, const float* std_,
+                                 const float* betas, const int32_t* beta_index, const float* A, const float* posefeat,
+                                 const float* g_verts, const float* g_joints, const float* g_aa, float* d_vposed,
+                                 float* dA, float* d_pf, float* grad_x, int n_bodies, cudaStream_t stream);
+
 }  // namespace ehb

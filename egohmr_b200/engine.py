@@ -181,6 +181,21 @@ class Engine:
         check(self.lib.ehb_rot6d_to_rotmat(self._h, _dev_ptr(x6), n, _dev_ptr(R), _stream()))
         return R
 
+    def rotmat_to_angle_axis(self, R):
+        n = R.numel() // 9
+        aa = torch.empty(n, 3, device=R.device, dtype=torch.float32)
+        if n:
+            check(self.lib.ehb_rotmat_to_angle_axis(self._h, _dev_ptr(R), n, _dev_ptr(aa), _stream()))
+        return aa
+
+    def smpl_backward(self, x_t, betas, g_verts=None, g_joints=None, g_aa=None):
+        """dL/dx_t [B,144] for the bodies of set_bodies (guide_coll's autograd.grad, egohmr.py:562)."""
+        grad = torch.empty_like(x_t)
+        check(self.lib.ehb_smpl_backward(self._h, _dev_ptr(x_t), _dev_ptr(betas), _dev_ptr(g_verts, allow_none=True),
+                                         _dev_ptr(g_joints, allow_none=True), _dev_ptr(g_aa, allow_none=True),
+                                         _dev_ptr(grad), _stream()))
+        return grad
+
     # ------------------------------------------------------------------ diagnostics
     def launch_count(self):
         return int(self.lib.ehb_launch_count(self._h))

@@ -317,12 +317,79 @@ class EgoHMR(nn.Module):
         self._temb_key = None  # the sampler's table must be re-uploaded after a stand-alone forward
         return self.assemble_outputs(batch, x0, cond)
 
-    # ------------------------------------------------------------------ collision hooks (boundary only)
-    def guide_coll(self, batch, output, t, compute_grad="x_t"):
-        raise NotImplementedError("collision-guided sampling: native LBS backward (K6) is scheduled after K1-K5")
+    # ------------------------------------------------------------------ collision guidance / evaluation
+    UPPER_BODY = [0, 3, 6, 9, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23]  # egohmr.py:567
 
+    def _smpl_state(self, x):
+        """x (normalised rot6d) -> vertices, joints, axis-angle full pose, exactly what guide_coll / eval_coll hand to
+        the collision model (egohmr.py:528-540, 492-495)."""
+        cond = self._cond
+        _, R, verts, joints = self.engine.decode(x, cond["betas_img"], want_smpl=True)
+        aa = self.engine.rotmat_to_angle_axis(R.reshape(-1, 3, 3)).reshape(x.shape[0], -1)
+        return verts, joints, aa
+
+    def _crop_scene(self, verts_i, img_index):
+        """Scene points of the body's image inside the body's bounding box (egohmr.py:550-554)."""
+        pts = self.scene_pcd_verts[[img_index]]
+        bb_min = verts_i.min(1).values.reshape(1, 3).detach()
+        bb_max = verts_i.max(1).values.reshape(1, 3).detach()
+        inds = (pts >= bb_min).all(-1) & (pts <= bb_max).all(-1)
+        return pts, inds
+
+    def guide_coll(self, batch, output, t, compute_grad="x_t"):
+        """EgoHMR.guide_coll (egohmr.py:517-570): gradient of -mean(collision loss) w.r.t. x_t, leg joints only.
+        Forward and backward through de-normalise / rot6d / SMPL / axis-angle run in the CUDA library; only the
+        pluggable collision term itself is differentiated by autograd, w.r.t. the three tensors it receives."""
+        if self.collision_model is None:
+            raise RuntimeError("guide_coll needs a collision model with COAP's collision_loss() (pass collision_model=...)")
+        x_t = batch["x_t"] if compute_grad == "x_t" else output["pred_x_start"]
+        x = x_t.detach().float().contiguous()
+        B = x.shape[0]
+        cond = self._cond
+        if cond is None or self.engine.n_bodies != B:
+            cond = self.prepare(batch, num_samples=1)
+        verts, joints, aa = self._smpl_state(x)
+        idx = cond["img_of_body"].tolist()
+        v = verts.detach().requires_grad_()
+        j = joints.detach().requires_grad_()
+        fp = aa.detach().requires_grad_()
+        with torch.enable_grad():
+            losses = torch.zeros(B, device=x.device)
+            for i in range(B):  # the reference evaluates the collision model body by body (:545-559)
+                pts, inds = self._crop_scene(v[[i]], idx[i])
+                if inds.any():
+                    so = smpl_mod.SMPLOutput(vertices=v[[i]], joints=j[[i]], full_pose=fp[[i]])
+                    losses[i] = self.collision_model.collision_loss(pts[inds].unsqueeze(0), so, ret_collision_mask=None)
+            if int((losses == 0).sum()) >= B:
+                return torch.zeros(B, 144, device=x.device)
+            gv, gj, ga = torch.autograd.grad([-losses.mean()], [v, j, fp], allow_unused=True)
+        c = lambda g: None if g is None else g.float().contiguous()
+        grad = self.engine.smpl_backward(x, cond["betas_img"], c(gv), c(gj), c(ga)).reshape(-1, 24, 6)
+        grad[:, 3:] = grad[:, 3:] * 2            # :564-565
+        grad[:, self.UPPER_BODY] = 0             # :567
+        return grad.reshape(-1, 144)
+
+    @torch.no_grad()
     def eval_coll(self, output):
-        raise NotImplementedError("eval_coll needs a collision model with COAP's query() (SURVEY.md 2 #10)")
+        """EgoHMR.eval_coll (egohmr.py:487-514): fraction of scene points the collision model marks as inside."""
+        if self.collision_model is None:
+            raise RuntimeError("eval_coll needs a collision model with COAP's query() (pass collision_model=...)")
+        p = output["pred_smpl_params"]
+        B = p["body_pose"].shape[0]
+        R = torch.cat([p["global_orient"].reshape(B, 1, 3, 3), p["body_pose"].reshape(B, 23, 3, 3)], dim=1).float().contiguous()
+        verts, joints = self.engine.smpl_forward(R, p["betas"].float().contiguous())
+        aa = self.engine.rotmat_to_angle_axis(R.reshape(-1, 3, 3)).reshape(B, -1)
+        idx = self._cond["img_of_body"].tolist() if self._cond is not None and len(self._cond["img_of_body"]) == B else list(range(B))
+        ratios = []
+        for i in range(B):
+            pts, inds = self._crop_scene(verts[[i]], idx[i])
+            if inds.any():
+                so = smpl_mod.SMPLOutput(vertices=verts[[i]].clone(), joints=joints[[i]].clone(), full_pose=aa[[i]].clone())
+                occ = self.collision_model.query(pts[inds].unsqueeze(0), so)
+                ratios.append(((occ > 0.5).sum() / self.scene_pcd_verts.shape[1]).item())
+            else:
+                ratios.append(0.0)
+        return ratios
 
     def compute_loss(self, batch, output, cur_epoch=0):
         raise NotImplementedError("validation losses need ground-truth keys and are outside the sampling hot path; "

@@ -135,6 +135,17 @@ int ehb_decode(ehb_ctx* ctx, const float* x0, const float* betas, float* pose6d,
 int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, const float* transl, float* verts,
                      float* joints, void* stream);
 
+/* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
+ * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
+int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);
+
+/* Backward of egohmr.py:528-540 (x_t*std+mean -> rot6d -> SMPL -> axis-angle), i.e. what torch.autograd.grad computes in
+ * guide_coll (:562): given g_verts [n_bodies][V][3], g_joints [n_bodies][45][3], g_aa [n_bodies][24][3] (any may be
+ * NULL = zero) for the bodies of ehb_set_bodies, writes grad_x [n_bodies][144].  Like the reference (which rebinds x_t to
+ * x_t*std+mean before autograd.grad, :523-528,562) the gradient is w.r.t. the de-normalised pose.  betas [n_img][n_betas]. */
+int ehb_smpl_backward(ehb_ctx* ctx, const float* x_t, const float* betas, const float* g_verts, const float* g_joints,
+                      const float* g_aa, float* grad_x, void* stream);
+
 /* Diagnostics.  gemm_mode 0 = tcgen05 fp16x3 kernel on CTA pairs (cta_group::2, product path), 1 = fp32 FFMA check
  * path (tests only), 2 = tcgen05 fp16x3 kernel on single CTAs (cta_group::1, bring-up comparison). */
 int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);

@@ -76,7 +76,7 @@ def build_reference(hid, n_blocks, dtype, seed=0):
     return model, mean, std
 
 
-def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0):
+def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0, guided=False):
     from diffusion.model_util import create_gaussian_diffusion
     import diffusion.gaussian_diffusion as gd
     model, mean, std = build_reference(hid, n_blocks, dtype, seed)
@@ -110,10 +110,10 @@ def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0):
     old_randn, old_randn_like = torch.randn, torch.randn_like
     torch.randn, torch.randn_like = feed.randn, feed.randn_like
     try:
-        with torch.no_grad():
+        with torch.no_grad():   # the reference re-enables grad inside guide_coll (egohmr.py:518)
             out = diffusion.val_losses(model=Wrapped(model), batch=batch, shape=[n_img, 144], progress=False,
                                        clip_denoised=False, cur_epoch=0, timestep_respacing=respacing,
-                                       cond_fn_with_grad=False, cond_grad_weight=2.0, compute_loss=False)
+                                       cond_fn_with_grad=guided, cond_grad_weight=2.0, compute_loss=False)
     finally:
         torch.randn, torch.randn_like = old_randn, old_randn_like
     g = lambda t: t.detach().numpy()
@@ -135,6 +135,25 @@ def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0):
         rec["transl_feat"] = g(model.transl_enc(batch["smpl_params"]["transl"]))
     np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
     print("wrote", name, {k: getattr(v, "shape", v) for k, v in rec.items() if k in ("trace_x0", "pred_vertices")})
+
+
+def guide_case(name, dtype, n_img=3, seed=0):
+    """EgoHMR.guide_coll (egohmr.py:517-570) on a fixed x_t: the gradient the guided sampler adds to the mean."""
+    model, mean, std = build_reference(256, 2, dtype, seed)
+    batch = to_torch(synth.make_batch(seed, n_img), dtype)
+    rng = np.random.default_rng(31)
+    x_t = (0.7 * rng.normal(0, 1, (n_img, 144))).astype(np.float32)
+    batch["x_t"] = torch.from_numpy(x_t).to(dtype)
+    t = torch.tensor([8] * n_img)
+    with torch.no_grad():
+        out = model(batch, t)          # sets model.scene_pcd_verts and yields the betas guide_coll reads
+        grad = model.guide_coll(batch, out, t, compute_grad="x_t")
+        ratios = model.eval_coll(out)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), x_t=x_t, grad=grad.detach().numpy(),
+                        betas=out["pred_smpl_params"]["betas"].detach().numpy(), coll_ratio=np.array(ratios),
+                        pred_x_start=out["pred_x_start"].detach().numpy())
+    print("wrote", name, "max|grad| =", float(grad.abs().max()), "nonzero joints:",
+          sorted(set(np.nonzero(grad.detach().numpy().reshape(n_img, 24, 6).any(axis=(0, 2)))[0].tolist())), "coll", ratios)
 
 
 def schedule_tables():
@@ -189,3 +208,7 @@ if __name__ == "__main__":
     run_case("ddim5_T50_hid1024_f64", 50, "ddim5", 1024, 4, 2, torch.float64)
     run_case("ddpm_T50_hid256_f32", 50, "", 256, 2, 3, torch.float32)
     run_case("ddpm_T50_hid256_f64", 50, "", 256, 2, 3, torch.float64)
+    guide_case("guide_grad_f32", torch.float32)
+    guide_case("guide_grad_f64", torch.float64)
+    run_case("ddpm_guided_T100_hid256_f32", 100, "", 256, 2, 3, torch.float32, guided=True)
+    run_case("ddpm_guided_T100_hid256_f64", 100, "", 256, 2, 3, torch.float64, guided=True)

@@ -92,29 +92,7 @@ class TorchSMPL(nn.Module):
                           global_orient=global_orient, body_pose=body_pose)
 
 
-class SyntheticCollision:
-    """COAP-signature stand-in: a smooth differentiable penalty that is positive when scene points
-    come close to the body's joints.  ``collision_loss(points[1,n,3], smpl_output, ret_collision_mask=None) -> scalar``,
-    ``query(points[1,n,3], smpl_output) -> occupancy[1,n]``."""
-
-    radius = 0.25
-
-    def eval(self):
-        return self
-
-    def parameters(self):
-        return []
-
-    def _occ(self, points, smpl_output):
-        j = smpl_output.joints[:, :24]  # [1,24,3]
-        d2 = ((points[:, :, None, :] - j[:, None, :, :]) ** 2).sum(-1)  # [1,n,24]
-        return torch.exp(-d2 / (2 * self.radius ** 2)).max(dim=-1).values  # [1,n]
-
-    def collision_loss(self, points, smpl_output, ret_collision_mask=None):
-        return self._occ(points, smpl_output).mean()
-
-    def query(self, points, smpl_output):
-        return self._occ(points, smpl_output)
+from egohmr_b200.testing import SyntheticCollision  # noqa: E402  (the one collision stand-in, shared by both sides)
 
 
 def make_cfg():

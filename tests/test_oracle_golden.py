@@ -105,3 +105,56 @@ def test_encoders_match_reference_features(golden_dir):
     assert np.abs(c["img_feats"] - g["img_feats"]).max() < 1e-10
     assert np.abs(c["rest_feats"][:, :512] - g["scene_feats"]).max() < 1e-10
     assert np.abs(c["rest_feats"][:, 512:640] - g["transl_feat"]).max() < 1e-10
+
+
+def test_guide_coll_gradient_golden(golden_dir):
+    """EgoHMR.guide_coll with the shared synthetic collision term: the oracle's autograd restatement vs the reference."""
+    from egohmr_b200.testing import SyntheticCollision
+    from oracle import guidance
+    g = np.load(os.path.join(golden_dir, "guide_grad_f64.npz"))
+    sm = synth.make_smpl_model(0)
+    b = synth.make_batch(0, 3)
+    mean, std = synth.body_rep_stats(0)
+    pts = b["scene_pcd_verts_full"] - b["smpl_params"]["transl"][:, None]
+    gr = guidance.guide_coll(sm, SyntheticCollision(), g["x_t"], g["betas"], pts, mean, std)
+    assert np.abs(g["grad"]).max() > 1e-3
+    assert np.abs(gr - g["grad"]).max() < 2e-8        # the reference runs SMPL in fp32 (egohmr.py:537 casts .float())
+    nz = sorted(set(np.nonzero(gr.reshape(3, 24, 6).any(axis=(0, 2)))[0].tolist()))
+    assert nz == [1, 2, 4, 5, 7, 8, 10, 11]            # only leg joints survive (egohmr.py:567)
+
+
+def test_rotation_matrix_to_angle_axis_branches():
+    """All four quaternion branches + the small-angle path, against the closed form."""
+    def rot(axis, ang):
+        axis = np.asarray(axis, np.float64) / np.linalg.norm(axis)
+        K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+        return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+    cases = [([1, 0, 0], 0.3), ([0, 1, 0], 3.0), ([1, 0.1, 0], 3.1), ([0, 0, 1], 3.1), ([0.1, 1, 0.2], 3.0), ([1, 2, 3], 1e-4)]
+    R = np.stack([rot(a, t) for a, t in cases])
+    aa = geometry.rotation_matrix_to_angle_axis(R)
+    for (a, t), v in zip(cases, aa):
+        expect = np.asarray(a, np.float64) / np.linalg.norm(a) * t
+        assert np.abs(v - expect).max() < 1e-5, (a, t, v, expect)
+
+
+def test_guided_ddpm100_fp64_trace(golden_dir):
+    """cfg-3 shape at small size: DDPM T=100 with the collision-guided mean shift for t <= 10 (gaussian_diffusion.py:378-385)."""
+    from egohmr_b200.testing import SyntheticCollision
+    from oracle import guidance
+    g = np.load(os.path.join(golden_dir, "ddpm_guided_T100_hid256_f64.npz"))
+    hid, nb, n_img = int(g["hid"]), int(g["n_blocks"]), int(g["n_img"])
+    smpl = synth.make_smpl_model(0)
+    sd = synth.make_state_dict(0, hid=hid, n_blocks=nb, init_betas=smpl["init_betas"])
+    b = synth.make_batch(0, n_img)
+    mean, std = synth.body_rep_stats(0)
+    sch = schedule.Schedule(100, "")
+    noise = synth.make_noise(0, 1, n_img, 100)[0]
+    pts = b["scene_pcd_verts_full"] - b["smpl_params"]["transl"][:, None]
+    col = SyntheticCollision()
+    grad_fn = lambda x, out, i: guidance.guide_coll(smpl, col, x, out["pred_smpl_params"]["betas"], pts, mean, std)
+    trace = []
+    out = o_egohmr.sample(sd, synth.skeleton_adjacency(), nb, smpl, b, sch, noise, mean, std, "ddpm", dtype=np.float64,
+                          grad_fn=grad_fn, cond_grad_weight=2.0, trace=trace)
+    x0s = np.stack([t["pred_x_start"] for t in trace])
+    assert np.abs(x0s - g["trace_x0"]).max() < 2e-6
+    assert np.abs(out["pred_x_start"] - g["pred_x_start"]).max() < 2e-6
