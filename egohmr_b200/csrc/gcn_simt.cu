@@ -9,8 +9,11 @@ namespace ehb {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ sgemm
-constexpr int GT = 64, GK = 16;
+constexpr int GK = 16;
 
+// GT x GT output tile per 256-thread block, (GT/16)^2 outputs per thread.  GT = 32 is used for skinny problems (the
+// per-batch conditioning folds have M = n_img rows) so that the grid still covers the SMs.
+template <int GT>
 __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ C, int M, int N, int K, int lda, int ldb,
                                                        int ldc, int accumulate) {
@@ -18,7 +21,8 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
   __shared__ float Bs[GK][GT + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
-  float acc[4][4] = {};
+  constexpr int R = GT / 16;
+  float acc[R][R] = {};
   for (int k0 = 0; k0 < K; k0 += GK) {
     for (int e = threadIdx.x; e < GT * GK; e += 256) {
       const int mm = e / GK, kk = e % GK;
@@ -33,25 +37,25 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < GK; ++kk) {
-      float a[4], b[4];
+      float a[R], b[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < R; ++i) a[i] = As[kk][ty * R + i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) b[i] = Bs[kk][tx * 4 + i];
+      for (int i = 0; i < R; ++i) b[i] = Bs[kk][tx * R + i];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i)
 #pragma unroll
-        for (int jn = 0; jn < 4; ++jn) acc[i][jn] = fmaf(a[i], b[jn], acc[i][jn]);
+        for (int jn = 0; jn < R; ++jn) acc[i][jn] = fmaf(a[i], b[jn], acc[i][jn]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int gm = m0 + ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int gm = m0 + ty * R + i;
     if (gm >= M) continue;
 #pragma unroll
-    for (int jn = 0; jn < 4; ++jn) {
-      const int gn = n0 + tx * 4 + jn;
+    for (int jn = 0; jn < R; ++jn) {
+      const int gn = n0 + tx * R + jn;
       if (gn >= N) continue;
       float* dst = C + static_cast<size_t>(gm) * ldc + gn;
       *dst = accumulate ? (*dst + acc[i][jn]) : acc[i][jn];
@@ -269,8 +273,13 @@ __global__ void __launch_bounds__(128) gcn_hidden_epilogue_kernel(const __grid_c
 cudaError_t launch_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
                             int accumulate, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return cudaSuccess;
-  dim3 grid((N + GT - 1) / GT, (M + GT - 1) / GT);
-  sgemm_nn_kernel<<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  if (static_cast<long long>((N + 63) / 64) * ((M + 63) / 64) < 256) {   // skinny: smaller tiles, more blocks
+    dim3 grid((N + 31) / 32, (M + 31) / 32);
+    sgemm_nn_kernel<32><<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  } else {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    sgemm_nn_kernel<64><<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+  }
   return cudaGetLastError();
 }
 

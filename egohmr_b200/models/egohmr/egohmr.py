@@ -18,6 +18,7 @@ from ... import smpl as smpl_mod
 from ... import synth
 from ...engine import Engine
 from ...utils.geometry import perspective_projection
+from ..fast_encoders import FoldedResNet50, SplitPointNet
 from ..resnet import ResNet50Features
 from ..respointnet import ResnetPointnet
 
@@ -196,6 +197,8 @@ class EgoHMR(nn.Module):
         std = self.body_rep_std if self.body_rep_std is not None else torch.ones(144)
         self.engine.set_norm(torch.as_tensor(mean).detach().float().cpu().numpy(),
                              torch.as_tensor(std).detach().float().cpu().numpy())
+        self._fast_backbone = FoldedResNet50(self.backbone)
+        self._fast_scene_enc = SplitPointNet(self.scene_enc)
         self._weights_dirty = False
         self._cond_key = None
         self._temb_key = None
@@ -240,8 +243,8 @@ class EgoHMR(nn.Module):
         vis = vis_op[:, self.openpose_to_smpl]
         pts = batch["scene_pcd_verts_full"] - transl.unsqueeze(1) if self.scene_cano else batch["scene_pcd_verts_full"]
         if features is None:
-            img_feats = self.backbone(batch["img"])
-            scene_feats = self.scene_enc(pts)
+            img_feats = self._fast_backbone(batch["img"])
+            scene_feats = self._fast_scene_enc(pts)
             transl_feat = self.transl_enc(transl)
         else:
             img_feats, scene_feats, transl_feat = features["img_feats"], features["scene_feats"], features["transl_feat"]
