@@ -73,16 +73,19 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// 2-D fp16 row-major [rows][cols] tensor, box = [box_rows][32 halfs] with the 64-byte swizzle the UMMA descriptors use
+// 2-D fp16 row-major [rows][cols] tensor, box = [box_rows][BK halfs]; the swizzle span equals the box row (64 B or 128 B)
+// and matches the UMMA shared-memory descriptors of gcn_umma.cu
 int make_tmap_f16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   auto fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {cols * sizeof(__half)};
-  cuuint32_t box[2] = {32, box_rows};
+  const int bk = ehb::gcn_hidden_umma_bk();
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
   return 0;

@@ -41,6 +41,10 @@ struct HiddenLayerParams {
 cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
                                    int num_sms, int ctas, cudaStream_t stream);
 size_t gcn_hidden_umma_smem_bytes();
+int gcn_hidden_umma_bk();   // fp16 elements per TMA box row (32: SWIZZLE_64B, 64: SWIZZLE_128B)
+#ifndef EHB_UMMA_BK
+#define EHB_UMMA_BK 64
+#endif
 
 // fp32 SIMT check path for the same layer: H = X * Wcat via sgemm, then the identical epilogue.
 cudaError_t launch_gcn_hidden_simt(const float* x_f32, const float* wcat /*[K][2C] fp32*/, float* h_tmp /*[rows][2C]*/,

@@ -194,6 +194,53 @@ __device__ __forceinline__ void umma_commit_2sm_mc(uint64_t* bar, uint16_t cta_m
       : "memory");
 }
 
+// Warp-convergent variants: the whole warp executes the statement with identical (warp-uniform) operands and ONE
+// elected lane issues.  Keeping the operands uniform lets ptxas feed the UTCHMMA/UTCBAR uniform-register operands
+// directly instead of wrapping every issue in a divergent R2UR waterfall loop.
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mc_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are exactly one swizzle span wide
 // (BLOCK_K * sizeof(T) == SWIZZLE bytes), rows packed densely: 8-row groups are SWIZZLE*8 bytes apart (SBO).
