@@ -169,6 +169,8 @@ class EgoHMR(nn.Module):
         self._cond_key = None
         self._cond = None
         self._temb_key = None
+        self._bodies_key = None
+        self._bodies_idx = None
 
     # ------------------------------------------------------------------ weight ingestion
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -202,6 +204,7 @@ class EgoHMR(nn.Module):
         self._weights_dirty = False
         self._cond_key = None
         self._temb_key = None
+        self._bodies_key = None
 
     def validation_setup(self):  # egohmr.py:475-484
         self.training = False
@@ -253,8 +256,11 @@ class EgoHMR(nn.Module):
         betas = self.beta_layer(torch.cat([img_feats, rest], dim=1))  # :263-265
         self.engine.set_cond(img_feats, rest, vis.to(torch.uint8).contiguous())
         iob = np.repeat(np.arange(bs, dtype=np.int32), num_samples)
-        self.engine.set_bodies(iob)
-        idx = torch.from_numpy(iob.astype(np.int64)).to(img_feats.device)
+        if self._bodies_key != (bs, num_samples) or self.engine.n_bodies != iob.shape[0]:
+            self.engine.set_bodies(iob)      # uploads the slot tables (synchronising): only when the layout changes
+            self._bodies_key = (bs, num_samples)
+            self._bodies_idx = torch.from_numpy(iob.astype(np.int64)).to(img_feats.device)
+        idx = self._bodies_idx
         self._cond = {"vis": vis, "betas_img": betas.float().contiguous(), "scene_pts": pts, "transl": transl,
                       "img_of_body": idx, "num_samples": num_samples, "bs": bs}
         self.scene_pcd_verts = pts

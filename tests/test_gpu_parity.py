@@ -354,6 +354,7 @@ def test_smpl_backward_matches_autograd_oracle(full):
     c = lambda a: torch.from_numpy(a).cuda()
     got = eng.smpl_backward(c(x), c(betas), c(gv), c(gj), c(ga.reshape(n, 72))).cpu().numpy()
     model._cond_key = None
+    model._bodies_key = None   # the engine's body table was changed behind the model's back
     scale = np.abs(ref).max()
     print(f"smpl_backward: max err {np.abs(got - ref).max():.3e} of max|grad| {scale:.3e}")
     assert np.abs(got - ref).max() < 2e-5 * scale
