@@ -31,6 +31,12 @@ class GcnWeights(C.Structure):
                 ("inproc_w", c_float_p), ("inproc_b", c_float_p), ("layers", C.POINTER(GConv)), ("n_layers", C.c_int32)]
 
 
+class PointnetWeights(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("out_dim", C.c_int32), ("fc_pos_w", c_float_p), ("fc_pos_b", c_float_p),
+                ("fc0_w", c_float_p * 4), ("fc0_b", c_float_p * 4), ("fc1_w", c_float_p * 4), ("fc1_b", c_float_p * 4),
+                ("shortcut_w", c_float_p * 4), ("fc_c_w", c_float_p), ("fc_c_b", c_float_p)]
+
+
 class SmplModel(C.Structure):
     _fields_ = [("n_verts", C.c_int32), ("n_betas", C.c_int32), ("n_extra", C.c_int32), ("v_template", c_float_p),
                 ("shapedirs", c_float_p), ("posedirs", c_float_p), ("J_regressor", c_float_p),
@@ -57,6 +63,8 @@ SIGNATURES = {
     "ehb_rot6d_to_rotmat": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "ehb_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_smpl_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_pointnet_load": (C.c_int, [_vp, C.POINTER(PointnetWeights)]),
+    "ehb_pointnet_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "ehb_rotmat_to_angle_axis": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "ehb_smpl_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_debug_set_gemm_mode": (C.c_int, [_vp, C.c_int]),

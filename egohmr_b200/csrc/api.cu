@@ -177,6 +177,13 @@ struct ehb_ctx {
   DevBuf s_vt, s_sd, s_pd, s_w, s_jt, s_jsd, s_ex;
   DevBuf sc_R, sc_A, sc_j24, sc_pf, sc_p6, sc_dvp, sc_dA, sc_dpf;
 
+  // ---- ResPointNet
+  bool pn_loaded = false;
+  int pn_hidden = 0, pn_out = 0;
+  float pn_wscale[4][2] = {};   // [block][0 = fc_0, 1 = fc_1 + shortcut (shared)]
+  DevBuf pn_pos_w, pn_pos_b, pn_fc0[4], pn_fc1[4], pn_sc[4], pn_b0[4], pn_b1[4], pn_w0b_t[4], pn_wsb_t[4], pn_fcc_t, pn_fcc_b;
+  DevBuf pn_x[2], pn_y[2], pn_h, pn_pool, pn_pooled, pn_pooled_relu, pn_row0, pn_rows;
+
   DevBuf overflow;
 
   ~ehb_ctx() {
@@ -709,6 +716,204 @@ int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, co
   if (n <= 0) return fail("ehb_smpl_forward: n must be positive");
   EHB_CUDA(cudaSetDevice(ctx->device));
   return smpl_run(ctx, n, R, betas, nullptr, transl, verts, joints, static_cast<cudaStream_t>(stream_));
+}
+
+static void split_hl(const float* W, int rows, int cols, int ld, int col0, float scale, std::vector<__half>& out) {
+  // rows x cols block of W (row stride ld, first column col0) -> [rows][hi(cols) | lo(cols)] fp16 of scale*W
+  out.assign(static_cast<size_t>(rows) * 2 * cols, __half());
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      const float sv = W[static_cast<size_t>(r) * ld + col0 + c] * scale;
+      const __half hi = __float2half_rn(sv);
+      out[static_cast<size_t>(r) * 2 * cols + c] = hi;
+      out[static_cast<size_t>(r) * 2 * cols + cols + c] = __float2half_rn(sv - __half2float(hi));
+    }
+}
+static float pow2_scale(float maxabs) {
+  if (!(maxabs > 0.f)) return 1.f;
+  float s = std::exp2(std::floor(std::log2(16384.f / maxabs)));
+  if (maxabs * s >= 16384.f) s *= 0.5f;
+  return s;
+}
+
+__global__ void relu_copy_kernel(const float* in, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fmaxf(in[i], 0.f);
+}
+
+int ehb_pointnet_load(ehb_ctx* ctx, const ehb_pointnet_weights* w) {
+  if (!ctx || !w) return fail("ehb_pointnet_load: null argument");
+  if (w->hidden != 256) return fail("ehb_pointnet_load: hidden_dim must be 256");
+  if (w->out_dim <= 0) return fail("ehb_pointnet_load: bad out_dim");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  const int H = w->hidden, H2 = 2 * H;
+  auto up = [&](DevBuf& b, const float* src, size_t n) {
+    std::vector<float> h(src, src + n);
+    return b.upload(h);
+  };
+  {  // fc_pos_0 as [3][2H] for coalesced reads
+    std::vector<float> t(static_cast<size_t>(3) * H2);
+    for (int c = 0; c < H2; ++c)
+      for (int d = 0; d < 3; ++d) t[static_cast<size_t>(d) * H2 + c] = w->fc_pos_w[static_cast<size_t>(c) * 3 + d];
+    EHB_CUDA(ctx->pn_pos_w.upload(t));
+    EHB_CUDA(up(ctx->pn_pos_b, w->fc_pos_b, H2));
+  }
+  for (int b = 0; b < 4; ++b) {
+    const int kin = b == 0 ? H2 : H;   // per-point K of fc_0 / shortcut (the pooled half is a per-cloud row term)
+    float m0 = 0.f, m1 = 0.f;
+    for (int r = 0; r < H; ++r)
+      for (int c = 0; c < kin; ++c) {
+        m0 = std::max(m0, std::fabs(w->fc0_w[b][static_cast<size_t>(r) * H2 + c]));
+        m1 = std::max(m1, std::fabs(w->shortcut_w[b][static_cast<size_t>(r) * H2 + c]));
+      }
+    for (size_t i = 0; i < static_cast<size_t>(H) * H; ++i) m1 = std::max(m1, std::fabs(w->fc1_w[b][i]));
+    ctx->pn_wscale[b][0] = pow2_scale(m0);
+    ctx->pn_wscale[b][1] = pow2_scale(m1);   // fc_1 and shortcut accumulate into one TMEM accumulator: one scale
+    std::vector<__half> hl;
+    split_hl(w->fc0_w[b], H, kin, H2, 0, ctx->pn_wscale[b][0], hl);
+    EHB_CUDA(ctx->pn_fc0[b].upload(hl));
+    split_hl(w->fc1_w[b], H, H, H, 0, ctx->pn_wscale[b][1], hl);
+    EHB_CUDA(ctx->pn_fc1[b].upload(hl));
+    split_hl(w->shortcut_w[b], H, kin, H2, 0, ctx->pn_wscale[b][1], hl);
+    EHB_CUDA(ctx->pn_sc[b].upload(hl));
+    EHB_CUDA(up(ctx->pn_b0[b], w->fc0_b[b], H));
+    EHB_CUDA(up(ctx->pn_b1[b], w->fc1_b[b], H));
+    if (b > 0) {  // pooled halves, transposed to [K=H][N=H] for sgemm_nn
+      std::vector<float> t0(static_cast<size_t>(H) * H), ts(static_cast<size_t>(H) * H);
+      for (int r = 0; r < H; ++r)
+        for (int c = 0; c < H; ++c) {
+          t0[static_cast<size_t>(c) * H + r] = w->fc0_w[b][static_cast<size_t>(r) * H2 + H + c];
+          ts[static_cast<size_t>(c) * H + r] = w->shortcut_w[b][static_cast<size_t>(r) * H2 + H + c];
+        }
+      EHB_CUDA(ctx->pn_w0b_t[b].upload(t0));
+      EHB_CUDA(ctx->pn_wsb_t[b].upload(ts));
+    }
+  }
+  {
+    std::vector<float> t(static_cast<size_t>(H) * w->out_dim);
+    for (int r = 0; r < w->out_dim; ++r)
+      for (int c = 0; c < H; ++c) t[static_cast<size_t>(c) * w->out_dim + r] = w->fc_c_w[static_cast<size_t>(r) * H + c];
+    EHB_CUDA(ctx->pn_fcc_t.upload(t));
+    EHB_CUDA(up(ctx->pn_fcc_b, w->fc_c_b, w->out_dim));
+  }
+  ctx->pn_hidden = H;
+  ctx->pn_out = w->out_dim;
+  ctx->pn_loaded = true;
+  return 0;
+}
+
+int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts, float* feats, void* stream_) {
+  if (!ctx || !pts || !feats) return fail("ehb_pointnet_forward: null argument");
+  if (!ctx->pn_loaded) return fail("ehb_pointnet_forward: call ehb_pointnet_load first");
+  if (n_clouds <= 0 || n_pts <= 0) return fail("ehb_pointnet_forward: n_clouds and n_pts must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int H = ctx->pn_hidden, H2 = 2 * H;
+  const long long M = static_cast<long long>(n_clouds) * n_pts;
+  const int n_mtiles = static_cast<int>((M + 255) / 256) * 2;
+  const size_t rows = static_cast<size_t>(n_mtiles) * 128;
+  const float act_scale = ctx->act_scale;
+  for (int i = 0; i < 2; ++i) {
+    EHB_CUDA(ctx->pn_x[i].ensure(rows * 2 * H2 * sizeof(__half), true));
+    EHB_CUDA(ctx->pn_y[i].ensure(rows * 2 * H * sizeof(__half), true));
+  }
+  EHB_CUDA(ctx->pn_h.ensure(rows * 2 * H * sizeof(__half), true));
+  const size_t pc = static_cast<size_t>(n_clouds) * H;
+  EHB_CUDA(ctx->pn_pool.ensure(pc * sizeof(int)));
+  EHB_CUDA(ctx->pn_pooled.ensure(pc * sizeof(float)));
+  EHB_CUDA(ctx->pn_pooled_relu.ensure(pc * sizeof(float)));
+  EHB_CUDA(ctx->pn_row0.ensure(pc * sizeof(float)));
+  EHB_CUDA(ctx->pn_rows.ensure(pc * sizeof(float)));
+  int* ovf = ctx->overflow.as<int>();
+
+  EHB_CUDA(ehb::launch_pointnet_pos(pts, ctx->pn_pos_w.as<float>(), ctx->pn_pos_b.as<float>(), ctx->pn_x[0].as<__half>(),
+                                    ctx->pn_x[1].as<__half>(), M, H2, act_scale, ovf, stream));
+  ctx->launches += 1;
+  // current block input: plain / relu'd fp16 operands with K = kin
+  __half* x_plain = ctx->pn_x[0].as<__half>();
+  __half* x_relu = ctx->pn_x[1].as<__half>();
+  __half* y_plain = ctx->pn_y[0].as<__half>();
+  __half* y_relu = ctx->pn_y[1].as<__half>();
+  for (int b = 0; b < 4; ++b) {
+    const int kin = b == 0 ? H2 : H;
+    const bool last = b == 3;
+    CUtensorMap tA_relu, tA_plain, tA_h, tB0, tB1, tBs;
+    if (make_tmap_f16(&tA_relu, x_relu, rows, 2 * kin, 128)) return 1;
+    if (make_tmap_f16(&tA_plain, x_plain, rows, 2 * kin, 128)) return 1;
+    if (make_tmap_f16(&tA_h, ctx->pn_h.p, rows, 2 * H, 128)) return 1;
+    if (make_tmap_f16(&tB0, ctx->pn_fc0[b].p, H, 2 * kin, 128)) return 1;
+    if (make_tmap_f16(&tB1, ctx->pn_fc1[b].p, H, 2 * H, 128)) return 1;
+    if (make_tmap_f16(&tBs, ctx->pn_sc[b].p, H, 2 * kin, 128)) return 1;
+    const float* row0 = nullptr;
+    const float* rows_s = nullptr;
+    if (b > 0) {
+      // per-cloud rows from the pooled half of the concatenated input (respointnet.py:38-40):
+      //   row0 = relu(pooled) W0[:, H:]^T + b0      rows_s = pooled Ws[:, H:]^T + b1
+      const size_t n = pc;
+      fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(ctx->pn_row0.as<float>(), ctx->pn_b0[b].as<float>(), n_clouds, H);
+      fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(ctx->pn_rows.as<float>(), ctx->pn_b1[b].as<float>(), n_clouds, H);
+      EHB_CUDA(cudaGetLastError());
+      EHB_CUDA(ehb::launch_sgemm_nn(ctx->pn_pooled_relu.as<float>(), ctx->pn_w0b_t[b].as<float>(), ctx->pn_row0.as<float>(),
+                                    n_clouds, H, H, H, H, H, 1, stream));
+      EHB_CUDA(ehb::launch_sgemm_nn(ctx->pn_pooled.as<float>(), ctx->pn_wsb_t[b].as<float>(), ctx->pn_rows.as<float>(),
+                                    n_clouds, H, H, H, H, H, 1, stream));
+      row0 = ctx->pn_row0.as<float>();
+      rows_s = ctx->pn_rows.as<float>();
+      ctx->launches += 4;
+    }
+    ehb::LinearParams p{};
+    p.overflow_flag = ovf;
+    p.M = M;
+    p.act_scale = act_scale;
+    p.n_mtiles = n_mtiles;
+    p.pts_per_cloud = n_pts;
+    // h = fc_0(relu(x))  -> only relu(h) is consumed (by fc_1)
+    p.bias = b == 0 ? ctx->pn_b0[b].as<float>() : nullptr;
+    p.rowvec = row0;
+    p.out_hl_relu = ctx->pn_h.as<__half>();
+    p.acc_scale_inv = 1.f / (act_scale * ctx->pn_wscale[b][0]);
+    p.K1 = kin;
+    p.K2 = 0;
+    EHB_CUDA(ehb::launch_linear_umma(tA_relu, tB0, tA_relu, tB0, p, ctx->num_sms, stream));
+    // net = shortcut(x) + fc_1(relu(h))  -> next block's operands (plain + relu) and the per-cloud max
+    EHB_CUDA(ehb::launch_pool_init(ctx->pn_pool.as<int>(), static_cast<int>(pc), stream));
+    ehb::LinearParams q{};
+    q.overflow_flag = ovf;
+    q.M = M;
+    q.act_scale = act_scale;
+    q.n_mtiles = n_mtiles;
+    q.pts_per_cloud = n_pts;
+    q.bias = b == 0 ? ctx->pn_b1[b].as<float>() : nullptr;
+    q.rowvec = rows_s;
+    q.out_hl = last ? nullptr : y_plain;
+    q.out_hl_relu = last ? nullptr : y_relu;
+    q.pool = ctx->pn_pool.as<int>();
+    q.acc_scale_inv = 1.f / (act_scale * ctx->pn_wscale[b][1]);
+    q.K1 = H;
+    q.K2 = kin;
+    EHB_CUDA(ehb::launch_linear_umma(tA_h, tB1, tA_plain, tBs, q, ctx->num_sms, stream));
+    EHB_CUDA(ehb::launch_pool_decode(ctx->pn_pool.as<int>(), ctx->pn_pooled.as<float>(), static_cast<int>(pc), stream));
+    relu_copy_kernel<<<static_cast<unsigned>((pc + 255) / 256), 256, 0, stream>>>(ctx->pn_pooled.as<float>(),
+                                                                                 ctx->pn_pooled_relu.as<float>(),
+                                                                                 static_cast<int>(pc));
+    EHB_CUDA(cudaGetLastError());
+    ctx->launches += 5;
+    // the block's outputs are the next block's inputs (K = H from now on)
+    x_plain = y_plain;
+    x_relu = y_relu;
+    y_plain = (y_plain == ctx->pn_y[0].as<__half>()) ? ctx->pn_x[0].as<__half>() : ctx->pn_y[0].as<__half>();
+    y_relu = (y_relu == ctx->pn_y[1].as<__half>()) ? ctx->pn_x[1].as<__half>() : ctx->pn_y[1].as<__half>();
+  }
+  // c = fc_c(relu(max_pool(net)))  (respointnet.py:55-57)
+  {
+    const size_t n = static_cast<size_t>(n_clouds) * ctx->pn_out;
+    fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(feats, ctx->pn_fcc_b.as<float>(), n_clouds, ctx->pn_out);
+    EHB_CUDA(cudaGetLastError());
+    EHB_CUDA(ehb::launch_sgemm_nn(ctx->pn_pooled_relu.as<float>(), ctx->pn_fcc_t.as<float>(), feats, n_clouds, ctx->pn_out, H, H,
+                                  ctx->pn_out, ctx->pn_out, 1, stream));
+    ctx->launches += 2;
+  }
+  return 0;
 }
 
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream_) {

@@ -140,6 +140,29 @@ cudaError_t launch_smpl_skin(const SmplDevice& m, const float* betas, const int3
 cudaError_t launch_smpl_joints(const SmplDevice& m, const float* joints24, const float* verts, const float* transl,
                                float* joints /*[B][24+n_extra][3]*/, int n_bodies, cudaStream_t stream);
 
+// ---- ResPointNet linear layers (linear_umma.cu)
+struct LinearParams {
+  const float* bias;      // [256] or null
+  const float* rowvec;    // [n_clouds][256] or null: per-cloud row added to every point of the cloud
+  float* out_f32;         // [M][256] or null
+  __half* out_hl;         // [M_pad][hi(256) | lo(256)] of act_scale * Y, or null
+  __half* out_hl_relu;    // same for relu(Y), or null
+  int* pool;              // [n_clouds][256] order-preserving-int column max over the cloud's points, or null
+  int* overflow_flag;
+  long long M;            // valid rows
+  float acc_scale_inv;    // 1 / (act_scale * w_scale)
+  float act_scale;
+  int K1, K2;             // K of the two accumulated operand pairs (K2 = 0: single)
+  int n_mtiles;           // 128-row tiles, even
+  int pts_per_cloud;
+};
+cudaError_t launch_linear_umma(const CUtensorMap& tmA1, const CUtensorMap& tmB1, const CUtensorMap& tmA2,
+                               const CUtensorMap& tmB2, const LinearParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_pointnet_pos(const float* pts, const float* w, const float* b, __half* out_hl, __half* out_hl_relu,
+                                long long M, int C, float act_scale, int* overflow_flag, cudaStream_t stream);
+cudaError_t launch_pool_init(int* pool, int n, cudaStream_t stream);
+cudaError_t launch_pool_decode(const int* pool, float* out, int n, cudaStream_t stream);
+
 // ---- guidance backward (smpl_bwd.cu)
 cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, cudaStream_t stream);
 // dL/dx [B][144] from dL/dverts [B][V][3], dL/djoints [B][24+E][3], dL/dfull_pose_aa [B][24][3] (each may be null).

@@ -1,0 +1,358 @@
+// K7 — point-wise linear layers of the ResPointNet scene encoder (models/respointnet.py:33-59, 88-97) on tcgen05:
+//     Y[M,256] = A1[M,K1] W1^T (+ A2[M,K2] W2^T) (+ bias) (+ rowvec[cloud(row)])
+// with M = clouds x points, and a fused epilogue that writes what the NEXT layer consumes instead of fp32 activations:
+// the fp16 hi/lo operand of relu(Y) and/or of Y, and the per-cloud column max (the PointNet pooling, :38,42,46,55).
+// Same fp16x3 error-compensated scheme, CTA pairs (cta_group::2) and TMA/mbarrier pipeline as gcn_umma.cu; two operand
+// pairs may accumulate into one TMEM accumulator, which is how a ResnetBlockFC's `shortcut(x) + fc_1(relu(h))` becomes
+// ONE launch with no fp32 round trip.  Step-invariant: runs once per image batch.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace ehb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 256;           // ResPointNet hidden width
+constexpr int BK = 64;            // 128-byte swizzled rows
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;            // 16 KiB
+constexpr int B_BYTES = BN * BK * 2 / 2;        // per CTA of the pair: half of the N rows
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KiB
+constexpr int STAGES = 3;
+constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant: warp w and w+4 split the 256 columns
+constexpr int TMA_WARP = 8, MMA_WARP = 9;
+constexpr int NUM_THREADS = 10 * 32;
+constexpr int TMEM_COLS = 512;
+
+struct Barriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
+
+__device__ __forceinline__ int encode_max(float v) {
+  const int i = __float_as_int(v);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;   // order-preserving float -> int
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                   const __grid_constant__ LinearParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_units = p.n_mtiles / 2;
+  const int unit0 = blockIdx.x / 2, unit_step = gridDim.x / 2;
+  const int KB1 = p.K1 / BK, KB2 = p.K2 / BK;
+
+  if (warp == TMA_WARP && lane == 0) {
+    ptx::prefetch_tensormap(&tmA1);
+    ptx::prefetch_tensormap(&tmB1);
+    if (KB2) {
+      ptx::prefetch_tensormap(&tmA2);
+      ptx::prefetch_tensormap(&tmB2);
+    }
+  }
+  if (warp == MMA_WARP && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&bars->tfull[s], 1);
+      ptx::mbar_init(&bars->tempty[s], 2 * NUM_EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == TMA_WARP) {
+    ptx::tmem_alloc_2sm(&bars->tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == TMA_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = unit0; u < n_units; u += unit_step) {
+        const int m_row = (u * 2 + static_cast<int>(rank)) * BM;
+        const int b_row = static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < KB1 + KB2; ++kb) {
+          const bool second = kb >= KB1;
+          const CUtensorMap* ta = second ? &tmA2 : &tmA1;
+          const CUtensorMap* tb = second ? &tmB2 : &tmB1;
+          const int K = second ? p.K2 : p.K1;
+          const int kk = (second ? kb - KB1 : kb) * BK;
+          ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* s = smem + stage * STAGE_BYTES;
+          const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
+          if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
+          ptx::tma_load_2d_2sm(s, ta, lfull, kk, m_row);
+          ptx::tma_load_2d_2sm(s + A_BYTES, ta, lfull, K + kk, m_row);
+          ptx::tma_load_2d_2sm(s + 2 * A_BYTES, tb, lfull, kk, b_row);
+          ptx::tma_load_2d_2sm(s + 2 * A_BYTES + B_BYTES, tb, lfull, K + kk, b_row);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16_f32(2 * BM, BN);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int u = unit0; u < n_units; u += unit_step) {
+        ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < KB1 + KB2; ++kb) {
+          ptx::mbar_wait(&bars->full[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint32_t koff = ks * UMMA_K * 2;
+            const uint64_t a_hi = ptx::make_kmajor_desc<128>(sa + koff);
+            const uint64_t a_lo = ptx::make_kmajor_desc<128>(sa + A_BYTES + koff);
+            const uint64_t b_hi = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + koff);
+            const uint64_t b_lo = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + B_BYTES + koff);
+            ptx::umma_f16_2sm_elect(tacc, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+            ptx::umma_f16_2sm_elect(tacc, a_hi, b_lo, idesc, 1u);
+            ptx::umma_f16_2sm_elect(tacc, a_lo, b_hi, idesc, 1u);
+          }
+          ptx::umma_commit_2sm_mc_elect(&bars->empty[stage], 0b11);
+          if (kb == KB1 + KB2 - 1) ptx::umma_commit_2sm_mc_elect(&bars->tfull[as], 0b11);
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: thread = row, 4 x 32 columns each
+    const int q = warp & 3;             // TMEM lane quadrant
+    const int col_half = warp >> 2;     // columns [128*col_half, +128)
+    int as = 0;
+    uint32_t aphase = 0;
+    float amax = 0.f;
+    for (int u = unit0; u < n_units; u += unit_step) {
+      const long long row = static_cast<long long>(u * 2 + static_cast<int>(rank)) * BM + q * 32 + lane;
+      const bool valid = row < p.M;
+      const int cloud = valid ? static_cast<int>(row / p.pts_per_cloud) : 0;
+      // pooling fast path: all 32 rows of this warp are valid and in one cloud
+      const long long row_first = row - lane;
+      const bool warp_one_cloud = (row_first + 31 < p.M) && (row_first / p.pts_per_cloud == (row_first + 31) / p.pts_per_cloud);
+      ptx::mbar_wait(&bars->tfull[as], aphase);
+      ptx::tc_fence_after_sync();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * 128;
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {
+        float v[32];
+        ptx::tmem_ld_32x32b_x32(trow + ch * 32, v);
+        ptx::tmem_ld_wait();
+        if (ch == 3) {
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&bars->tempty[as]);
+            else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tempty[as]), 0));
+          }
+        }
+        const int c0 = col_half * 128 + ch * 32;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          float y = v[c] * p.acc_scale_inv;
+          if (p.bias) y += __ldg(p.bias + c0 + c);
+          if (p.rowvec) y += __ldg(p.rowvec + static_cast<size_t>(cloud) * BN + c0 + c);
+          v[c] = y;
+        }
+        if (p.out_f32 && valid) {
+          float4* o = reinterpret_cast<float4*>(p.out_f32 + row * BN + c0);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        if (p.pool) {
+          if (warp_one_cloud) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float mx = v[c];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+              if (lane == (c & 31)) atomicMax(p.pool + static_cast<size_t>(cloud) * BN + c0 + c, encode_max(mx));
+            }
+          } else if (valid) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) atomicMax(p.pool + static_cast<size_t>(cloud) * BN + c0 + c, encode_max(v[c]));
+          }
+        }
+        if (valid && (p.out_hl || p.out_hl_relu)) {
+          // 32 consecutive channels of this row: 64 B of hi and 64 B of lo per destination
+          __align__(16) __half hi[32], lo[32];
+          if (p.out_hl) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float sv = v[c] * p.act_scale;
+              hi[c] = __float2half_rn(sv);
+              lo[c] = __float2half_rn(sv - __half2float(hi[c]));
+              amax = fmaxf(amax, fabsf(sv));
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hl + row * (2 * BN) + c0);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_hl + row * (2 * BN) + BN + c0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              dh[c] = reinterpret_cast<const uint4*>(hi)[c];
+              dl[c] = reinterpret_cast<const uint4*>(lo)[c];
+            }
+          }
+          if (p.out_hl_relu) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float sv = fmaxf(v[c], 0.f) * p.act_scale;
+              hi[c] = __float2half_rn(sv);
+              lo[c] = __float2half_rn(sv - __half2float(hi[c]));
+              amax = fmaxf(amax, fabsf(sv));
+            }
+            uint4* dh = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + c0);
+            uint4* dl = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + BN + c0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              dh[c] = reinterpret_cast<const uint4*>(hi)[c];
+              dl[c] = reinterpret_cast<const uint4*>(lo)[c];
+            }
+          }
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == TMA_WARP) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+// fc_pos_0 (3 -> 2*hidden, models/respointnet.py:21,35): K = 3 is not a tensor-core shape; this writes the two fp16
+// hi/lo operands block_0 consumes — relu(net) for fc_0 and net itself for the shortcut (:88-97).
+__global__ void __launch_bounds__(256) pointnet_pos_kernel(const float* __restrict__ pts, const float* __restrict__ w /*[3][C]*/,
+                                                           const float* __restrict__ b, __half* __restrict__ out_hl,
+                                                           __half* __restrict__ out_hl_relu, long long M, int C,
+                                                           float act_scale, int* overflow_flag) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = M * (C / 8);
+  if (i >= total) return;
+  const long long row = i / (C / 8);
+  const int c0 = static_cast<int>(i % (C / 8)) * 8;
+  const float x = pts[row * 3 + 0], y = pts[row * 3 + 1], z = pts[row * 3 + 2];
+  __align__(16) __half hi[8], lo[8], rhi[8], rlo[8];
+  float amax = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float v = fmaf(z, w[2 * C + c0 + c], fmaf(y, w[C + c0 + c], fmaf(x, w[c0 + c], b[c0 + c])));
+    const float sv = v * act_scale, rv = fmaxf(v, 0.f) * act_scale;
+    hi[c] = __float2half_rn(sv);
+    lo[c] = __float2half_rn(sv - __half2float(hi[c]));
+    rhi[c] = __float2half_rn(rv);
+    rlo[c] = __float2half_rn(rv - __half2float(rhi[c]));
+    amax = fmaxf(amax, fabsf(sv));
+  }
+  *reinterpret_cast<uint4*>(out_hl + row * (2 * C) + c0) = *reinterpret_cast<const uint4*>(hi);
+  *reinterpret_cast<uint4*>(out_hl + row * (2 * C) + C + c0) = *reinterpret_cast<const uint4*>(lo);
+  *reinterpret_cast<uint4*>(out_hl_relu + row * (2 * C) + c0) = *reinterpret_cast<const uint4*>(rhi);
+  *reinterpret_cast<uint4*>(out_hl_relu + row * (2 * C) + C + c0) = *reinterpret_cast<const uint4*>(rlo);
+  if (!(amax <= 65504.f)) atomicExch(overflow_flag, 1);
+}
+
+__global__ void pool_init_kernel(int* pool, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) pool[i] = encode_max(-INFINITY);
+}
+__global__ void pool_decode_kernel(const int* pool, float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int e = pool[i];
+    out[i] = __int_as_float(e >= 0 ? e : e ^ 0x7FFFFFFF);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_linear_umma(const CUtensorMap& tmA1, const CUtensorMap& tmB1, const CUtensorMap& tmA2,
+                               const CUtensorMap& tmB2, const LinearParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(linear_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (p.K1 <= 0 || p.K1 % BK || p.K2 % BK || p.n_mtiles % 2) return cudaErrorInvalidValue;
+  const int units = p.n_mtiles / 2;
+  if (units == 0) return cudaSuccess;
+  const int grid = units * 2 < num_sms ? units * 2 : (num_sms / 2) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, linear_umma_kernel, tmA1, tmB1, tmA2, tmB2, p);
+}
+
+cudaError_t launch_pointnet_pos(const float* pts, const float* w, const float* b, __half* out_hl, __half* out_hl_relu,
+                                long long M, int C, float act_scale, int* overflow_flag, cudaStream_t stream) {
+  const long long total = M * (C / 8);
+  if (total <= 0) return cudaSuccess;
+  pointnet_pos_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(pts, w, b, out_hl, out_hl_relu, M, C,
+                                                                                     act_scale, overflow_flag);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pool_init(int* pool, int n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pool_init_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pool, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_decode(const int* pool, float* out, int n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  pool_decode_kernel<<<(n + 255) / 256, 256, 0, stream>>>(pool, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace ehb

@@ -111,6 +111,37 @@ class Engine:
         check(self.lib.ehb_smpl_load(self._h, C.byref(m)))
         self.n_verts, self.n_extra, self.n_betas, self.smpl_loaded = m.n_verts, m.n_extra, m.n_betas, True
 
+    def load_pointnet(self, sd, prefix="scene_enc", hidden=256):
+        """ResnetPointnet parameters by their reference names (models/respointnet.py:13-27)."""
+        keep = []
+
+        def arr(name):
+            v = sd[f"{prefix}.{name}"]
+            if isinstance(v, torch.Tensor):
+                v = v.detach().cpu().numpy()
+            a = f32(v)
+            keep.append(a)
+            return fptr(a)
+
+        w = _lib.PointnetWeights()
+        w.hidden = hidden
+        w.out_dim = int(sd[f"{prefix}.fc_c.weight"].shape[0])
+        w.fc_pos_w, w.fc_pos_b = arr("fc_pos_0.weight"), arr("fc_pos_0.bias")
+        for i in range(4):
+            w.fc0_w[i], w.fc0_b[i] = arr(f"block_{i}.fc_0.weight"), arr(f"block_{i}.fc_0.bias")
+            w.fc1_w[i], w.fc1_b[i] = arr(f"block_{i}.fc_1.weight"), arr(f"block_{i}.fc_1.bias")
+            w.shortcut_w[i] = arr(f"block_{i}.shortcut.weight")
+        w.fc_c_w, w.fc_c_b = arr("fc_c.weight"), arr("fc_c.bias")
+        check(self.lib.ehb_pointnet_load(self._h, C.byref(w)))
+        self.pointnet_out = w.out_dim
+
+    def pointnet_forward(self, pts):
+        """scene_enc(pts): [n_clouds, n_pts, 3] -> [n_clouds, out_dim] (K7, tcgen05)."""
+        n_clouds, n_pts = pts.shape[0], pts.shape[1]
+        out = torch.empty(n_clouds, self.pointnet_out, device=pts.device, dtype=torch.float32)
+        check(self.lib.ehb_pointnet_forward(self._h, _dev_ptr(pts), n_clouds, n_pts, _dev_ptr(out), _stream()))
+        return out
+
     def set_norm(self, mean, std):
         m, s = f32(mean).reshape(144), f32(std).reshape(144)
         check(self.lib.ehb_set_norm(self._h, fptr(m), fptr(s)))

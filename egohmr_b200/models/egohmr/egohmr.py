@@ -171,6 +171,7 @@ class EgoHMR(nn.Module):
         self._temb_key = None
         self._bodies_key = None
         self._bodies_idx = None
+        self.native_scene_enc = True   # ResPointNet on the tcgen05 linear kernel (K7); False = PyTorch/cuBLAS form
 
     # ------------------------------------------------------------------ weight ingestion
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -200,7 +201,8 @@ class EgoHMR(nn.Module):
         self.engine.set_norm(torch.as_tensor(mean).detach().float().cpu().numpy(),
                              torch.as_tensor(std).detach().float().cpu().numpy())
         self._fast_backbone = FoldedResNet50(self.backbone)
-        self._fast_scene_enc = SplitPointNet(self.scene_enc)
+        self._fast_scene_enc = SplitPointNet(self.scene_enc)   # PyTorch form (kept for comparison / odd shapes)
+        self.engine.load_pointnet({k: v for k, v in self.state_dict().items() if k.startswith("scene_enc.")})
         self._weights_dirty = False
         self._cond_key = None
         self._temb_key = None
@@ -247,7 +249,8 @@ class EgoHMR(nn.Module):
         pts = batch["scene_pcd_verts_full"] - transl.unsqueeze(1) if self.scene_cano else batch["scene_pcd_verts_full"]
         if features is None:
             img_feats = self._fast_backbone(batch["img"])
-            scene_feats = self._fast_scene_enc(pts)
+            scene_feats = (self.engine.pointnet_forward(pts.float().contiguous()) if self.native_scene_enc
+                           else self._fast_scene_enc(pts))
             transl_feat = self.transl_enc(transl)
         else:
             img_feats, scene_feats, transl_feat = features["img_feats"], features["scene_feats"], features["transl_feat"]

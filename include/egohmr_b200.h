@@ -135,6 +135,25 @@ int ehb_decode(ehb_ctx* ctx, const float* x0, const float* betas, float* pose6d,
 int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, const float* transl, float* verts,
                      float* joints, void* stream);
 
+/* ResnetPointnet scene encoder (models/respointnet.py:13-59), nn.Linear parameters in the reference layout ([out][in]).
+ * hidden_dim must be 256 (EgoHMR constructs ResnetPointnet(out_dim=scene_feat_dim, hidden_dim=256), egohmr.py:69). HOST. */
+typedef struct {
+  int32_t hidden;   /* 256 */
+  int32_t out_dim;  /* scene_feat_dim, 512 */
+  const float* fc_pos_w; /* [2*hidden][3] */
+  const float* fc_pos_b; /* [2*hidden]    */
+  const float* fc0_w[4];      /* block_i.fc_0.weight     [hidden][2*hidden] */
+  const float* fc0_b[4];      /* block_i.fc_0.bias       [hidden]           */
+  const float* fc1_w[4];      /* block_i.fc_1.weight     [hidden][hidden]   */
+  const float* fc1_b[4];      /* block_i.fc_1.bias       [hidden]           */
+  const float* shortcut_w[4]; /* block_i.shortcut.weight [hidden][2*hidden] */
+  const float* fc_c_w;   /* [out_dim][hidden] */
+  const float* fc_c_b;   /* [out_dim]         */
+} ehb_pointnet_weights;
+int ehb_pointnet_load(ehb_ctx* ctx, const ehb_pointnet_weights* w);
+/* scene_enc(scene_pcd_verts) (egohmr.py:214): pts [n_clouds][n_pts][3] -> feats [n_clouds][out_dim]. */
+int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts, float* feats, void* stream);
+
 /* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
  * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);

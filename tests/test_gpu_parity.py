@@ -382,3 +382,21 @@ def test_guided_ddpm100_vs_reference_golden(golden_dir):
     assert moved > 1e-6      # small (|grad| ~ 5e-3 times 0.02 .. 0.07) but far above the parity tolerance
     assert d64 < 5e-6
     assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < 2e-5
+
+
+def test_pointnet_tcgen05_vs_torch_and_oracle(full):
+    """K7: ResPointNet (models/respointnet.py:33-59) on the tcgen05 linear kernel vs the float64 oracle and vs the
+    PyTorch fp32 module, including a ragged cloud size (pooling across tile boundaries) and a single cloud."""
+    model, _, sd, *_ = full
+    model._sync_engine()
+    for n_clouds, n_pts, seed in ((5, 1024, 0), (3, 1000, 1), (1, 300, 2)):
+        rng = np.random.default_rng(seed)
+        pts = rng.uniform(-1, 1, (n_clouds, n_pts, 3)).astype(np.float32)
+        ref = encoders.respointnet(sd, pts.astype(np.float64))
+        with torch.no_grad():
+            tor = model.scene_enc(torch.from_numpy(pts).cuda()).cpu().numpy()
+        got = model.engine.pointnet_forward(torch.from_numpy(pts).cuda()).cpu().numpy()
+        assert not model.engine.check_overflow()
+        e_got, e_tor = np.abs(got - ref).max(), np.abs(tor - ref).max()
+        print(f"pointnet {n_clouds}x{n_pts}: tcgen05 vs f64 {e_got:.3e}, torch fp32 vs f64 {e_tor:.3e} (max|ref| {np.abs(ref).max():.3f})")
+        assert e_got < 5e-6
