@@ -28,7 +28,8 @@ class GConv(C.Structure):
 class GcnWeights(C.Structure):
     _fields_ = [("hid", C.c_int32), ("n_blocks", C.c_int32), ("img_dim", C.c_int32), ("cond_dim", C.c_int32),
                 ("xfeat_dim", C.c_int32), ("temb_dim", C.c_int32), ("diffuse_fuse", C.c_int32), ("adj", c_float_p),
-                ("inproc_w", c_float_p), ("inproc_b", c_float_p), ("layers", C.POINTER(GConv)), ("n_layers", C.c_int32)]
+                ("inproc_w", c_float_p), ("inproc_b", c_float_p), ("layers", C.POINTER(GConv)), ("n_layers", C.c_int32),
+                ("mask_all_cond", C.c_int32)]
 
 
 class PointnetWeights(C.Structure):
@@ -48,6 +49,7 @@ _vp = C.c_void_p
 SIGNATURES = {
     "ehb_last_error": (C.c_char_p, []),
     "ehb_launch_count": (C.c_int64, [_vp]),
+    "ehb_alloc_epoch": (C.c_uint64, []),
     "ehb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "ehb_ctx_destroy": (None, [_vp]),
     "ehb_gcn_load": (C.c_int, [_vp, C.POINTER(GcnWeights)]),
@@ -70,6 +72,7 @@ SIGNATURES = {
     "ehb_debug_set_gemm_mode": (C.c_int, [_vp, C.c_int]),
     "ehb_check_overflow": (C.c_int, [_vp, _vp]),
     "ehb_time_hidden_layer": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), _vp]),
+    "ehb_time_stage": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_float), _vp]),
     "ehb_debug_get_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_uint64)]),
 }
 

@@ -29,11 +29,16 @@ int fail_cuda(const char* what, cudaError_t e) {
     if (_e != cudaSuccess) return fail_cuda(#expr, _e);  \
   } while (0)
 
+// bumped whenever a workspace moves: a captured CUDA graph holds raw workspace pointers, so its owner compares this
+// against the value at capture time before every replay (ehb_alloc_epoch)
+uint64_t g_alloc_epoch = 0;
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   cudaError_t ensure(size_t n, bool zero = false) {
     if (n <= bytes && p) return cudaSuccess;
+    ++g_alloc_epoch;
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
@@ -142,7 +147,7 @@ struct ehb_ctx {
 
   // ---- denoiser
   bool gcn_loaded = false;
-  int hid = 0, n_blocks = 0, img_dim = 0, cond_dim = 0, xfeat_dim = 0, temb_dim = 0, diffuse_fuse = 0;
+  int hid = 0, n_blocks = 0, img_dim = 0, cond_dim = 0, xfeat_dim = 0, temb_dim = 0, diffuse_fuse = 0, mask_all = 0;
   struct Hidden {
     ehb::AdjMix adj;
     DevBuf mod_scaled, mod, bn_scale, bn_shift, w_hl, wcat;
@@ -196,6 +201,8 @@ extern "C" {
 const char* ehb_last_error(void) { return g_last_error.c_str(); }
 
 int64_t ehb_launch_count(const ehb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+uint64_t ehb_alloc_epoch(void) { return g_alloc_epoch; }
 
 int ehb_ctx_create(int device, ehb_ctx** out) {
   if (!out) return fail("ehb_ctx_create: out is NULL");
@@ -257,6 +264,7 @@ int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w) {
   ctx->xfeat_dim = w->xfeat_dim;
   ctx->temb_dim = w->temb_dim;
   ctx->diffuse_fuse = w->diffuse_fuse;
+  ctx->mask_all = w->mask_all_cond ? 1 : 0;
   const size_t C2 = 2 * static_cast<size_t>(C);
 
   // ---- input layer: split W[2][in_dim][C] by feature block, columns concatenated as k*C + c
@@ -502,6 +510,63 @@ static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
   return 0;
 }
 
+static int run_input(ehb_ctx* ctx, int step, const float* x_t, cudaStream_t stream) {
+  ehb::InputLayerParams p;
+  p.adj = ctx->adj_in;
+  p.a01 = ctx->a01.as<float>();
+  p.be01 = ctx->be01.as<float>();
+  p.cx01 = ctx->cx01.as<float>();
+  p.ct01 = ctx->ct01.as<float>();
+  p.wx01 = ctx->wx01.as<float>();
+  p.mod = ctx->mod_in.as<float>();
+  p.bn_scale = ctx->bn_scale_in.as<float>();
+  p.bn_shift = ctx->bn_shift_in.as<float>();
+  p.vis = ctx->vis.as<uint8_t>();
+  p.slot_body = ctx->slot_body.as<int32_t>();
+  p.slot_cond = ctx->slot_cond.as<uint8_t>();
+  p.img_of_body = ctx->img_of_body.as<int32_t>();
+  p.x_t = x_t;
+  p.res = ctx->res.as<float>();
+  p.out_hl = ctx->act_hl[0].as<__half>();
+  p.overflow_flag = ctx->overflow.as<int>();
+  p.act_scale = ctx->act_scale;
+  p.C = ctx->hid;
+  p.n_slots = ctx->n_slots;
+  p.step = step;
+  p.mask_all = ctx->mask_all;
+  EHB_CUDA(ehb::launch_gcn_input(p, stream));
+  ctx->launches += 1;
+  return 0;
+}
+
+static int run_output(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad, float* x_prev,
+                      float* x0, float* out_cond, float* out_uncond, cudaStream_t stream) {
+  ehb::OutputLayerParams p;
+  p.adj = ctx->adj_out;
+  p.act = ctx->res.as<float>();
+  p.wout = ctx->wout.as<float>();
+  p.mod = ctx->mod_out.as<float>();
+  p.bias = ctx->bias_out.as<float>();
+  p.vis = ctx->vis.as<uint8_t>();
+  p.img_of_body = ctx->img_of_body.as<int32_t>();
+  p.body_slot = ctx->body_slot.as<int32_t>();
+  p.x_t = x_t;
+  p.noise = noise;
+  p.grad = grad;
+  p.x_prev = x_prev;
+  p.x0 = x0;
+  p.out_cond = out_cond;
+  p.out_uncond = out_uncond;
+  p.coef = ctx->coef[step];
+  p.kind = ctx->kind;
+  p.C = ctx->hid;
+  p.n_bodies = ctx->n_bodies;
+  p.diffuse_fuse = ctx->diffuse_fuse;
+  EHB_CUDA(ehb::launch_gcn_output(p, stream));
+  ctx->launches += 1;
+  return 0;
+}
+
 int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
                            float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream_) {
   if (!ctx || !x_t || !x_prev || !x0) return fail("ehb_denoise_step: null argument");
@@ -510,58 +575,43 @@ int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float
     return fail("ehb_denoise_step: step out of range of the schedule / conditioning tables");
   EHB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  {
-    ehb::InputLayerParams p;
-    p.adj = ctx->adj_in;
-    p.a01 = ctx->a01.as<float>();
-    p.be01 = ctx->be01.as<float>();
-    p.ct01 = ctx->ct01.as<float>();
-    p.wx01 = ctx->wx01.as<float>();
-    p.mod = ctx->mod_in.as<float>();
-    p.bn_scale = ctx->bn_scale_in.as<float>();
-    p.bn_shift = ctx->bn_shift_in.as<float>();
-    p.vis = ctx->vis.as<uint8_t>();
-    p.slot_body = ctx->slot_body.as<int32_t>();
-    p.slot_cond = ctx->slot_cond.as<uint8_t>();
-    p.img_of_body = ctx->img_of_body.as<int32_t>();
-    p.x_t = x_t;
-    p.res = ctx->res.as<float>();
-    p.out_hl = ctx->act_hl[0].as<__half>();
-    p.overflow_flag = ctx->overflow.as<int>();
-    p.act_scale = ctx->act_scale;
-    p.C = ctx->hid;
-    p.n_slots = ctx->n_slots;
-    p.step = step;
-    EHB_CUDA(ehb::launch_gcn_input(p, stream));
-    ctx->launches += 1;
-  }
+  if (run_input(ctx, step, x_t, stream)) return 1;
   for (int l = 0; l < static_cast<int>(ctx->hidden.size()); ++l)
     if (run_hidden(ctx, l, stream)) return 1;
-  {
-    ehb::OutputLayerParams p;
-    p.adj = ctx->adj_out;
-    p.act = ctx->res.as<float>();
-    p.wout = ctx->wout.as<float>();
-    p.mod = ctx->mod_out.as<float>();
-    p.bias = ctx->bias_out.as<float>();
-    p.vis = ctx->vis.as<uint8_t>();
-    p.img_of_body = ctx->img_of_body.as<int32_t>();
-    p.body_slot = ctx->body_slot.as<int32_t>();
-    p.x_t = x_t;
-    p.noise = noise;
-    p.grad = grad;
-    p.x_prev = x_prev;
-    p.x0 = x0;
-    p.out_cond = out_cond;
-    p.out_uncond = out_uncond;
-    p.coef = ctx->coef[step];
-    p.kind = ctx->kind;
-    p.C = ctx->hid;
-    p.n_bodies = ctx->n_bodies;
-    p.diffuse_fuse = ctx->diffuse_fuse;
-    EHB_CUDA(ehb::launch_gcn_output(p, stream));
-    ctx->launches += 1;
+  return run_output(ctx, step, x_t, noise, grad, x_prev, x0, out_cond, out_uncond, stream);
+}
+
+/* stage 0 = folded input layer (K2), 1 .. 2*n_blocks = hidden layers (K1), 2*n_blocks + 1 = output layer + sampler
+ * update (K3); runs it `iters` times on the context's current activations and returns the mean device time. */
+int ehb_time_stage(ehb_ctx* ctx, int stage, int step, const float* x_t, float* x_prev, float* x0, int iters, float* ms,
+                   void* stream_) {
+  if (!ctx || !ms || !x_t || !x_prev || !x0) return fail("ehb_time_stage: null argument");
+  if (!ctx->gcn_loaded || ctx->n_bodies <= 0 || ctx->n_img <= 0) return fail("ehb_time_stage: context not set up");
+  const int L = static_cast<int>(ctx->hidden.size());
+  if (stage < 0 || stage > L + 1) return fail("ehb_time_stage: bad stage");
+  if (step < 0 || step >= static_cast<int>(ctx->coef.size()) || step >= ctx->n_steps_cond)
+    return fail("ehb_time_stage: step out of range");
+  if (iters <= 0) return fail("ehb_time_stage: iters must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaEvent_t e0, e1;
+  EHB_CUDA(cudaEventCreate(&e0));
+  EHB_CUDA(cudaEventCreate(&e1));
+  EHB_CUDA(cudaEventRecord(e0, stream));
+  for (int i = 0; i < iters; ++i) {
+    int rc;
+    if (stage == 0) rc = run_input(ctx, step, x_t, stream);
+    else if (stage <= L) rc = run_hidden(ctx, stage - 1, stream);
+    else rc = run_output(ctx, step, x_t, nullptr, nullptr, x_prev, x0, nullptr, nullptr, stream);
+    if (rc) return 1;
   }
+  EHB_CUDA(cudaEventRecord(e1, stream));
+  EHB_CUDA(cudaEventSynchronize(e1));
+  float t = 0.f;
+  EHB_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms = t / iters;
   return 0;
 }
 

@@ -82,9 +82,14 @@ __device__ __forceinline__ size_t slot_row0(int slot) {
 // and feeds it to gconv_input (modulated_gcn.py:99-101).  Because the feature is a concatenation and the layer is
 // linear before the joint mix, feat.W_k splits into per-image, per-step and per-joint terms:
 //   h_k[j] = vis[j]*a_k[img] (conditioned pass only) + be_k[img] + ct_k[step] + x_t[j,:].wx_k
+// The image-masked pass drops the a_k term (mask_cond(force_mask=True, only_mask_img_cond=True), egohmr.py:150-156);
+// with only_mask_img_cond=False it drops every condition (:157-158), i.e. be_k falls back to its constant part cx_k.
+// HBM-bound: 2 x 98.3 KB written per slot.  Compute is thread = channel (coalesced parameter reads); the 24 x 128
+// output tile is staged in shared memory and written out as 128-bit fp32 / 64-bit fp16 row segments.
 __global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ InputLayerParams p) {
   __shared__ float xs[NJ][6];
   __shared__ float visf[NJ];
+  __shared__ __align__(16) float tile[NJ][128];
   const int slot = blockIdx.x;
   const int body = p.slot_body[slot];
   const int img = p.img_of_body[body];
@@ -94,13 +99,16 @@ __global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ 
   __syncthreads();
   const int C = p.C;
   const size_t row0 = slot_row0(slot);
-  float amax = 0.f;
+  const int c0 = blockIdx.y * 128;  // C % 128 == 0
   {
-    const int c = blockIdx.y * 128 + threadIdx.x;  // C % 128 == 0
+    const int c = c0 + threadIdx.x;
     const float a0 = p.a01[(static_cast<size_t>(img) * 2 + 0) * C + c];
     const float a1 = p.a01[(static_cast<size_t>(img) * 2 + 1) * C + c];
-    const float base0 = p.be01[(static_cast<size_t>(img) * 2 + 0) * C + c] + p.ct01[(static_cast<size_t>(p.step) * 2 + 0) * C + c];
-    const float base1 = p.be01[(static_cast<size_t>(img) * 2 + 1) * C + c] + p.ct01[(static_cast<size_t>(p.step) * 2 + 1) * C + c];
+    const bool drop_all = !cond && p.mask_all;
+    const float be0 = drop_all ? p.cx01[c] : p.be01[(static_cast<size_t>(img) * 2 + 0) * C + c];
+    const float be1 = drop_all ? p.cx01[C + c] : p.be01[(static_cast<size_t>(img) * 2 + 1) * C + c];
+    const float base0 = be0 + p.ct01[(static_cast<size_t>(p.step) * 2 + 0) * C + c];
+    const float base1 = be1 + p.ct01[(static_cast<size_t>(p.step) * 2 + 1) * C + c];
     float w0[6], w1[6];
 #pragma unroll
     for (int d = 0; d < 6; ++d) {
@@ -122,20 +130,34 @@ __global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ 
       g[j] = m * h1;
       y[j] = p.adj.diag[j] * (m * h0);
     }
+    const float sc = p.bn_scale[c], sh = p.bn_shift[c];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       float acc = y[j];
 #pragma unroll
       for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[j][i], g[i], acc);
-      y[j] = acc;
+      tile[j][threadIdx.x] = fmaxf(fmaf(acc, sc, sh), 0.f);
     }
-    const float sc = p.bn_scale[c], sh = p.bn_shift[c];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const float v = fmaxf(fmaf(y[j], sc, sh), 0.f);
-      p.res[(row0 + j) * C + c] = v;
-      amax = fmaxf(amax, store_hl(p.out_hl, row0 + j, C, c, v, p.act_scale));
-    }
+  }
+  __syncthreads();
+  float amax = 0.f;
+  const size_t C2 = 2 * static_cast<size_t>(C);
+  for (int e = threadIdx.x; e < NJ * 32; e += 128) {
+    const int j = e >> 5, q = (e & 31) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(&tile[j][q]);
+    *reinterpret_cast<float4*>(p.res + (row0 + j) * C + c0 + q) = v;
+    const float s0 = v.x * p.act_scale, s1 = v.y * p.act_scale, s2 = v.z * p.act_scale, s3 = v.w * p.act_scale;
+    const __half2 h01 = __floats2half2_rn(s0, s1), h23 = __floats2half2_rn(s2, s3);
+    const __half2 l01 = __floats2half2_rn(s0 - __low2float(h01), s1 - __high2float(h01));
+    const __half2 l23 = __floats2half2_rn(s2 - __low2float(h23), s3 - __high2float(h23));
+    uint2 hi, lo;
+    hi.x = *reinterpret_cast<const uint32_t*>(&h01);
+    hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lo.x = *reinterpret_cast<const uint32_t*>(&l01);
+    lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(p.out_hl + (row0 + j) * C2 + c0 + q) = hi;
+    *reinterpret_cast<uint2*>(p.out_hl + (row0 + j) * C2 + C + c0 + q) = lo;
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(s0), fabsf(s1)), fmaxf(fabsf(s2), fabsf(s3))));
   }
   if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
 }
@@ -165,29 +187,50 @@ __global__ void sampler_update_kernel(const StepCoef coef, int kind, const float
 // (guidance_param == 0: invisible joints take the image-masked pass, visible joints the image-conditioned pass)
 // and one sampler update (gaussian_diffusion.py:298-337 p_sample, :340-388 with gradient, :511-556 ddim_sample).
 // The update replays the reference's fp32 op order with contraction disabled so equal inputs give equal bits.
-__global__ void __launch_bounds__(256) gcn_output_kernel(const __grid_constant__ OutputLayerParams p) {
+__global__ void __launch_bounds__(256, 2) gcn_output_kernel(const __grid_constant__ OutputLayerParams p) {
   __shared__ float hs[2][NJ][12];
   const int body = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.C;
   const int slots[2] = {p.body_slot[body * 2 + 0], p.body_slot[body * 2 + 1]};
-  for (int rr = warp; rr < 2 * NJ; rr += 8) {
-    const int pass = rr / NJ, j = rr % NJ;
-    if (slots[pass] < 0) continue;
-    const float* arow = p.act + (slot_row0(slots[pass]) + j) * C;
-    float acc[12] = {};
-    for (int k = lane; k < C; k += 32) {
-      const float a = arow[k];
-      const float4* wp = reinterpret_cast<const float4*>(p.wout + static_cast<size_t>(k) * 12);
-      const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-      acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]);
-      acc[3] = fmaf(a, w0.w, acc[3]); acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
-      acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]); acc[8] = fmaf(a, w2.x, acc[8]);
-      acc[9] = fmaf(a, w2.y, acc[9]); acc[10] = fmaf(a, w2.z, acc[10]); acc[11] = fmaf(a, w2.w, acc[11]);
+  // HBM-bound: 2 x 98.3 KB read per body.  Each warp reduces six (pass, joint) rows at once so that one pass over the
+  // [C][12] output weights (L1-resident, 48 KB) serves six rows: the kernel moves 2 B of L1 traffic per HBM byte
+  // instead of 12.  Lane l owns k = 128*it + 4*l .. +3 of every row (128-bit coalesced loads).
+  constexpr int RW = 6;   // rows per warp = 2*NJ / 8 warps
+  const float* arow[RW];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int rr = warp + 8 * r, pass = rr / NJ, j = rr % NJ;
+    arow[r] = slots[pass] < 0 ? nullptr : p.act + (slot_row0(slots[pass]) + j) * C;
+  }
+  float acc[RW][12] = {};
+  for (int k = lane * 4; k < C; k += 128) {
+    float4 a[RW];
+#pragma unroll
+    for (int r = 0; r < RW; ++r)
+      a[r] = arow[r] ? *reinterpret_cast<const float4*>(arow[r] + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* wp = reinterpret_cast<const float4*>(p.wout + static_cast<size_t>(k) * 12);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float4 w0 = __ldg(wp + 3 * kk), w1 = __ldg(wp + 3 * kk + 1), w2 = __ldg(wp + 3 * kk + 2);
+#pragma unroll
+      for (int r = 0; r < RW; ++r) {
+        const float av = kk == 0 ? a[r].x : (kk == 1 ? a[r].y : (kk == 2 ? a[r].z : a[r].w));
+        acc[r][0] = fmaf(av, w0.x, acc[r][0]); acc[r][1] = fmaf(av, w0.y, acc[r][1]);
+        acc[r][2] = fmaf(av, w0.z, acc[r][2]); acc[r][3] = fmaf(av, w0.w, acc[r][3]);
+        acc[r][4] = fmaf(av, w1.x, acc[r][4]); acc[r][5] = fmaf(av, w1.y, acc[r][5]);
+        acc[r][6] = fmaf(av, w1.z, acc[r][6]); acc[r][7] = fmaf(av, w1.w, acc[r][7]);
+        acc[r][8] = fmaf(av, w2.x, acc[r][8]); acc[r][9] = fmaf(av, w2.y, acc[r][9]);
+        acc[r][10] = fmaf(av, w2.z, acc[r][10]); acc[r][11] = fmaf(av, w2.w, acc[r][11]);
+      }
     }
+  }
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int rr = warp + 8 * r, pass = rr / NJ, j = rr % NJ;
 #pragma unroll
     for (int o = 0; o < 12; ++o) {
-      float v = acc[o];
+      float v = acc[r][o];
 #pragma unroll
       for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
       if (lane == 0) hs[pass][j][o] = v;

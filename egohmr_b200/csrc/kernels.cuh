@@ -59,6 +59,7 @@ struct InputLayerParams {
   AdjMix adj;
   const float* a01;      // [n_img][2][C]   img_feat . W_k[0:img_dim]
   const float* be01;     // [n_img][2][C]   rest_feat . W_k[img_dim:cond_dim] + inproc_b . W_k[x rows]
+  const float* cx01;     // [2][C]          inproc_b . W_k[x rows]  (the condition-free part of be01)
   const float* ct01;     // [n_steps][2][C] temb(step) . W_k[temb rows]
   const float* wx01;     // [2][6][C]       inproc_w^T . W_k[x rows]
   const float* mod;      // [24][C] (unscaled M)
@@ -74,6 +75,7 @@ struct InputLayerParams {
   int* overflow_flag;
   float act_scale;
   int C, n_slots, step;
+  int mask_all;          // image-masked pass drops every condition (only_mask_img_cond=False, egohmr.py:157-158)
 };
 cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream);
 

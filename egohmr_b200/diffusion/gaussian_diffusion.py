@@ -323,6 +323,12 @@ class GaussianDiffusion:
         out["sample"] = final["sample"]
         return out
 
+    def capture_sample_many(self, model, batch, num_samples, timestep_respacing=""):
+        """`sample_many` captured once as a CUDA graph (egohmr_b200/diffusion/graphed.py): returns a callable
+        `sampler(batch) -> out` that replays the whole pass with no per-launch host work."""
+        from .graphed import GraphedSampler
+        return GraphedSampler(self, model, batch, num_samples, timestep_respacing)
+
 
 class _NoiseFeed:
     """Feeds pre-drawn noise to the loop in the reference's draw order (tests / reproducible multi-GPU sharding)."""

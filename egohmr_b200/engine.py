@@ -55,7 +55,7 @@ class Engine:
 
     # ------------------------------------------------------------------ loading
     def load_gcn(self, sd, adj, hid, n_blocks, diffuse_fuse=True, img_dim=2048, cond_dim=2694, xfeat_dim=512,
-                 temb_dim=512, prefix="diffusion_model", bn_eps=1e-5):
+                 temb_dim=512, prefix="diffusion_model", bn_eps=1e-5, mask_all_cond=False):
         """`sd`: mapping reference-state_dict-name -> array (numpy or torch), see include/egohmr_b200.h::ehb_gconv."""
         keep = []
 
@@ -90,6 +90,7 @@ class Engine:
         w = _lib.GcnWeights()
         w.hid, w.n_blocks, w.img_dim, w.cond_dim, w.xfeat_dim, w.temb_dim = hid, n_blocks, img_dim, cond_dim, xfeat_dim, temb_dim
         w.diffuse_fuse = 1 if diffuse_fuse else 0
+        w.mask_all_cond = 1 if mask_all_cond else 0
         adj_a = f32(adj.detach().cpu().numpy() if isinstance(adj, torch.Tensor) else adj)
         w.adj = fptr(adj_a)
         w.inproc_w, w.inproc_b = fptr(arr("input_process.poseEmbedding.weight")), fptr(arr("input_process.poseEmbedding.bias"))
@@ -231,11 +232,22 @@ class Engine:
     def launch_count(self):
         return int(self.lib.ehb_launch_count(self._h))
 
+    def alloc_epoch(self):
+        return int(self.lib.ehb_alloc_epoch())
+
     def set_gemm_mode(self, mode):
         check(self.lib.ehb_debug_set_gemm_mode(self._h, int(mode)))
 
     def check_overflow(self):
         return bool(self.lib.ehb_check_overflow(self._h, _stream()))
+
+    def time_stage(self, stage, step, x_t, iters):
+        """Mean device ms of one stage of a reverse step (0 = K2 input layer, 1..8 = K1, 9 = K3 output + update)."""
+        ms = C.c_float()
+        x_prev, x0 = torch.empty_like(x_t), torch.empty_like(x_t)
+        check(self.lib.ehb_time_stage(self._h, int(stage), int(step), _dev_ptr(x_t), _dev_ptr(x_prev), _dev_ptr(x0),
+                                      int(iters), C.byref(ms), _stream()))
+        return float(ms.value)
 
     def time_hidden_layer(self, layer, iters):
         ms = C.c_float()

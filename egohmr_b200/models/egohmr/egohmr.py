@@ -126,9 +126,6 @@ class EgoHMR(nn.Module):
         if gcn_nonlocal_layer:
             raise NotImplementedError("gcn_nonlocal_layer=True is never enabled by the reference's drivers "
                                       "(egohmr.py:37, test_egohmr.py:112-118) and is not on the accelerated path")
-        if diffuse_fuse and not only_mask_img_cond:
-            raise NotImplementedError("diffuse_fuse with only_mask_img_cond=False (mask every condition) is not "
-                                      "implemented; the reference's test default is only_mask_img_cond=True")
         self.cfg = cfg
         self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
         self.with_focal_length, self.with_bbox_info, self.with_cam_center = with_focal_length, with_bbox_info, with_cam_center
@@ -171,6 +168,8 @@ class EgoHMR(nn.Module):
         self._temb_key = None
         self._bodies_key = None
         self._bodies_idx = None
+        self._op2smpl_idx = None
+        self._default_center = None
         self.native_scene_enc = True   # ResPointNet on the tcgen05 linear kernel (K7); False = PyTorch/cuBLAS form
 
     # ------------------------------------------------------------------ weight ingestion
@@ -193,7 +192,7 @@ class EgoHMR(nn.Module):
               if k.startswith("diffusion_model.") or k.startswith("input_process.")}
         bn_eps = self.diffusion_model.gconv_input[0].bn.eps
         self.engine.load_gcn(sd, self.adj, self.hid, self.n_blocks, self.diffuse_fuse, self.img_dim, self.cond_dim,
-                             512, 512, bn_eps=bn_eps)
+                             512, 512, bn_eps=bn_eps, mask_all_cond=not self.only_mask_img_cond)
         if not self.engine.smpl_loaded:
             self.engine.load_smpl(self.smpl.model)
         mean = self.body_rep_mean if self.body_rep_mean is not None else torch.zeros(144)
@@ -245,7 +244,9 @@ class EgoHMR(nn.Module):
         bs = batch["img"].shape[0]
         vis_op = batch["orig_keypoints_2d"][:, :, -1] > 0  # egohmr.py:186-189
         vis_op[:, 8] = True
-        vis = vis_op[:, self.openpose_to_smpl]
+        if self._op2smpl_idx is None or self._op2smpl_idx.device != vis_op.device:
+            self._op2smpl_idx = torch.tensor(self.openpose_to_smpl, device=vis_op.device, dtype=torch.long)
+        vis = vis_op.index_select(1, self._op2smpl_idx)   # device-resident index: no per-call upload, graph-capturable
         pts = batch["scene_pcd_verts_full"] - transl.unsqueeze(1) if self.scene_cano else batch["scene_pcd_verts_full"]
         if features is None:
             img_feats = self._fast_backbone(batch["img"])
@@ -294,14 +295,16 @@ class EgoHMR(nn.Module):
         betas = cond["betas_img"][idx]
         transl = cond["transl"][idx]
         out = {"pred_x_start": x0, "pred_pose_6d": pose6d,
-               "pred_smpl_params": {"global_orient": R[:, [0]].clone(), "body_pose": R[:, 1:].clone(), "betas": betas.clone()},
+               "pred_smpl_params": {"global_orient": R[:, 0:1].clone(), "body_pose": R[:, 1:].clone(), "betas": betas.clone()},
                "pred_keypoints_3d": joints, "pred_vertices": verts}
         if self.with_focal_length:
             focal = (batch["fx"].unsqueeze(-1).repeat(1, 2) * self.cfg.CAM.FX_NORM_COEFF)[idx]
             center = torch.stack([batch["cam_cx"], batch["cam_cy"]], dim=-1)[idx]
         else:
             focal = self.cfg.EXTRA.FOCAL_LENGTH * torch.ones(x0.shape[0], 2, device=x0.device)
-            center = torch.tensor([[960.0, 540.0]], device=x0.device).repeat(x0.shape[0], 1)
+            if self._default_center is None or self._default_center.device != x0.device:
+                self._default_center = torch.tensor([[960.0, 540.0]], device=x0.device)
+            center = self._default_center.repeat(x0.shape[0], 1)
         self.camera_center_full, self.focal_length = center, focal
         out["pred_keypoints_3d_full"] = joints + transl.unsqueeze(1)
         kp2d = perspective_projection(joints, transl, focal, center)

@@ -22,7 +22,7 @@ def torch_batch(batch_np, device):
 
 
 def build_model(hid=1024, n_blocks=4, T=50, respacing="ddim5", seed=0, device="cuda:0", diffuse_fuse=True,
-                collision=True):
+                collision=True, only_mask_img_cond=True):
     """-> (model, diffusion, state_dict(numpy), smpl_model, Xmean, Xstd) with the reference's test-default flags
     (test_egohmr.py:53-78, 112-118)."""
     from .diffusion.model_util import create_gaussian_diffusion
@@ -34,7 +34,7 @@ def build_model(hid=1024, n_blocks=4, T=50, respacing="ddim5", seed=0, device="c
     model = EgoHMR(cfg=make_cfg(), device=dev, body_rep_mean=torch.from_numpy(mean).to(dev),
                    body_rep_std=torch.from_numpy(std).to(dev), with_focal_length=True, with_bbox_info=True,
                    with_cam_center=True, scene_feat_dim=512, scene_type="cube", scene_cano=True, cond_mask_prob=0.0,
-                   only_mask_img_cond=True, pelvis_vis_loosen=True, diffuse_fuse=diffuse_fuse, diffusion_blk=n_blocks,
+                   only_mask_img_cond=only_mask_img_cond, pelvis_vis_loosen=True, diffuse_fuse=diffuse_fuse, diffusion_blk=n_blocks,
                    gcn_hid_dim=hid, smpl_model=smpl_model,
                    collision_model=SyntheticCollision() if collision else None)
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)

@@ -52,6 +52,8 @@ typedef struct {
   const float* inproc_b; /* [xfeat_dim]     "input_process.poseEmbedding.bias"   */
   const ehb_gconv* layers; /* [0] gconv_input, [1 .. 2*n_blocks] gconv_layers.{b}.gconv{1,2}, [last] gconv_output */
   int32_t n_layers;        /* 2*n_blocks + 2 */
+  int32_t mask_all_cond;   /* !only_mask_img_cond: the image-masked pass of diffuse_fuse zeroes EVERY condition
+                              (mask_cond(force_mask=True), egohmr.py:150-158) instead of the image features only */
 } ehb_gcn_weights;
 
 /* SMPL model tensors as smplx stores them (smplx/body_models.py::SMPL.__init__).  HOST. */
@@ -71,6 +73,9 @@ typedef struct {
 const char* ehb_last_error(void);
 /* number of kernels this library has launched on `ctx` since creation (bench.py's gpu_launches) */
 int64_t ehb_launch_count(const ehb_ctx* ctx);
+/* Counter bumped whenever the library (re)allocates a device workspace.  Hot calls only allocate when a problem size
+ * grows; a caller that captured hot calls into a CUDA graph must re-capture if this value changed since the capture. */
+uint64_t ehb_alloc_epoch(void);
 
 int ehb_ctx_create(int device, ehb_ctx** out);
 void ehb_ctx_destroy(ehb_ctx* ctx);
@@ -173,6 +178,12 @@ int ehb_check_overflow(ehb_ctx* ctx, void* stream);
 /* Runs only hidden layer `layer` (1-based index into ehb_gcn_weights.layers) `iters` times on the current
  * activations and returns the average device time in ms through *ms (bench.py's roofline leg). */
 int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* stream);
+
+/* Same for any stage of one reverse step on the context's current activations: stage 0 = folded input layer,
+ * 1 .. 2*n_blocks = hidden layers, 2*n_blocks+1 = output layer + fuse-select + sampler update (noise/grad = NULL).
+ * x_t / x_prev / x0 as in ehb_denoise_step. */
+int ehb_time_stage(ehb_ctx* ctx, int stage, int step, const float* x_t, float* x_prev, float* x0, int iters, float* ms,
+                   void* stream);
 
 /* Device pointer + size of an internal activation buffer (tests / bring-up only):
  * which 0 = fp32 block-boundary activations [rows_pad][hid], 1/2 = fp16 [hi|lo] operand ping/pong [rows_pad][2*hid]. */

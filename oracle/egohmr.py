@@ -10,13 +10,13 @@ from . import encoders, gcn, geometry, schedule, smpl
 
 
 def forward(sd, adj, n_blocks, smpl_model, batch, x_t, t_orig, mean, std, cond=None, dtype=np.float32,
-            diffuse_fuse=True, with_smpl=True):
+            diffuse_fuse=True, with_smpl=True, only_mask_img_cond=True):
     """EgoHMR.forward (models/egohmr/egohmr.py:173-303) -> the reference's output dict (numpy)."""
     if cond is None:
         cond = encoders.conditioning(sd, batch, dtype)
     B = x_t.shape[0]
     x0, oc, ou = gcn.denoise(sd, adj, n_blocks, x_t.astype(dtype), t_orig, cond["img_feats"], cond["rest_feats"],
-                             cond["vis"], diffuse_fuse)
+                             cond["vis"], diffuse_fuse, only_mask_img_cond)
     out = {"pred_x_start": x0, "out_cond": oc, "out_uncond": ou}
     pose6d = x0 * std.astype(dtype) + mean.astype(dtype)  # :258
     R = geometry.rot6d_to_rotmat(pose6d, "diffusion").reshape(B, 24, 3, 3)  # :260
@@ -39,7 +39,7 @@ def forward(sd, adj, n_blocks, smpl_model, batch, x_t, t_orig, mean, std, cond=N
 
 
 def sample(sd, adj, n_blocks, smpl_model, batch, sch, noise, mean, std, mode="ddim", dtype=np.float32, hoist=True,
-           diffuse_fuse=True, grad_fn=None, cond_grad_weight=1.0, trace=None):
+           diffuse_fuse=True, grad_fn=None, cond_grad_weight=1.0, trace=None, only_mask_img_cond=True):
     """One chain of p_sample_loop / ddim_sample_loop (gaussian_diffusion.py:391-508, 618-718).
 
     noise: [n_steps+1, B, 144] in the reference's draw order — noise[0] is `th.randn(*shape)` (:478), noise[1+k] the
@@ -53,7 +53,7 @@ def sample(sd, adj, n_blocks, smpl_model, batch, sch, noise, mean, std, mode="dd
         t_orig = np.full(B, sch.timestep_map[i], dtype=np.int64)  # respace.py:124-126
         last = i == 0
         out = forward(sd, adj, n_blocks, smpl_model, batch, x, t_orig, mean, std, cond=cond, dtype=dtype,
-                      diffuse_fuse=diffuse_fuse, with_smpl=(last or not hoist))
+                      diffuse_fuse=diffuse_fuse, with_smpl=(last or not hoist), only_mask_img_cond=only_mask_img_cond)
         x0 = out["pred_x_start"]
         if mode == "ddim":
             x_new = schedule.ddim_update(sch, x, x0, i, np.dtype(dtype).type)

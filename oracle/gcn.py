@@ -63,7 +63,7 @@ def timestep_embedding(t_orig, sd, dtype):
     return linear(h, sd, "embed_timestep.time_embed.2")
 
 
-def denoise(sd, adj, n_blocks, x_t, t_orig, img_feats, rest_feats, vis, diffuse_fuse=True):
+def denoise(sd, adj, n_blocks, x_t, t_orig, img_feats, rest_feats, vis, diffuse_fuse=True, only_mask_img_cond=True):
     """EgoHMR.forward's x_t-dependent part (egohmr.py:178-179, 190-191, 220-257) -> pred_x_start [B, 144]
     (plus the raw conditioned / image-masked outputs).
 
@@ -81,7 +81,10 @@ def denoise(sd, adj, n_blocks, x_t, t_orig, img_feats, rest_feats, vis, diffuse_
     if not diffuse_fuse:
         return out_c.reshape(B, 144), out_c.reshape(B, 144), None
     cond_u = cond.copy()
-    cond_u[:, :, 0:2048] = 0  # mask_cond(force_mask=True, only_mask_img_cond=True) :150-156, :242-244
+    if only_mask_img_cond:
+        cond_u[:, :, 0:2048] = 0  # mask_cond(force_mask=True, only_mask_img_cond=True) :150-156, :242-244
+    else:
+        cond_u[:] = 0             # mask_cond(force_mask=True, only_mask_img_cond=False) :157-158
     out_u = modulated_gcn(np.concatenate([cond_u, x_feat, temb], axis=-1), sd, adj, n_blocks)  # :245-246
     guidance_param = 0  # :248
     out = out_u + guidance_param * (out_c - out_u)  # :249

@@ -52,7 +52,7 @@ class NoiseFeed:
         return self._next(x.shape)
 
 
-def build_reference(hid, n_blocks, dtype, seed=0):
+def build_reference(hid, n_blocks, dtype, seed=0, only_mask_img_cond=True, diffuse_fuse=True):
     smpl_model = synth.make_smpl_model(seed)
     ref_standins.install(smpl_model, smpl_model["init_betas"])
     from models.egohmr.egohmr import EgoHMR
@@ -60,8 +60,8 @@ def build_reference(hid, n_blocks, dtype, seed=0):
     model = EgoHMR(cfg=ref_standins.make_cfg(), device="cpu",
                    body_rep_mean=torch.from_numpy(mean).to(dtype), body_rep_std=torch.from_numpy(std).to(dtype),
                    with_focal_length=True, with_bbox_info=True, with_cam_center=True, scene_feat_dim=512,
-                   scene_type="cube", scene_cano=True, cond_mask_prob=0.0, only_mask_img_cond=True,
-                   pelvis_vis_loosen=True, diffuse_fuse=True, diffusion_blk=n_blocks, gcn_hid_dim=hid)
+                   scene_type="cube", scene_cano=True, cond_mask_prob=0.0, only_mask_img_cond=only_mask_img_cond,
+                   pelvis_vis_loosen=True, diffuse_fuse=diffuse_fuse, diffusion_blk=n_blocks, gcn_hid_dim=hid)
     sd = synth.make_state_dict(seed, hid=hid, n_blocks=n_blocks, init_betas=smpl_model["init_betas"])
     res = model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
     assert not res.unexpected_keys and all(k.startswith("smpl") for k in res.missing_keys), res
@@ -76,10 +76,11 @@ def build_reference(hid, n_blocks, dtype, seed=0):
     return model, mean, std
 
 
-def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0, guided=False):
+def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0, guided=False, only_mask_img_cond=True,
+             diffuse_fuse=True):
     from diffusion.model_util import create_gaussian_diffusion
     import diffusion.gaussian_diffusion as gd
-    model, mean, std = build_reference(hid, n_blocks, dtype, seed)
+    model, mean, std = build_reference(hid, n_blocks, dtype, seed, only_mask_img_cond, diffuse_fuse)
     diffusion = create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=respacing,
                                           body_rep_mean=torch.from_numpy(mean).to(dtype),
                                           body_rep_std=torch.from_numpy(std).to(dtype))
@@ -202,6 +203,10 @@ if __name__ == "__main__":
     # the stand-ins must be installed before importing reference modules
     smpl_model = synth.make_smpl_model(0)
     ref_standins.install(smpl_model, smpl_model["init_betas"])
+    if len(sys.argv) > 1 and sys.argv[1] == "flags":   # the non-default model flags only (added later; small cases)
+        run_case("ddim5_T50_hid256_maskall_f64", 50, "ddim5", 256, 2, 3, torch.float64, only_mask_img_cond=False)
+        run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)
+        raise SystemExit(0)
     schedule_tables()
     small_ops()
     run_case("ddim5_T50_hid1024_f32", 50, "ddim5", 1024, 4, 2, torch.float32)
@@ -212,3 +217,5 @@ if __name__ == "__main__":
     guide_case("guide_grad_f64", torch.float64)
     run_case("ddpm_guided_T100_hid256_f32", 100, "", 256, 2, 3, torch.float32, guided=True)
     run_case("ddpm_guided_T100_hid256_f64", 100, "", 256, 2, 3, torch.float64, guided=True)
+    run_case("ddim5_T50_hid256_maskall_f64", 50, "ddim5", 256, 2, 3, torch.float64, only_mask_img_cond=False)
+    run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)

@@ -225,6 +225,48 @@ def test_ddpm50_sampling_vs_reference_golden(small, golden_dir):
     assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < 2e-5
 
 
+@pytest.mark.parametrize("case,flags", [("ddim5_T50_hid256_maskall_f64", {"only_mask_img_cond": False}),
+                                        ("ddim5_T50_hid256_nofuse_f64", {"diffuse_fuse": False})])
+def test_model_flag_variants_vs_reference_golden(golden_dir, case, flags):
+    """The two non-default denoiser flags of EgoHMR.__init__ (egohmr.py:36-40): the image-masked pass dropping EVERY
+    condition (only_mask_img_cond=False, :157-158) and a single conditioned pass (diffuse_fuse=False, :239)."""
+    from egohmr_b200.testing import build_model
+    model, diffusion, sd, smpl_model, mean, std = build_model(256, 2, T=50, respacing="ddim5", collision=False, **flags)
+    g64 = np.load(os.path.join(golden_dir, case + ".npz"))
+    batch = _tb(synth.make_batch(0, 3))
+    noise = synth.make_noise(0, 1, 3, 5)[0]
+    x0s = [o["pred_xstart"].cpu().numpy() for o in
+           diffusion.ddim_sample_loop_progressive(model, batch, [3, 144], noise=torch.from_numpy(noise[0]).cuda())]
+    d = np.abs(np.stack(x0s) - g64["trace_x0"]).max()
+    print(f"{case}: max|x0 - ref_f64| = {d:.3e}")
+    assert d < X0_TOL
+    model.engine.close()
+
+
+def test_graphed_sampler_equals_eager(full):
+    """The whole pass captured as one CUDA graph (diffusion/graphed.py) replays to the same bits as the eager loop, on
+    the capture batch and on a new batch copied into the static inputs; with torch's generator as the noise source two
+    replays draw different chains."""
+    model, diffusion, *_ = full
+    n_img, S = 4, 3
+    b0, b1 = _tb(synth.make_batch(5, n_img)), _tb(synth.make_batch(6, n_img))
+    nz = torch.from_numpy(synth.make_noise(9, 1, n_img * S, 5)[0]).cuda()
+    from egohmr_b200.diffusion.graphed import GraphedSampler
+    sampler = GraphedSampler(diffusion, model, b0, S, "ddim5", external_noise=True)
+    assert sampler.launches_per_replay > 40
+    for b in (b0, b1, b0):
+        got = {k: v.clone() for k, v in sampler(b, noise=nz).items() if isinstance(v, torch.Tensor)}
+        model._cond_key = None
+        ref = diffusion.sample_many(model, b, S, "ddim5", noise=nz)
+        for k in ("pred_x_start", "pred_vertices", "pred_keypoints_3d", "pred_keypoints_2d_full", "sample"):
+            assert torch.equal(got[k], ref[k]), k
+    rng_sampler = diffusion.capture_sample_many(model, b0, S, "ddim5")
+    a = rng_sampler(b0)["pred_x_start"].clone()
+    c = rng_sampler(b0)["pred_x_start"].clone()
+    assert torch.isfinite(a).all() and not torch.equal(a, c)
+    assert not model.engine.check_overflow()
+
+
 def test_sample_many_equals_sequential_chains(full):
     """Flattening the num_samples loop (test_egohmr.py:251-255) into one batch changes nothing: chain (img i, sample n)
     of the flattened run equals the n-th sequential call when both see the same noise."""

@@ -47,7 +47,7 @@ def test_modulated_graph_conv_golden(golden_dir):
     assert np.abs(y32 - so["gconv_y32"]).max() < 2e-5
 
 
-def _run_case(golden_dir, case, dtype):
+def _run_case(golden_dir, case, dtype, **flags):
     g = np.load(os.path.join(golden_dir, case + ".npz"))
     hid, nb, n_img, T, resp = int(g["hid"]), int(g["n_blocks"]), int(g["n_img"]), int(g["T"]), str(g["respacing"])
     smpl = synth.make_smpl_model(0)
@@ -59,7 +59,7 @@ def _run_case(golden_dir, case, dtype):
     noise = synth.make_noise(0, 1, n_img, sch.num_timesteps)[0]
     trace = []
     out = o_egohmr.sample(sd, synth.skeleton_adjacency(), nb, smpl, b, sch, noise, mean, std,
-                          "ddim" if resp else "ddpm", dtype=dtype, trace=trace)
+                          "ddim" if resp else "ddpm", dtype=dtype, trace=trace, **flags)
     return g, out, np.stack([t["pred_x_start"] for t in trace]), np.stack([t["x_t"] for t in trace])
 
 
@@ -95,6 +95,23 @@ def test_ddpm50_fp64_trace(golden_dir):
     # exp(0.5*log_var) is evaluated in fp32 by torch and by numpy: 1-ulp libm differences times the noise
     assert np.abs(x0s - g["trace_x0"]).max() < 1e-6
     assert np.abs(xts - g["trace_x_t"]).max() < 2e-6
+
+
+def test_ddim5_mask_all_conditions_fp64(golden_dir):
+    """diffuse_fuse with only_mask_img_cond=False: the second pass zeroes every condition (egohmr.py:157-158)."""
+    g, out, x0s, xts = _run_case(golden_dir, "ddim5_T50_hid256_maskall_f64", np.float64, only_mask_img_cond=False)
+    assert np.abs(x0s - g["trace_x0"]).max() < 1e-12
+    assert np.abs(out["pred_vertices"] - g["pred_vertices"]).max() < 5e-6
+    # and it is a different computation from the default flag
+    _, out2, x0d, _ = _run_case(golden_dir, "ddim5_T50_hid256_maskall_f64", np.float64)
+    assert np.abs(x0d - g["trace_x0"]).max() > 1e-4
+
+
+def test_ddim5_no_diffuse_fuse_fp64(golden_dir):
+    """diffuse_fuse=False: a single image-conditioned pass, no fuse-select (egohmr.py:239)."""
+    g, out, x0s, xts = _run_case(golden_dir, "ddim5_T50_hid256_nofuse_f64", np.float64, diffuse_fuse=False)
+    assert np.abs(x0s - g["trace_x0"]).max() < 1e-12
+    assert np.abs(out["pred_vertices"] - g["pred_vertices"]).max() < 5e-6
 
 
 def test_encoders_match_reference_features(golden_dir):
