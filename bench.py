@@ -273,9 +273,13 @@ def run_b200(args):
                 "joints": torch.empty(B, 45, 3).pin_memory()}
     d2h_bytes = sum(t.numel() * 4 for t in res_host.values())
 
-    def e2e_step():
+    def e2e_step(last=False):
         if sampler is not None:
-            out = sampler(host)      # pinned host tensors -> the graph's static inputs (async H2D), then one replay
+            # pinned host tensors -> device staging copy on the copy stream (overlaps the previous replay) -> the graph's
+            # static inputs (device-to-device) -> one replay; the next step's upload starts as soon as this one is queued
+            out = sampler(staged=True)
+            if not last:
+                sampler.stage(host)
         else:
             b = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in host.items()}
             b["smpl_params"] = {"transl": host["smpl_params"]["transl"].to(dev, non_blocking=True)}
@@ -286,11 +290,17 @@ def run_b200(args):
         res_host["betas"].copy_(out["pred_smpl_params"]["betas"], non_blocking=True)
         res_host["joints"].copy_(out["pred_keypoints_3d"], non_blocking=True)
 
+    if sampler is not None:
+        sampler.stage(host)
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    # exactly K uploads, K passes and K downloads inside the timed region: the first upload is issued here (the warm-up
+    # step's look-ahead copy is simply overwritten), each step issues the next one, the last step issues none
+    if sampler is not None:
+        sampler.stage(host)
+    for i in range(args.steps):
+        e2e_step(last=(i == args.steps - 1))
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -399,7 +409,8 @@ def run_b200(args):
                                 "gcn_hidden_layers_per_step": float(np.sum(layer_ms)), "gcn_output_per_step": k3_ms,
                                 "decode_once_per_pass": dec_ms}},
         "e2e": {"value": total_bodies / e2e_s, "unit": "bodies/s", "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes), "timer": "host wall clock, synchronize on both sides"},
+                "d2h_bytes_per_step": int(d2h_bytes), "timer": "host wall clock, synchronize on both sides",
+                "pipelining": "inputs of step i+1 upload on a copy stream while step i computes (GraphedSampler.stage)"},
         "gpu_launches": int(launches),
         "clocks": clk, "roofline": roofline, "roofline_other": roofline_other,
     }

@@ -189,12 +189,24 @@ struct ehb_ctx {
   DevBuf pn_pos_w, pn_pos_b, pn_fc0[4], pn_fc1[4], pn_sc[4], pn_b0[4], pn_b1[4], pn_w0b_t[4], pn_wsb_t[4], pn_fcc_t, pn_fcc_b;
   DevBuf pn_x[2], pn_y[2], pn_h, pn_pool, pn_pooled, pn_pooled_relu, pn_row0, pn_rows;
 
-  DevBuf overflow;
+  DevBuf overflow, splitk;
 
   ~ehb_ctx() {
     for (auto* h : hidden) delete h;
   }
 };
+
+// skinny fp32 GEMM of the once-per-batch folds / per-cloud rows, split over K so that it fills the GPU
+static int ctx_sgemm(ehb_ctx* ctx, const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb,
+                     int ldc, int accumulate, cudaStream_t stream) {
+  const int splits = ehb::sgemm_splitk_plan(M, N, K, ctx->num_sms);
+  if (splits > 1) EHB_CUDA(ctx->splitk.ensure(static_cast<size_t>(splits) * M * N * sizeof(float)));
+  int nl = 0;
+  EHB_CUDA(ehb::launch_sgemm_nn_splitk(A, B, C, M, N, K, lda, ldb, ldc, accumulate, ctx->splitk.as<float>(), splits, &nl,
+                                       stream));
+  ctx->launches += nl;
+  return 0;
+}
 
 extern "C" {
 
@@ -399,17 +411,18 @@ int ehb_set_cond(ehb_ctx* ctx, int n_img, const float* img_feat, const float* re
   EHB_CUDA(ctx->be01.ensure(sizeof(float) * n_img * C2));
   EHB_CUDA(ctx->vis.ensure(static_cast<size_t>(n_img) * ehb::NJ));
   EHB_CUDA(cudaMemcpyAsync(ctx->vis.p, vis, static_cast<size_t>(n_img) * ehb::NJ, cudaMemcpyDeviceToDevice, stream));
-  EHB_CUDA(ehb::launch_sgemm_nn(img_feat, ctx->w_img.as<float>(), ctx->a01.as<float>(), n_img, C2, ctx->img_dim,
-                                ctx->img_dim, C2, C2, 0, stream));
+  if (ctx_sgemm(ctx, img_feat, ctx->w_img.as<float>(), ctx->a01.as<float>(), n_img, C2, ctx->img_dim, ctx->img_dim, C2, C2,
+                0, stream))
+    return 1;
   {
     const size_t n = static_cast<size_t>(n_img) * C2;
     fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(ctx->be01.as<float>(),
                                                                                  ctx->cx01.as<float>(), n_img, C2);
     EHB_CUDA(cudaGetLastError());
   }
-  EHB_CUDA(ehb::launch_sgemm_nn(rest_feat, ctx->w_rest.as<float>(), ctx->be01.as<float>(), n_img, C2, rest, rest, C2,
-                                C2, 1, stream));
-  ctx->launches += 3;
+  if (ctx_sgemm(ctx, rest_feat, ctx->w_rest.as<float>(), ctx->be01.as<float>(), n_img, C2, rest, rest, C2, C2, 1, stream))
+    return 1;
+  ctx->launches += 1;
   ctx->n_img = n_img;
   return 0;
 }
@@ -422,9 +435,9 @@ int ehb_set_temb(ehb_ctx* ctx, int n_steps, const float* temb, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int C2 = 2 * ctx->hid;
   EHB_CUDA(ctx->ct01.ensure(sizeof(float) * n_steps * C2));
-  EHB_CUDA(ehb::launch_sgemm_nn(temb, ctx->w_temb.as<float>(), ctx->ct01.as<float>(), n_steps, C2, ctx->temb_dim,
-                                ctx->temb_dim, C2, C2, 0, stream));
-  ctx->launches += 1;
+  if (ctx_sgemm(ctx, temb, ctx->w_temb.as<float>(), ctx->ct01.as<float>(), n_steps, C2, ctx->temb_dim, ctx->temb_dim, C2,
+                C2, 0, stream))
+    return 1;
   ctx->n_steps_cond = n_steps;
   return 0;
 }
@@ -903,13 +916,15 @@ int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts
       fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(ctx->pn_row0.as<float>(), ctx->pn_b0[b].as<float>(), n_clouds, H);
       fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(ctx->pn_rows.as<float>(), ctx->pn_b1[b].as<float>(), n_clouds, H);
       EHB_CUDA(cudaGetLastError());
-      EHB_CUDA(ehb::launch_sgemm_nn(ctx->pn_pooled_relu.as<float>(), ctx->pn_w0b_t[b].as<float>(), ctx->pn_row0.as<float>(),
-                                    n_clouds, H, H, H, H, H, 1, stream));
-      EHB_CUDA(ehb::launch_sgemm_nn(ctx->pn_pooled.as<float>(), ctx->pn_wsb_t[b].as<float>(), ctx->pn_rows.as<float>(),
-                                    n_clouds, H, H, H, H, H, 1, stream));
+      if (ctx_sgemm(ctx, ctx->pn_pooled_relu.as<float>(), ctx->pn_w0b_t[b].as<float>(), ctx->pn_row0.as<float>(), n_clouds, H,
+                    H, H, H, H, 1, stream))
+        return 1;
+      if (ctx_sgemm(ctx, ctx->pn_pooled.as<float>(), ctx->pn_wsb_t[b].as<float>(), ctx->pn_rows.as<float>(), n_clouds, H, H,
+                    H, H, H, 1, stream))
+        return 1;
       row0 = ctx->pn_row0.as<float>();
       rows_s = ctx->pn_rows.as<float>();
-      ctx->launches += 4;
+      ctx->launches += 2;
     }
     ehb::LinearParams p{};
     p.overflow_flag = ovf;
@@ -959,10 +974,23 @@ int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts
     const size_t n = static_cast<size_t>(n_clouds) * ctx->pn_out;
     fill_rows_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(feats, ctx->pn_fcc_b.as<float>(), n_clouds, ctx->pn_out);
     EHB_CUDA(cudaGetLastError());
-    EHB_CUDA(ehb::launch_sgemm_nn(ctx->pn_pooled_relu.as<float>(), ctx->pn_fcc_t.as<float>(), feats, n_clouds, ctx->pn_out, H, H,
-                                  ctx->pn_out, ctx->pn_out, 1, stream));
-    ctx->launches += 2;
+    if (ctx_sgemm(ctx, ctx->pn_pooled_relu.as<float>(), ctx->pn_fcc_t.as<float>(), feats, n_clouds, ctx->pn_out, H, H, ctx->pn_out,
+                  ctx->pn_out, 1, stream))
+      return 1;
+    ctx->launches += 1;
   }
+  return 0;
+}
+
+int ehb_maxpool3x3s2_nhwc(ehb_ctx* ctx, const float* in, int n, int h, int w, int c, float* out, void* stream_) {
+  if (!ctx || !in || !out) return fail("ehb_maxpool3x3s2_nhwc: null argument");
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || c % 4 != 0)
+    return fail("ehb_maxpool3x3s2_nhwc: need positive n, h, w and a channel count that is a multiple of 4");
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15)
+    return fail("ehb_maxpool3x3s2_nhwc: pointers must be 16-byte aligned");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_maxpool3x3s2_nhwc(in, out, n, h, w, c, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += 1;
   return 0;
 }
 

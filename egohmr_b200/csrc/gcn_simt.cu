@@ -9,30 +9,32 @@ namespace ehb {
 namespace {
 
 // ------------------------------------------------------------------------------------------------ sgemm
-constexpr int GK = 16;
-
-// GT x GT output tile per 256-thread block, (GT/16)^2 outputs per thread.  GT = 32 is used for skinny problems (the
-// per-batch conditioning folds have M = n_img rows) so that the grid still covers the SMs.
-template <int GT>
+// GT x GT output tile per 256-thread block, (GT/16)^2 outputs per thread, K consumed GK at a time.  GT = 32 is used for
+// skinny problems (the per-batch conditioning folds have M = n_img rows).  blockIdx.z selects a K chunk (split-K): chunk
+// z accumulates A[:, z*kc : (z+1)*kc] . B[z*kc : (z+1)*kc, :] into its own partial plane C + z*plane (summed in a fixed
+// order by splitk_reduce_kernel, so results do not depend on scheduling).
+template <int GT, int GK>
 __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                        float* __restrict__ C, int M, int N, int K, int lda, int ldb,
-                                                       int ldc, int accumulate) {
+                                                       int ldc, int accumulate, int kc, size_t plane) {
   __shared__ float As[GK][GT + 4];
   __shared__ float Bs[GK][GT + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+  const int kbeg = blockIdx.z * kc, kend = min(K, kbeg + kc);
+  C += static_cast<size_t>(blockIdx.z) * plane;
   constexpr int R = GT / 16;
   float acc[R][R] = {};
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
     for (int e = threadIdx.x; e < GT * GK; e += 256) {
       const int mm = e / GK, kk = e % GK;
       const int gm = m0 + mm, gk = k0 + kk;
-      As[kk][mm] = (gm < M && gk < K) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
+      As[kk][mm] = (gm < M && gk < kend) ? A[static_cast<size_t>(gm) * lda + gk] : 0.f;
     }
     for (int e = threadIdx.x; e < GT * GK; e += 256) {
       const int kk = e / GT, nn = e % GT;
       const int gk = k0 + kk, gn = n0 + nn;
-      Bs[kk][nn] = (gk < K && gn < N) ? B[static_cast<size_t>(gk) * ldb + gn] : 0.f;
+      Bs[kk][nn] = (gk < kend && gn < N) ? B[static_cast<size_t>(gk) * ldb + gn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -61,6 +63,18 @@ __global__ void __launch_bounds__(256) sgemm_nn_kernel(const float* __restrict__
       *dst = accumulate ? (*dst + acc[i][jn]) : acc[i][jn];
     }
   }
+}
+
+// C[m][n] = (accumulate ? C[m][n] : 0) + sum_z partial[z][m][n], z ascending
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int M, int N, int ldc,
+                                     int splits, int accumulate) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(M) * N) return;
+  const int m = static_cast<int>(i / N), n = static_cast<int>(i % N);
+  float* dst = C + static_cast<size_t>(m) * ldc + n;
+  float acc = accumulate ? *dst : 0.f;
+  for (int z = 0; z < splits; ++z) acc += partial[static_cast<size_t>(z) * M * N + i];
+  *dst = acc;
 }
 
 // fp16 hi/lo operand split shared by every producer of a GEMM A operand
@@ -318,11 +332,43 @@ cudaError_t launch_sgemm_nn(const float* A, const float* B, float* C, int M, int
   if (M <= 0 || N <= 0) return cudaSuccess;
   if (static_cast<long long>((N + 63) / 64) * ((M + 63) / 64) < 256) {   // skinny: smaller tiles, more blocks
     dim3 grid((N + 31) / 32, (M + 31) / 32);
-    sgemm_nn_kernel<32><<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+    sgemm_nn_kernel<32, 16><<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, K, 0);
   } else {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    sgemm_nn_kernel<64><<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate);
+    sgemm_nn_kernel<64, 16><<<grid, 256, 0, stream>>>(A, B, C, M, N, K, lda, ldb, ldc, accumulate, K, 0);
   }
+  return cudaGetLastError();
+}
+
+int sgemm_splitk_plan(int M, int N, int K, int num_sms) {
+  // skinny problems only (few output tiles, long K): enough K chunks for ~4 blocks per SM, each at least 32 deep
+  const long long tiles = static_cast<long long>((N + 31) / 32) * ((M + 31) / 32);
+  if (tiles >= 2LL * num_sms || K < 128) return 1;
+  long long want = (4LL * num_sms + tiles - 1) / tiles;
+  long long cap = K / 32;
+  long long s = want < cap ? want : cap;
+  return static_cast<int>(s < 1 ? 1 : (s > 64 ? 64 : s));
+}
+
+cudaError_t launch_sgemm_nn_splitk(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb,
+                                   int ldc, int accumulate, float* scratch, int splits, int* n_launches,
+                                   cudaStream_t stream) {
+  if (n_launches) *n_launches = 0;
+  if (M <= 0 || N <= 0) return cudaSuccess;
+  if (splits <= 1 || !scratch) {
+    if (n_launches) *n_launches = 1;
+    return launch_sgemm_nn(A, B, C, M, N, K, lda, ldb, ldc, accumulate, stream);
+  }
+  int kc = (K + splits - 1) / splits;
+  kc = (kc + 31) / 32 * 32;
+  splits = (K + kc - 1) / kc;
+  dim3 grid((N + 31) / 32, (M + 31) / 32, splits);
+  sgemm_nn_kernel<32, 32><<<grid, 256, 0, stream>>>(A, B, scratch, M, N, K, lda, ldb, N, 0, kc,
+                                                    static_cast<size_t>(M) * N);
+  const size_t n = static_cast<size_t>(M) * N;
+  splitk_reduce_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(scratch, C, M, N, ldc, splits,
+                                                                                   accumulate);
+  if (n_launches) *n_launches = 2;
   return cudaGetLastError();
 }
 

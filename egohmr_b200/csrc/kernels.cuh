@@ -55,6 +55,13 @@ cudaError_t launch_gcn_hidden_simt(const float* x_f32, const float* wcat /*[K][2
 cudaError_t launch_sgemm_nn(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb, int ldc,
                             int accumulate, cudaStream_t stream);
 
+// Deterministic split-K variant for skinny problems (M = images / clouds): `splits` K chunks write partial planes into
+// `scratch` (>= splits*M*N floats), a second kernel sums them in a fixed order.  splits <= 1 falls back to the above.
+int sgemm_splitk_plan(int M, int N, int K, int num_sms);
+cudaError_t launch_sgemm_nn_splitk(const float* A, const float* B, float* C, int M, int N, int K, int lda, int ldb,
+                                   int ldc, int accumulate, float* scratch, int splits, int* n_launches,
+                                   cudaStream_t stream);
+
 struct InputLayerParams {
   AdjMix adj;
   const float* a01;      // [n_img][2][C]   img_feat . W_k[0:img_dim]
@@ -164,6 +171,9 @@ cudaError_t launch_pointnet_pos(const float* pts, const float* w, const float* b
                                 long long M, int C, float act_scale, int* overflow_flag, cudaStream_t stream);
 cudaError_t launch_pool_init(int* pool, int n, cudaStream_t stream);
 cudaError_t launch_pool_decode(const int* pool, float* out, int n, cudaStream_t stream);
+
+// ---- image ops (image_ops.cu): MaxPool2d(3, 2, 1) on NHWC fp32, C % 4 == 0; out is [N][(H+1)/2][(W+1)/2][C]
+cudaError_t launch_maxpool3x3s2_nhwc(const float* in, float* out, int N, int H, int W, int C, cudaStream_t stream);
 
 // ---- guidance backward (smpl_bwd.cu)
 cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, cudaStream_t stream);

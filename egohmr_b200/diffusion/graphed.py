@@ -47,6 +47,7 @@ class GraphedSampler:
         # every tensor of the batch is a graph input, except the two keys the sampler itself writes into the dict
         # (gaussian_diffusion.py:256 'x_t', egohmr.py:189 'vis_mask_smpl')
         self._paths = [p for p, _ in _flat_items(self.static_batch) if p[0] not in ("x_t", "vis_mask_smpl")]
+        self._staging = None
         self.static_noise = None
         if external_noise:
             n_bodies = batch["img"].shape[0] * num_samples
@@ -75,11 +76,33 @@ class GraphedSampler:
         self._iob = np.repeat(np.arange(batch["img"].shape[0], dtype=np.int32), num_samples)
         model._cond_key = None   # the eager cache must not believe it has seen a later batch
 
+    # ---------------------------------------------------------------- pipelined host -> device input staging
+    def stage(self, batch):
+        """Start copying `batch` (typically pinned host tensors) into a device-side staging copy of the inputs on a
+        separate copy stream, so that the transfer of batch i+1 overlaps the replay of batch i.  Consume it with
+        `sampler(staged=True)`."""
+        if self._staging is None:
+            self._staging = self._clone({k: v for k, v in self.static_batch.items() if k not in ("x_t", "vis_mask_smpl")})
+            self._copy_stream = th.cuda.Stream()
+            self._staged_evt, self._consumed_evt = th.cuda.Event(), th.cuda.Event()
+            self._consumed_evt.record()
+        self._copy_stream.wait_event(self._consumed_evt)     # the previous staging content has been moved on
+        with th.cuda.stream(self._copy_stream):
+            for path in self._paths:
+                _get(self._staging, path).copy_(_get(batch, path), non_blocking=True)
+            self._staged_evt.record()
+
     def _version(self):
         return sum(p._version for p in self.model.parameters())
 
-    def __call__(self, batch=None, noise=None):
-        """Replay the pass on `batch` (same shapes as at capture; None = reuse the static inputs as they are)."""
+    def __call__(self, batch=None, noise=None, staged=False):
+        """Replay the pass on `batch` (same shapes as at capture; None = reuse the static inputs as they are;
+        `staged=True` = the batch handed to the last `stage()` call)."""
+        if staged:
+            if self._staging is None:
+                raise RuntimeError("stage(batch) must be called before sampler(staged=True)")
+            th.cuda.current_stream().wait_event(self._staged_evt)
+            batch = self._staging
         if (noise is not None) != (self.static_noise is not None) and noise is not None:
             raise ValueError("this sampler was captured with torch's generator as the noise source (external_noise=False)")
         if noise is not None:
@@ -103,5 +126,7 @@ class GraphedSampler:
                 if src.shape != dst.shape:
                     raise ValueError(f"batch['{'/'.join(path)}'] has shape {tuple(src.shape)}, captured {tuple(dst.shape)}")
                 dst.copy_(src, non_blocking=True)
+            if staged:
+                self._consumed_evt.record()
         self.graph.replay()
         return self.static_out

@@ -143,6 +143,17 @@ class Engine:
         check(self.lib.ehb_pointnet_forward(self._h, _dev_ptr(pts), n_clouds, n_pts, _dev_ptr(out), _stream()))
         return out
 
+    def maxpool3x3s2(self, x):
+        """nn.MaxPool2d(3, 2, 1) on a channels_last [N,C,H,W] fp32 CUDA tensor (NHWC in memory) -> channels_last."""
+        N, Cc, H, W = x.shape
+        if not x.is_contiguous(memory_format=torch.channels_last) or x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError("maxpool3x3s2 expects a channels_last float32 CUDA tensor")
+        out = torch.empty((N, Cc, (H + 1) // 2, (W + 1) // 2), device=x.device, dtype=torch.float32,
+                          memory_format=torch.channels_last)
+        check(self.lib.ehb_maxpool3x3s2_nhwc(self._h, C.c_void_p(x.data_ptr()), N, H, W, Cc, C.c_void_p(out.data_ptr()),
+                                             _stream()))
+        return out
+
     def set_norm(self, mean, std):
         m, s = f32(mean).reshape(144), f32(std).reshape(144)
         check(self.lib.ehb_set_norm(self._h, fptr(m), fptr(s)))

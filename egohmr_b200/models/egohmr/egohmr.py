@@ -199,7 +199,7 @@ class EgoHMR(nn.Module):
         std = self.body_rep_std if self.body_rep_std is not None else torch.ones(144)
         self.engine.set_norm(torch.as_tensor(mean).detach().float().cpu().numpy(),
                              torch.as_tensor(std).detach().float().cpu().numpy())
-        self._fast_backbone = FoldedResNet50(self.backbone)
+        self._fast_backbone = FoldedResNet50(self.backbone, self.engine)
         self._fast_scene_enc = SplitPointNet(self.scene_enc)   # PyTorch form (kept for comparison / odd shapes)
         self.engine.load_pointnet({k: v for k, v in self.state_dict().items() if k.startswith("scene_enc.")})
         self._weights_dirty = False

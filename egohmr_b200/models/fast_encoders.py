@@ -21,15 +21,20 @@ def _fold(conv, bn):
 
 
 class FoldedResNet50:
-    def __init__(self, net):
+    def __init__(self, net, engine=None):
+        self.engine = engine   # optional: the stem max-pool runs on the library's NHWC kernel (5x torch's)
         with torch.no_grad():
             self.stem = _fold(net.conv1, net.bn1)
             self.blocks = []
             for li in range(1, 5):
                 for blk in getattr(net, f"layer{li}"):
                     ds = None if blk.downsample is None else (_fold(blk.downsample[0], blk.downsample[1]), blk.downsample[0].stride)
+                    c3 = _fold(blk.conv3, blk.bn3)
+                    # relu(conv3(y) + b3 + ds(x) + b_ds): the projection's bias rides on conv3's, so the projection is a
+                    # bias-free convolution and no separate elementwise bias-add pass over the block output is needed
+                    c3_gpu = c3 if ds is None else (c3[0], (c3[1] + ds[0][1]).contiguous())
                     self.blocks.append((_fold(blk.conv1, blk.bn1), _fold(blk.conv2, blk.bn2), blk.conv2.stride,
-                                        _fold(blk.conv3, blk.bn3), ds))
+                                        c3, ds, c3_gpu))
 
     @torch.no_grad()
     def __call__(self, x):
@@ -38,16 +43,16 @@ class FoldedResNet50:
             # cuDNN's fused conv + bias (+ residual) + ReLU: one kernel per convolution instead of conv, bias-add, relu
             cr = lambda t, wb, stride, pad: torch.cudnn_convolution_relu(t, wb[0], wb[1], stride, pad, (1, 1), 1)
             x = cr(x, self.stem, (2, 2), (3, 3))
-            x = F.max_pool2d(x, 3, 2, 1)
-            for (c1, c2, s2, c3, ds) in self.blocks:
+            x = self.engine.maxpool3x3s2(x) if self.engine is not None else F.max_pool2d(x, 3, 2, 1)
+            for (c1, c2, s2, c3, ds, c3g) in self.blocks:
                 y = cr(x, c1, (1, 1), (0, 0))
                 y = cr(y, c2, tuple(s2), (1, 1))
-                idt = x if ds is None else F.conv2d(x, ds[0][0], ds[0][1], stride=ds[1])
-                x = torch.cudnn_convolution_add_relu(y, c3[0], idt, 1.0, c3[1], (1, 1), (0, 0), (1, 1), 1)
+                idt = x if ds is None else F.conv2d(x, ds[0][0], None, stride=ds[1])
+                x = torch.cudnn_convolution_add_relu(y, c3g[0], idt, 1.0, c3g[1], (1, 1), (0, 0), (1, 1), 1)
             return x.mean(dim=(2, 3))
         x = F.relu_(F.conv2d(x, self.stem[0], self.stem[1], stride=2, padding=3))
         x = F.max_pool2d(x, 3, 2, 1)
-        for (c1, c2, s2, c3, ds) in self.blocks:
+        for (c1, c2, s2, c3, ds, _) in self.blocks:
             y = F.relu_(F.conv2d(x, c1[0], c1[1]))
             y = F.relu_(F.conv2d(y, c2[0], c2[1], stride=s2, padding=1))
             y = F.conv2d(y, c3[0], c3[1])

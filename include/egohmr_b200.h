@@ -159,6 +159,10 @@ int ehb_pointnet_load(ehb_ctx* ctx, const ehb_pointnet_weights* w);
 /* scene_enc(scene_pcd_verts) (egohmr.py:214): pts [n_clouds][n_pts][3] -> feats [n_clouds][out_dim]. */
 int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts, float* feats, void* stream);
 
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) of the ResNet stem (models/resnet.py:113,142) on an NHWC fp32
+ * tensor: in [n][h][w][c] -> out [n][(h+1)/2][(w+1)/2][c]; c % 4 == 0, 16-byte aligned pointers. */
+int ehb_maxpool3x3s2_nhwc(ehb_ctx* ctx, const float* in, int n, int h, int w, int c, float* out, void* stream);
+
 /* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
  * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);

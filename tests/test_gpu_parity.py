@@ -260,11 +260,41 @@ def test_graphed_sampler_equals_eager(full):
         ref = diffusion.sample_many(model, b, S, "ddim5", noise=nz)
         for k in ("pred_x_start", "pred_vertices", "pred_keypoints_3d", "pred_keypoints_2d_full", "sample"):
             assert torch.equal(got[k], ref[k]), k
+    # pipelined input staging from pinned host memory gives the same bits
+    pin = lambda d: {k: (pin(v) if isinstance(v, dict) else v.cpu().pin_memory()) for k, v in d.items()
+                     if k not in ("x_t", "vis_mask_smpl")}
+    sampler.stage(pin(b1))
+    got = sampler(staged=True, noise=nz)["pred_x_start"].clone()
+    model._cond_key = None
+    assert torch.equal(got, diffusion.sample_many(model, b1, S, "ddim5", noise=nz)["pred_x_start"])
     rng_sampler = diffusion.capture_sample_many(model, b0, S, "ddim5")
     a = rng_sampler(b0)["pred_x_start"].clone()
     c = rng_sampler(b0)["pred_x_start"].clone()
     assert torch.isfinite(a).all() and not torch.equal(a, c)
     assert not model.engine.check_overflow()
+
+
+def test_maxpool_nhwc_bit_exact(full):
+    """The ResNet stem's MaxPool2d(3, 2, 1) on the library's NHWC kernel equals torch's, including odd sizes."""
+    eng = full[0].engine
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape in [(2, 64, 112, 112), (3, 8, 7, 9), (1, 4, 1, 1)]:
+        x = torch.randn(*shape, device="cuda", generator=g).contiguous(memory_format=torch.channels_last)
+        assert torch.equal(eng.maxpool3x3s2(x), torch.nn.functional.max_pool2d(x, 3, 2, 1))
+
+
+def test_folded_resnet_matches_module(full):
+    """Inference-form ResNet-50 (BN folded, fused cuDNN conv+bias+ReLU, projection bias folded into conv3, NHWC max-pool
+    kernel) against the plain nn.Module with the reference's layer structure; TF32 is off in this module."""
+    model = full[0]
+    model._sync_engine()
+    img = _tb(synth.make_batch(4, 3))["img"]
+    with torch.no_grad():
+        ref = model.backbone(img)
+        got = model._fast_backbone(img)
+    d = (ref - got).abs().max().item()
+    print(f"folded ResNet-50 vs module: max|d| = {d:.3e} (max|feat| = {ref.abs().max().item():.3f})")
+    assert d < 2e-5 * max(1.0, ref.abs().max().item())
 
 
 def test_sample_many_equals_sequential_chains(full):
