@@ -161,6 +161,11 @@ class EgoHMR(nn.Module):
         # collision guidance is a pluggable callable with COAP's signature: `attach_coap` upstream
         self.collision_model = collision_model
         self.weight_coap_penetration, self.start_coap_epoch = weight_coap_penetration, start_coap_epoch
+        self.loss_weights = {"v2v": weight_loss_v2v, "keypoints_3d": weight_loss_keypoints_3d,
+                             "keypoints_3d_full": weight_loss_keypoints_3d_full,
+                             "keypoints_2d_full": weight_loss_keypoints_2d_full, "betas": weight_loss_betas,
+                             "body_pose": weight_loss_body_pose, "global_orient": weight_loss_global_orient,
+                             "pose_6d_ortho": weight_loss_pose_6d_ortho}
         self.to(self.device)
         self._weights_dirty = True
         self._cond_key = None
@@ -406,6 +411,65 @@ class EgoHMR(nn.Module):
                 ratios.append(0.0)
         return ratios
 
+    SMPL_TO_OPENPOSE = [24, 12, 17, 19, 21, 16, 18, 20, 0, 2, 5, 8, 1, 4, 7, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34]  # :108
+
+    @torch.no_grad()
     def compute_loss(self, batch, output, cur_epoch=0):
-        raise NotImplementedError("validation losses need ground-truth keys and are outside the sampling hot path; "
-                                  "call val_losses(..., compute_loss=False)")
+        """EgoHMR.compute_loss in validation mode (egohmr.py:305-445) — what `val_losses` runs by default
+        (gaussian_diffusion.py:777-778; test_egohmr.py:252-255 does not pass compute_loss).  Adds `output['losses']` and
+        `output['joint_vis_num_batch']`, returns the weighted total.  Small host-side tensor plumbing on the final
+        outputs; the ground-truth bodies go through the CUDA SMPL (pose2rot=True)."""
+        if self.training:
+            raise NotImplementedError("training-mode compute_loss (autograd through the denoiser) is out of scope")
+        for k in ("keypoints_3d", "keypoints_3d_full", "smpl_params_is_axis_angle", "gender"):
+            if k not in batch:
+                raise KeyError(f"compute_loss needs batch['{k}'] (ground truth, egobody_dataset.py:241-277); pass "
+                               f"compute_loss=False to val_losses for label-free sampling")
+        p = output["pred_smpl_params"]
+        kp3d = output["pred_keypoints_3d"][:, 0:24]
+        kp3d_full = output["pred_keypoints_3d_full"][:, 0:24]
+        kp2d = output["pred_keypoints_2d_full"][:, self.SMPL_TO_OPENPOSE, :]
+        bs = p["body_pose"].shape[0]
+        gt2d, gt3d, gt3d_full = batch["orig_keypoints_2d"], batch["keypoints_3d"], batch["keypoints_3d_full"]
+        gp, is_aa, gender = batch["smpl_params"], batch["smpl_params_is_axis_angle"], batch["gender"]
+        conf = gt2d[:, :, -1].unsqueeze(-1).clone()                               # losses.py:20-24
+        conf[:, [1, 9, 12], :] = 0
+        l_2d = (conf * (kp2d - gt2d[:, :, :-1]).abs()).sum(dim=(1, 2)).mean()
+        l_3d = ((kp3d - kp3d[:, [0]]) - (gt3d - gt3d[:, [0]])).abs().sum(dim=(1, 2)).mean()      # pelvis_align=True
+        l_3d_full = (kp3d_full - gt3d_full).abs().sum(dim=(1, 2)).mean()
+        gt_args = {k: v.float() for k, v in gp.items()}
+        gm, gf = self.smpl_male(**gt_args), self.smpl_female(**gt_args)            # :344-351
+        gt_v, gt_j = gm.vertices, gm.joints
+        fem = gender == 1
+        gt_v[fem], gt_j[fem] = gf.vertices[fem], gf.joints[fem]
+        l_v2v = ((output["pred_vertices"] - kp3d[:, [0]]) - (gt_v - gt_j[:, [0]])).abs().mean()
+        g2d = perspective_projection(gt_j, torch.zeros(bs, 3, device=gt_j.device), self.focal_length,
+                                     self.camera_center_full)[:, :24]              # :361-366
+        vis = (g2d[:, :, 0] >= 0) * (g2d[:, :, 0] < 1920) * (g2d[:, :, 1] >= 0) * (g2d[:, :, 1] < 1080)
+        l_vis = (torch.sqrt((((kp3d - kp3d[:, [0]]) - (gt3d[:, 0:24] - gt3d[:, [0]])) ** 2).sum(dim=-1)) * vis).sum()
+        from ...utils.geometry import aa_to_rotmat
+        lp = {}
+        for k, pred in p.items():
+            if k != "transl":
+                gt = gp[k]
+                if bool(torch.as_tensor(is_aa[k]).all()):
+                    gt = aa_to_rotmat(gt.reshape(-1, 3)).view(bs, -1, 3, 3)
+                lp[k] = ((pred - gt) ** 2).sum() / bs
+        p6 = output["pred_pose_6d"].reshape(-1, 3, 2)
+        l_ortho = ((torch.matmul(p6.permute(0, 2, 1), p6) - torch.eye(2, device=p6.device, dtype=p6.dtype).unsqueeze(0)) ** 2).mean()
+        l_coap = torch.tensor(0.0, device=p6.device)
+        if self.weight_coap_penetration > 0 and cur_epoch >= self.start_coap_epoch:
+            raise NotImplementedError("the COAP penetration term of compute_loss is a training loss (its weight is 0 in "
+                                      "test_egohmr.py:112-118)")
+        w = self.loss_weights
+        loss = (w["v2v"] * l_v2v + w["keypoints_3d"] * l_3d + w["keypoints_3d_full"] * l_3d_full
+                + w["keypoints_2d_full"] * l_2d + w["betas"] * lp["betas"] + w["body_pose"] * lp["body_pose"]
+                + w["global_orient"] * lp["global_orient"] + w["pose_6d_ortho"] * l_ortho
+                + self.weight_coap_penetration * l_coap)
+        output["losses"] = dict(loss=loss.detach(), loss_v2v=l_v2v.detach(), loss_keypoints_3d=l_3d.detach(),
+                                loss_keypoints_3d_full=l_3d_full.detach(), loss_keypoints_2d_full=l_2d.detach(),
+                                loss_betas=lp["betas"].detach(), loss_body_pose=lp["body_pose"].detach(),
+                                loss_global_orient=lp["global_orient"].detach(), loss_pose_6d_ortho=l_ortho.detach(),
+                                loss_coap_penetration=l_coap.detach(), loss_keypoints_3d_vis_batch_sum=l_vis.detach())
+        output["joint_vis_num_batch"] = vis.sum()
+        return loss

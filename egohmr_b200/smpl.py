@@ -88,9 +88,9 @@ class SMPL(nn.Module):
         n = betas.shape[0]
         eng = self._eng(dev)
         if pose2rot:
-            from .utils.geometry import aa_to_rotmat
+            from .utils.geometry import batch_rodrigues
             full = torch.cat([global_orient.reshape(n, -1, 3), body_pose.reshape(n, -1, 3)], dim=1)
-            R = aa_to_rotmat(full.reshape(-1, 3)).reshape(n, 24, 3, 3)
+            R = batch_rodrigues(full.reshape(-1, 3).float()).reshape(n, 24, 3, 3)
         else:
             R = torch.cat([global_orient.reshape(n, -1, 3, 3), body_pose.reshape(n, -1, 3, 3)], dim=1)
         R = R.float().contiguous()

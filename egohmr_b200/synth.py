@@ -189,6 +189,33 @@ def make_batch(seed=0, n_img=2, n_pts=1024):
     }
 
 
+def make_gt(seed=0, n_img=2):
+    """Ground-truth keys `model.compute_loss` reads (dataloaders/egobody_dataset.py:241-277, egohmr.py:320-325):
+    merge into a `make_batch` dict (smpl_params gains global_orient / body_pose / betas next to transl)."""
+    rng = np.random.default_rng(6000 + seed)
+    f32 = np.float32
+    kp3d = rng.normal(0, 0.3, (n_img, 24, 3)).astype(f32)
+    return {
+        "keypoints_3d": kp3d,
+        "keypoints_3d_full": (kp3d + np.array([0, 0, 3.0])).astype(f32),
+        "smpl_params": {"global_orient": rng.normal(0, 0.5, (n_img, 3)).astype(f32),
+                        "body_pose": rng.normal(0, 0.3, (n_img, 69)).astype(f32),
+                        "betas": rng.normal(0, 1.0, (n_img, 10)).astype(f32)},
+        "smpl_params_is_axis_angle": {"global_orient": np.ones(n_img, bool), "body_pose": np.ones(n_img, bool),
+                                      "betas": np.zeros(n_img, bool)},
+        "gender": (rng.uniform(0, 1, n_img) < 0.5).astype(np.int64),
+    }
+
+
+def merge_gt(batch, gt):
+    out = dict(batch)
+    out["smpl_params"] = {**batch["smpl_params"], **gt["smpl_params"]}
+    for k, v in gt.items():
+        if k != "smpl_params":
+            out[k] = v
+    return out
+
+
 def make_noise(seed, n_chains, n_bodies_per_chain, n_steps):
     """Pre-drawn noise in the reference's RNG consumption order: per chain, randn(bs,144) then one draw per step."""
     rng = np.random.default_rng(5000 + seed)

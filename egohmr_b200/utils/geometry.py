@@ -22,9 +22,23 @@ def rot6d_to_rotmat(x, rot6d_mode="diffusion", engine=None):
     return (engine or _engine_for(x6.device)).rot6d_to_rotmat(x6)
 
 
+def batch_rodrigues(rot_vecs):
+    """smplx/lbs.py::batch_rodrigues (what SMPL.forward(pose2rot=True) applies to axis-angle input — ground-truth bodies
+    in compute_loss, egohmr.py:344-347, and in the driver, test_egohmr.py:307-312): angle = |v + 1e-8|,
+    R = I + sin(angle) K + (1 - cos(angle)) K K."""
+    angle = torch.norm(rot_vecs + 1e-8, dim=1, keepdim=True)
+    rot_dir = rot_vecs / angle
+    cos, sin = torch.cos(angle).unsqueeze(1), torch.sin(angle).unsqueeze(1)
+    rx, ry, rz = torch.split(rot_dir, 1, dim=1)
+    zeros = torch.zeros_like(rx)
+    K = torch.cat([zeros, -rz, ry, rz, zeros, -rx, -ry, rx, zeros], dim=1).view(-1, 3, 3)
+    ident = torch.eye(3, dtype=rot_vecs.dtype, device=rot_vecs.device).unsqueeze(0)
+    return ident + sin * K + (1 - cos) * torch.bmm(K, K)
+
+
 def aa_to_rotmat(theta):
-    """utils/geometry.py:5-21 (axis-angle -> quaternion -> matrix); only reached through SMPL(pose2rot=True),
-    i.e. when the driver evaluates ground-truth bodies — not on the sampling path."""
+    """utils/geometry.py:5-43 (axis-angle -> quaternion -> matrix): the conversion compute_loss applies to the
+    ground-truth pose for the parameter losses (egohmr.py:381)."""
     norm = torch.norm(theta + 1e-8, p=2, dim=1)
     angle = norm.unsqueeze(-1)
     normalized = theta / angle

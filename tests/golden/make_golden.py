@@ -157,6 +157,35 @@ def guide_case(name, dtype, n_img=3, seed=0):
           sorted(set(np.nonzero(grad.detach().numpy().reshape(n_img, 24, 6).any(axis=(0, 2)))[0].tolist())), "coll", ratios)
 
 
+def loss_case(name, dtype, n_img=3, seed=0):
+    """val_losses with its DEFAULT compute_loss=True, exactly how test_egohmr.py:252-255 calls it: the sampler's last
+    output goes through EgoHMR.compute_loss (egohmr.py:305-445), which adds 'losses' and 'joint_vis_num_batch'."""
+    from diffusion.model_util import create_gaussian_diffusion
+    model, mean, std = build_reference(256, 2, dtype, seed)
+    diffusion = create_gaussian_diffusion(num_diffusion_timesteps=50, timestep_respacing="ddim5",
+                                          body_rep_mean=torch.from_numpy(mean).to(dtype),
+                                          body_rep_std=torch.from_numpy(std).to(dtype))
+    b = synth.merge_gt(synth.make_batch(seed, n_img), synth.make_gt(seed, n_img))
+    batch = to_torch(b, dtype)
+    batch["gender"] = torch.from_numpy(b["gender"])
+    batch["smpl_params_is_axis_angle"] = {k: torch.from_numpy(v) for k, v in b["smpl_params_is_axis_angle"].items()}
+    feed = NoiseFeed(synth.make_noise(seed, 1, n_img, 5)[0], dtype)
+    old_randn, old_randn_like = torch.randn, torch.randn_like
+    torch.randn, torch.randn_like = feed.randn, feed.randn_like
+    try:
+        with torch.no_grad():
+            out = diffusion.val_losses(model=model, batch=batch, shape=[n_img, 144], progress=False, clip_denoised=False,
+                                       cur_epoch=0, timestep_respacing="ddim5", cond_fn_with_grad=False,
+                                       cond_grad_weight=1.0)
+    finally:
+        torch.randn, torch.randn_like = old_randn, old_randn_like
+    rec = {"loss_" + k if not k.startswith("loss") else k: v.detach().numpy() for k, v in out["losses"].items()}
+    rec["joint_vis_num_batch"] = out["joint_vis_num_batch"].detach().numpy()
+    rec["pred_x_start"] = out["pred_x_start"].detach().numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, {k: float(v) for k, v in rec.items() if v.ndim == 0})
+
+
 def schedule_tables():
     from diffusion.model_util import create_gaussian_diffusion
     rec = {}
@@ -207,6 +236,9 @@ if __name__ == "__main__":
         run_case("ddim5_T50_hid256_maskall_f64", 50, "ddim5", 256, 2, 3, torch.float64, only_mask_img_cond=False)
         run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "loss":
+        loss_case("val_losses_compute_loss_f32", torch.float32)
+        raise SystemExit(0)
     schedule_tables()
     small_ops()
     run_case("ddim5_T50_hid1024_f32", 50, "ddim5", 1024, 4, 2, torch.float32)
@@ -219,3 +251,4 @@ if __name__ == "__main__":
     run_case("ddpm_guided_T100_hid256_f64", 100, "", 256, 2, 3, torch.float64, guided=True)
     run_case("ddim5_T50_hid256_maskall_f64", 50, "ddim5", 256, 2, 3, torch.float64, only_mask_img_cond=False)
     run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)
+    loss_case("val_losses_compute_loss_f32", torch.float32)

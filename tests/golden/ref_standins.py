@@ -36,6 +36,18 @@ class SMPLOutput:
         self.body_pose = body_pose
 
 
+def batch_rodrigues(rot_vecs):
+    """smplx/lbs.py::batch_rodrigues restated from the published algorithm (angle = |v + 1e-8|, R = I + sin K + (1-cos) K^2)."""
+    angle = torch.norm(rot_vecs + 1e-8, dim=1, keepdim=True)
+    rot_dir = rot_vecs / angle
+    cos, sin = torch.cos(angle).unsqueeze(1), torch.sin(angle).unsqueeze(1)
+    rx, ry, rz = torch.split(rot_dir, 1, dim=1)
+    zeros = torch.zeros_like(rx)
+    K = torch.cat([zeros, -rz, ry, rz, zeros, -rx, -ry, rx, zeros], dim=1).view(-1, 3, 3)
+    ident = torch.eye(3, dtype=rot_vecs.dtype, device=rot_vecs.device).unsqueeze(0)
+    return ident + sin * K + (1 - cos) * torch.bmm(K, K)
+
+
 class TorchSMPL(nn.Module):
     """Torch restatement of smplx.SMPL.forward(pose2rot=False) / lbs() used as the `smplx.create` stand-in."""
 
@@ -57,9 +69,12 @@ class TorchSMPL(nn.Module):
 
     def forward(self, betas=None, body_pose=None, global_orient=None, transl=None, return_full_pose=False,
                 pose2rot=True, **kwargs):
-        assert not pose2rot, "the hot path always passes rotation matrices (egohmr.py:276)"
         B = betas.shape[0]
-        full_pose = torch.cat([global_orient.reshape(B, -1, 3, 3), body_pose.reshape(B, -1, 3, 3)], dim=1)
+        if pose2rot:   # compute_loss evaluates the ground-truth body from axis-angle parameters (egohmr.py:344-347)
+            aa = torch.cat([global_orient.reshape(B, -1, 3), body_pose.reshape(B, -1, 3)], dim=1)
+            full_pose = batch_rodrigues(aa.reshape(-1, 3)).reshape(B, 24, 3, 3)
+        else:
+            full_pose = torch.cat([global_orient.reshape(B, -1, 3, 3), body_pose.reshape(B, -1, 3, 3)], dim=1)
         dt = full_pose.dtype
         v_shaped = self.v_template.to(dt) + torch.einsum("bl,mkl->bmk", betas, self.shapedirs.to(dt))
         J = torch.einsum("bik,ji->bjk", v_shaped, self.J_regressor.to(dt))

@@ -297,6 +297,42 @@ def test_folded_resnet_matches_module(full):
     assert d < 2e-5 * max(1.0, ref.abs().max().item())
 
 
+def test_val_losses_default_compute_loss_vs_reference_golden(small, golden_dir):
+    """test_egohmr.py:252-255 calls val_losses WITHOUT compute_loss=..., i.e. with the default True: the sampler's last
+    output goes through EgoHMR.compute_loss (egohmr.py:305-445).  Same call here, losses against the reference's."""
+    from egohmr_b200.diffusion.model_util import create_gaussian_diffusion
+    from oracle import losses as o_losses
+    model, _, sd, smpl_model, mean, std = small
+    dev = "cuda:0"
+    diffusion = create_gaussian_diffusion(num_diffusion_timesteps=50, timestep_respacing="ddim5",
+                                          body_rep_mean=torch.from_numpy(mean).to(dev), body_rep_std=torch.from_numpy(std).to(dev))
+    g = np.load(os.path.join(golden_dir, "val_losses_compute_loss_f32.npz"))
+    b_np = synth.merge_gt(synth.make_batch(0, 3), synth.make_gt(0, 3))
+    batch = _tb(b_np)
+    noise = torch.from_numpy(synth.make_noise(0, 1, 3, 5)[0]).cuda()
+    from egohmr_b200.diffusion import gaussian_diffusion as gd
+    feed = gd._NoiseFeed(noise)
+    old = (torch.randn, torch.randn_like)
+    torch.randn = lambda *a, **k: feed.initial()
+    torch.randn_like = feed.randn_like
+    try:
+        out = diffusion.val_losses(model=model, batch=batch, shape=[3, 144], progress=False, clip_denoised=False,
+                                   cur_epoch=0, timestep_respacing="ddim5", cond_fn_with_grad=False, cond_grad_weight=1.0)
+    finally:
+        torch.randn, torch.randn_like = old
+    assert np.abs(out["pred_x_start"].cpu().numpy() - g["pred_x_start"]).max() < 5e-6
+    assert int(out["joint_vis_num_batch"]) == int(g["joint_vis_num_batch"])
+    o_out = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else {kk: vv.cpu().numpy() for kk, vv in v.items()})
+             for k, v in out.items() if k not in ("losses", "joint_vis_num_batch")}
+    _, o_ls, _ = o_losses.compute_loss(smpl_model, b_np, o_out)
+    for k, v in out["losses"].items():
+        ref = float(g[k])
+        assert abs(float(v) - ref) <= 5e-5 * max(1.0, abs(ref)), (k, float(v), ref)
+        assert abs(float(v) - float(o_ls[k])) <= 5e-5 * max(1.0, abs(ref)), (k, float(v), float(o_ls[k]))
+    with pytest.raises(KeyError):   # label-free batches must say what is missing instead of failing obscurely
+        diffusion.val_losses(model=model, batch=_tb(synth.make_batch(0, 3)), shape=[3, 144], timestep_respacing="ddim5")
+
+
 def test_sample_many_equals_sequential_chains(full):
     """Flattening the num_samples loop (test_egohmr.py:251-255) into one batch changes nothing: chain (img i, sample n)
     of the flattened run equals the n-th sequential call when both see the same noise."""

@@ -175,3 +175,21 @@ def test_guided_ddpm100_fp64_trace(golden_dir):
     x0s = np.stack([t["pred_x_start"] for t in trace])
     assert np.abs(x0s - g["trace_x0"]).max() < 2e-6
     assert np.abs(out["pred_x_start"] - g["pred_x_start"]).max() < 2e-6
+
+
+def test_compute_loss_golden(golden_dir):
+    """val_losses' default compute_loss=True (what test_egohmr.py:252-255 runs): EgoHMR.compute_loss in eval mode."""
+    from oracle import losses
+    g = np.load(os.path.join(golden_dir, "val_losses_compute_loss_f32.npz"))
+    smpl = synth.make_smpl_model(0)
+    sd = synth.make_state_dict(0, hid=256, n_blocks=2, init_betas=smpl["init_betas"])
+    b = synth.merge_gt(synth.make_batch(0, 3), synth.make_gt(0, 3))
+    mean, std = synth.body_rep_stats(0)
+    sch = schedule.Schedule(50, "ddim5")
+    out = o_egohmr.sample(sd, synth.skeleton_adjacency(), 2, smpl, b, sch, synth.make_noise(0, 1, 3, 5)[0], mean, std, "ddim",
+                          dtype=np.float32)
+    assert np.abs(out["pred_x_start"] - g["pred_x_start"]).max() < 5e-6
+    loss, ls, nvis = losses.compute_loss(smpl, b, out)
+    assert nvis == int(g["joint_vis_num_batch"]) and float(g["loss"]) == 0.0 and loss == 0.0
+    for k, v in ls.items():
+        assert abs(float(v) - float(g[k])) <= 2e-5 * max(1.0, abs(float(g[k]))), (k, float(v), float(g[k]))
