@@ -994,6 +994,17 @@ int ehb_maxpool3x3s2_nhwc(ehb_ctx* ctx, const float* in, int n, int h, int w, in
   return 0;
 }
 
+int ehb_scene_crop(ehb_ctx* ctx, const float* verts, int n_bodies, int n_verts, const float* scene, int n_pts,
+                   const int32_t* img_of_body, uint8_t* mask, int32_t* count, float* bbox, void* stream_) {
+  if (!ctx || !verts || !scene || !mask || !count) return fail("ehb_scene_crop: null argument");
+  if (n_bodies <= 0 || n_verts <= 0 || n_pts <= 0) return fail("ehb_scene_crop: sizes must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_scene_crop(verts, n_bodies, n_verts, scene, n_pts, img_of_body, mask, count, bbox,
+                                  static_cast<cudaStream_t>(stream_)));
+  ctx->launches += 1;
+  return 0;
+}
+
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream_) {
   if (!ctx || !R || !aa) return fail("ehb_rotmat_to_angle_axis: null argument");
   if (n < 0) return fail("ehb_rotmat_to_angle_axis: negative n");

@@ -175,6 +175,11 @@ cudaError_t launch_pool_decode(const int* pool, float* out, int n, cudaStream_t 
 // ---- image ops (image_ops.cu): MaxPool2d(3, 2, 1) on NHWC fp32, C % 4 == 0; out is [N][(H+1)/2][(W+1)/2][C]
 cudaError_t launch_maxpool3x3s2_nhwc(const float* in, float* out, int N, int H, int W, int C, cudaStream_t stream);
 
+// per-body bounding-box crop of the scene cloud (egohmr.py:550-554): mask [B][n_pts], count [B], bbox [B][6] (optional)
+cudaError_t launch_scene_crop(const float* verts, int n_bodies, int V, const float* scene, int n_pts,
+                              const int32_t* img_of_body, uint8_t* mask, int32_t* count, float* bbox,
+                              cudaStream_t stream);
+
 // ---- guidance backward (smpl_bwd.cu)
 cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, cudaStream_t stream);
 // dL/dx [B][144] from dL/dverts [B][V][3], dL/djoints [B][24+E][3], dL/dfull_pose_aa [B][24][3] (each may be null).

@@ -231,6 +231,18 @@ class Engine:
             check(self.lib.ehb_rotmat_to_angle_axis(self._h, _dev_ptr(R), n, _dev_ptr(aa), _stream()))
         return aa
 
+    def scene_crop(self, verts, scene, img_of_body=None):
+        """Bounding-box crop of guide_coll / eval_coll (egohmr.py:550-554) for all bodies at once.
+        verts [B,V,3], scene [n_clouds,N,3], img_of_body int32 [B] (device) or None -> mask bool [B,N], count int32 [B]."""
+        B, V = verts.shape[0], verts.shape[1]
+        N = scene.shape[1]
+        mask = torch.empty(B, N, device=verts.device, dtype=torch.uint8)
+        count = torch.empty(B, device=verts.device, dtype=torch.int32)
+        check(self.lib.ehb_scene_crop(self._h, _dev_ptr(verts), B, V, _dev_ptr(scene), N,
+                                      _dev_ptr(img_of_body, torch.int32, allow_none=True), _dev_ptr(mask, torch.uint8),
+                                      _dev_ptr(count, torch.int32), None, _stream()))
+        return mask.bool(), count
+
     def smpl_backward(self, x_t, betas, g_verts=None, g_joints=None, g_aa=None):
         """dL/dx_t [B,144] for the bodies of set_bodies (guide_coll's autograd.grad, egohmr.py:562)."""
         grad = torch.empty_like(x_t)

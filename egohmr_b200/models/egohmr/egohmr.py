@@ -269,9 +269,10 @@ class EgoHMR(nn.Module):
             self.engine.set_bodies(iob)      # uploads the slot tables (synchronising): only when the layout changes
             self._bodies_key = (bs, num_samples)
             self._bodies_idx = torch.from_numpy(iob.astype(np.int64)).to(img_feats.device)
+            self._bodies_idx32 = self._bodies_idx.to(torch.int32)
         idx = self._bodies_idx
         self._cond = {"vis": vis, "betas_img": betas.float().contiguous(), "scene_pts": pts, "transl": transl,
-                      "img_of_body": idx, "num_samples": num_samples, "bs": bs}
+                      "img_of_body": idx, "img_of_body_i32": self._bodies_idx32, "num_samples": num_samples, "bs": bs}
         self.scene_pcd_verts = pts
         self.input_transl = transl
         self._cond_key = key
@@ -348,18 +349,29 @@ class EgoHMR(nn.Module):
         aa = self.engine.rotmat_to_angle_axis(R.reshape(-1, 3, 3)).reshape(x.shape[0], -1)
         return verts, joints, aa
 
-    def _crop_scene(self, verts_i, img_index):
-        """Scene points of the body's image inside the body's bounding box (egohmr.py:550-554)."""
-        pts = self.scene_pcd_verts[[img_index]]
-        bb_min = verts_i.min(1).values.reshape(1, 3).detach()
-        bb_max = verts_i.max(1).values.reshape(1, 3).detach()
-        inds = (pts >= bb_min).all(-1) & (pts <= bb_max).all(-1)
-        return pts, inds
+    def _crop_scene(self, verts, idx32):
+        """Scene points inside each body's bounding box (egohmr.py:550-554, 504-508), all bodies in ONE launch:
+        -> (mask bool [B,N], count int32 [B]).  The reference does two reductions, a compare and an `.any()` host sync
+        per body."""
+        pts = self.scene_pcd_verts
+        if pts.dtype != torch.float32 or not pts.is_contiguous():
+            pts = pts.float().contiguous()
+        return self.engine.scene_crop(verts, pts, idx32)
+
+    def _body_image_index(self, B):
+        cond = self._cond
+        if cond is not None and len(cond["img_of_body"]) == B:
+            return cond["img_of_body"], cond["img_of_body_i32"]
+        ar = torch.arange(B, device=self.device)
+        return ar, ar.to(torch.int32)
 
     def guide_coll(self, batch, output, t, compute_grad="x_t"):
         """EgoHMR.guide_coll (egohmr.py:517-570): gradient of -mean(collision loss) w.r.t. x_t, leg joints only.
-        Forward and backward through de-normalise / rot6d / SMPL / axis-angle run in the CUDA library; only the
-        pluggable collision term itself is differentiated by autograd, w.r.t. the three tensors it receives."""
+        Forward and backward through de-normalise / rot6d / SMPL / axis-angle run in the CUDA library, the per-body scene
+        crop is one kernel; only the pluggable collision term itself is differentiated by autograd, w.r.t. the three
+        tensors it receives.  A collision model that offers `collision_loss_batched(points[B,N,3], mask[B,N],
+        SMPLOutput) -> [B]` is called once for all bodies; otherwise COAP's per-body `collision_loss(points[1,n,3],
+        SMPLOutput, ret_collision_mask=None)` is called for the bodies that keep at least one point (:545-559)."""
         if self.collision_model is None:
             raise RuntimeError("guide_coll needs a collision model with COAP's collision_loss() (pass collision_model=...)")
         x_t = batch["x_t"] if compute_grad == "x_t" else output["pred_x_start"]
@@ -369,17 +381,25 @@ class EgoHMR(nn.Module):
         if cond is None or self.engine.n_bodies != B:
             cond = self.prepare(batch, num_samples=1)
         verts, joints, aa = self._smpl_state(x)
-        idx = cond["img_of_body"].tolist()
+        idx, idx32 = self._body_image_index(B)
+        mask, count = self._crop_scene(verts, idx32)
         v = verts.detach().requires_grad_()
         j = joints.detach().requires_grad_()
         fp = aa.detach().requires_grad_()
+        cm = self.collision_model
         with torch.enable_grad():
-            losses = torch.zeros(B, device=x.device)
-            for i in range(B):  # the reference evaluates the collision model body by body (:545-559)
-                pts, inds = self._crop_scene(v[[i]], idx[i])
-                if inds.any():
-                    so = smpl_mod.SMPLOutput(vertices=v[[i]], joints=j[[i]], full_pose=fp[[i]])
-                    losses[i] = self.collision_model.collision_loss(pts[inds].unsqueeze(0), so, ret_collision_mask=None)
+            if hasattr(cm, "collision_loss_batched"):
+                losses = cm.collision_loss_batched(self.scene_pcd_verts[idx], mask,
+                                                   smpl_mod.SMPLOutput(vertices=v, joints=j, full_pose=fp))
+            else:
+                counts = count.tolist()            # one host sync for the whole batch
+                idx_l = idx.tolist()
+                losses = torch.zeros(B, device=x.device)
+                for i in range(B):  # COAP's interface is one body per call (:545-559)
+                    if counts[i]:
+                        so = smpl_mod.SMPLOutput(vertices=v[[i]], joints=j[[i]], full_pose=fp[[i]])
+                        losses[i] = cm.collision_loss(self.scene_pcd_verts[idx_l[i]][mask[i]].unsqueeze(0), so,
+                                                      ret_collision_mask=None)
             if int((losses == 0).sum()) >= B:
                 return torch.zeros(B, 144, device=x.device)
             gv, gj, ga = torch.autograd.grad([-losses.mean()], [v, j, fp], allow_unused=True)
@@ -391,7 +411,8 @@ class EgoHMR(nn.Module):
 
     @torch.no_grad()
     def eval_coll(self, output):
-        """EgoHMR.eval_coll (egohmr.py:487-514): fraction of scene points the collision model marks as inside."""
+        """EgoHMR.eval_coll (egohmr.py:487-514): fraction of scene points the collision model marks as inside.
+        `query_batched(points[B,N,3], mask[B,N], SMPLOutput) -> occupancy[B,N]` is used when the model offers it."""
         if self.collision_model is None:
             raise RuntimeError("eval_coll needs a collision model with COAP's query() (pass collision_model=...)")
         p = output["pred_smpl_params"]
@@ -399,14 +420,20 @@ class EgoHMR(nn.Module):
         R = torch.cat([p["global_orient"].reshape(B, 1, 3, 3), p["body_pose"].reshape(B, 23, 3, 3)], dim=1).float().contiguous()
         verts, joints = self.engine.smpl_forward(R, p["betas"].float().contiguous())
         aa = self.engine.rotmat_to_angle_axis(R.reshape(-1, 3, 3)).reshape(B, -1)
-        idx = self._cond["img_of_body"].tolist() if self._cond is not None and len(self._cond["img_of_body"]) == B else list(range(B))
+        idx, idx32 = self._body_image_index(B)
+        mask, count = self._crop_scene(verts, idx32)
+        n_pts = self.scene_pcd_verts.shape[1]
+        cm = self.collision_model
+        if hasattr(cm, "query_batched"):
+            occ = cm.query_batched(self.scene_pcd_verts[idx], mask, smpl_mod.SMPLOutput(vertices=verts, joints=joints, full_pose=aa))
+            return (((occ > 0.5) & mask).sum(dim=1) / n_pts).tolist()
+        counts, idx_l = count.tolist(), idx.tolist()
         ratios = []
         for i in range(B):
-            pts, inds = self._crop_scene(verts[[i]], idx[i])
-            if inds.any():
+            if counts[i]:
                 so = smpl_mod.SMPLOutput(vertices=verts[[i]].clone(), joints=joints[[i]].clone(), full_pose=aa[[i]].clone())
-                occ = self.collision_model.query(pts[inds].unsqueeze(0), so)
-                ratios.append(((occ > 0.5).sum() / self.scene_pcd_verts.shape[1]).item())
+                occ = cm.query(self.scene_pcd_verts[idx_l[i]][mask[i]].unsqueeze(0), so)
+                ratios.append(((occ > 0.5).sum() / n_pts).item())
             else:
                 ratios.append(0.0)
         return ratios

@@ -77,3 +77,19 @@ class SyntheticCollision:
 
     def query(self, points, smpl_output):
         return self._occ(points, smpl_output)
+
+
+class BatchedSyntheticCollision(SyntheticCollision):
+    """The same penalty behind the batched interface `EgoHMR.guide_coll` / `eval_coll` prefer when a collision model
+    offers it: every body in one call, the per-body crop given as a mask instead of a compacted point list."""
+
+    def collision_loss_batched(self, points, mask, smpl_output):
+        m = mask.to(points.dtype)
+        n = m.sum(dim=1)
+        occ = self._occ(points, smpl_output)                                           # [B,N]
+        reg = 1e-2 * (smpl_output.full_pose.reshape(points.shape[0], -1) ** 2).mean(dim=1)
+        loss = (occ * m).sum(dim=1) / n.clamp_min(1) + reg
+        return torch.where(n > 0, loss, torch.zeros_like(loss))
+
+    def query_batched(self, points, mask, smpl_output):
+        return self._occ(points, smpl_output)

@@ -163,6 +163,14 @@ int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts
  * tensor: in [n][h][w][c] -> out [n][(h+1)/2][(w+1)/2][c]; c % 4 == 0, 16-byte aligned pointers. */
 int ehb_maxpool3x3s2_nhwc(ehb_ctx* ctx, const float* in, int n, int h, int w, int c, float* out, void* stream);
 
+/* The scene crop of guide_coll / eval_coll (egohmr.py:550-554, 504-508) for every body in one launch: body b's
+ * axis-aligned bounding box over verts [n_bodies][n_verts][3], then mask[b][i] = 1 iff point i of cloud
+ * img_of_body[b] (device int32 [n_bodies], NULL = identity) lies inside it (inclusive on both sides, like the
+ * reference's >= / <=).  scene [n_clouds][n_pts][3]; mask uint8 [n_bodies][n_pts]; count int32 [n_bodies] = points
+ * kept (the reference's `inds.any()` / `inds.sum()`); bbox float [n_bodies][6] = min xyz, max xyz, or NULL. */
+int ehb_scene_crop(ehb_ctx* ctx, const float* verts, int n_bodies, int n_verts, const float* scene, int n_pts,
+                   const int32_t* img_of_body, uint8_t* mask, int32_t* count, float* bbox, void* stream);
+
 /* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
  * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);

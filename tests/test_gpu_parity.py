@@ -438,6 +438,47 @@ def test_guide_coll_gradient_vs_reference_golden(small, golden_dir):
     assert np.allclose(ratios, g["coll_ratio"], atol=1.1 / 1024)   # a count of scene points out of 1024
 
 
+def test_scene_crop_matches_reference_expression(full):
+    """ehb_scene_crop (one launch for all bodies) equals the reference's per-body expression (egohmr.py:550-554):
+    inds = (pts >= verts.min(1)).all(-1) & (pts <= verts.max(1)).all(-1) — bit for bit, including empty crops,
+    ragged point counts and bodies sharing one cloud."""
+    eng = full[0].engine
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for (B, V, n_img, N) in [(7, 6890, 3, 1024), (2, 33, 2, 5), (5, 100, 1, 20000)]:
+        verts = torch.randn(B, V, 3, device="cuda", generator=g) * 0.4
+        verts[0] += 100.0                                    # body 0 far away from its cloud: empty crop
+        scene = torch.randn(n_img, N, 3, device="cuda", generator=g)
+        iob = (torch.arange(B, device="cuda") % n_img).to(torch.int32)
+        mask, count = eng.scene_crop(verts.contiguous(), scene.contiguous(), iob)
+        for b in range(B):
+            pts = scene[[int(iob[b])]]
+            ref = (pts >= verts[[b]].min(1).values.reshape(1, 3)).all(-1) & (pts <= verts[[b]].max(1).values.reshape(1, 3)).all(-1)
+            assert torch.equal(mask[b], ref[0]) and int(count[b]) == int(ref.sum())
+        assert int(count[0]) == 0
+
+
+def test_batched_collision_interface_equals_per_body_calls(golden_dir):
+    """A collision model offering collision_loss_batched / query_batched gives the same guidance
+    gradient and collision ratios as COAP's one-body-per-call interface, and both match the reference golden."""
+    from egohmr_b200.testing import BatchedSyntheticCollision, build_model
+    model, *_ = build_model(256, 2, T=50, respacing="", collision=True)
+    g = np.load(os.path.join(golden_dir, "guide_grad_f64.npz"))
+    batch = _tb(synth.make_batch(0, 3))
+    batch["x_t"] = torch.from_numpy(g["x_t"]).cuda()
+    cond = model.prepare(batch, 1)
+    t = torch.full((3,), 8, device="cuda", dtype=torch.long)
+    o = {"pred_smpl_params": {"betas": cond["betas_img"]}}
+    per_body = model.guide_coll(batch, o, t, compute_grad="x_t")
+    model.collision_model = BatchedSyntheticCollision()
+    batched = model.guide_coll(batch, o, t, compute_grad="x_t")
+    scale = np.abs(g["grad"]).max()
+    assert (per_body - batched).abs().max().item() < 1e-6 * scale + 1e-9
+    assert np.abs(batched.cpu().numpy() - g["grad"]).max() < 5e-8 + 2e-5 * scale
+    out = model(batch, t)
+    assert np.allclose(model.eval_coll(out), g["coll_ratio"], atol=1.1 / 1024)
+    model.engine.close()
+
+
 def test_smpl_backward_matches_autograd_oracle(full):
     """dL/dx from arbitrary upstream gradients on vertices, joints and axis-angle pose vs torch-CPU float64 autograd over
     the oracle's restatement (all three gradient paths, 11 bodies, ragged vs every tile size)."""

@@ -1,0 +1,90 @@
+"""Times the BASELINE.json configurations other than the bench headline (cfg 2) on one GPU, one JSON line each:
+  dropin   cfg 2 through the reference driver's own loop: num_samples sequential val_losses calls (test_egohmr.py:251-255)
+  guided   cfg 3: DDPM-100 + collision-guided gradient, 32 images x 10 samples (per-body and batched collision interface)
+  ddpm1000 cfg 5's per-GPU share: DDPM-1000, 64 images x 10 samples (512 x 10 over 8 GPUs)
+  strong   cfg 4's per-GPU share: DDIM-5, 32 images x 10 samples (256 x 10 over 8 GPUs), graph replay
+Usage: python tools/time_configs.py [dropin guided ddpm1000 strong]"""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from egohmr_b200 import synth  # noqa: E402
+from egohmr_b200.diffusion.model_util import create_gaussian_diffusion  # noqa: E402
+from egohmr_b200.testing import BatchedSyntheticCollision, SyntheticCollision, build_model, torch_batch  # noqa: E402
+
+which = sys.argv[1:] or ["dropin", "guided", "ddpm1000", "strong"]
+dev = "cuda:0"
+model, diffusion, sd, smpl_model, mean, std = build_model(1024, 4, T=50, respacing="ddim5")
+mk = lambda T, r: create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=r,
+                                            body_rep_mean=torch.from_numpy(mean).to(dev), body_rep_std=torch.from_numpy(std).to(dev))
+
+
+def timed(fn, reps, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) / reps * 1e3
+
+
+def emit(name, bodies, ms, wall, **kw):
+    print(json.dumps({"config": name, "bodies": bodies, "ms_per_pass": ms, "wall_ms_per_pass": wall,
+                      "bodies_per_s": bodies / (ms * 1e-3), **kw}), flush=True)
+
+
+if "dropin" in which:
+    batch = torch_batch(synth.make_batch(100, 64), dev)
+
+    def run():
+        model._cond_key = None
+        for _ in range(10):
+            diffusion.val_losses(model=model, batch=batch, shape=[64, 144], progress=False, clip_denoised=False,
+                                 cur_epoch=0, timestep_respacing="ddim5", compute_loss=False)
+    ms, wall = timed(run, 5)
+    emit("cfg2 drop-in loop: 10 sequential val_losses calls of 64 bodies (test_egohmr.py:251-255), DDIM-5", 640, ms, wall)
+
+if "guided" in which:
+    d100 = mk(100, "")
+    batch = torch_batch(synth.make_batch(101, 32), dev)
+    for label, cm in (("per-body collision_loss calls (COAP's interface)", SyntheticCollision()),
+                      ("collision_loss_batched (one call per guided step)", BatchedSyntheticCollision())):
+        model.collision_model = cm
+
+        def run():
+            model._cond_key = None
+            d100.sample_many(model, batch, 10, "", cond_fn_with_grad=True, cond_grad_weight=2.0)
+        ms, wall = timed(run, 2)
+        emit("cfg3 DDPM-100 + collision guidance (t <= 10), 32 images x 10 samples", 320, ms, wall, collision=label)
+
+if "ddpm1000" in which:
+    d1000 = mk(1000, "")
+    batch = torch_batch(synth.make_batch(102, 64), dev)
+
+    def run():
+        model._cond_key = None
+        d1000.sample_many(model, batch, 10, "")
+    ms, wall = timed(run, 1)
+    emit("cfg5 per-GPU share: DDPM-1000, 64 images x 10 samples (eager loop)", 640, ms, wall)
+
+if "strong" in which:
+    batch = torch_batch(synth.make_batch(103, 32), dev)
+    sampler = diffusion.capture_sample_many(model, batch, 10, "ddim5")
+    ms, wall = timed(lambda: sampler(batch), 20, warm=3)
+    emit("cfg4 per-GPU share: DDIM-5, 32 images x 10 samples, CUDA-graph replay", 320, ms, wall)
+
+    def run():
+        model._cond_key = None
+        diffusion.sample_many(model, batch, 10, "ddim5")
+    ms, wall = timed(run, 20, warm=3)
+    emit("cfg4 per-GPU share: DDIM-5, 32 images x 10 samples, eager launches", 320, ms, wall)
