@@ -1005,6 +1005,17 @@ int ehb_scene_crop(ehb_ctx* ctx, const float* verts, int n_bodies, int n_verts, 
   return 0;
 }
 
+int ehb_procrustes_align(ehb_ctx* ctx, const float* s1, const float* s2, const float* mask, int n_problems, int n_points,
+                         float* s1_hat, float* err, void* stream_) {
+  if (!ctx || !s1 || !s2) return fail("ehb_procrustes_align: null argument");
+  if (!s1_hat && !err) return fail("ehb_procrustes_align: at least one of s1_hat / err must be given");
+  if (n_problems < 0 || n_points <= 0) return fail("ehb_procrustes_align: bad sizes");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_procrustes(s1, s2, mask, n_problems, n_points, s1_hat, err, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += n_problems > 0;
+  return 0;
+}
+
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream_) {
   if (!ctx || !R || !aa) return fail("ehb_rotmat_to_angle_axis: null argument");
   if (n < 0) return fail("ehb_rotmat_to_angle_axis: negative n");

@@ -180,6 +180,11 @@ cudaError_t launch_scene_crop(const float* verts, int n_bodies, int V, const flo
                               const int32_t* img_of_body, uint8_t* mask, int32_t* count, float* bbox,
                               cudaStream_t stream);
 
+// ---- evaluation metrics (metrics.cu): batched Procrustes alignment (utils/pose_utils.py:11-105).  S1, S2 [P][N][3];
+// mask [P][N][3] or null (the *_with_vis_mask variant); S1_hat [P][N][3] and err [P][N] = |S1_hat - S2| may be null.
+cudaError_t launch_procrustes(const float* S1, const float* S2, const float* mask, int n_problems, int n_pts,
+                              float* S1_hat, float* err, cudaStream_t stream);
+
 // ---- guidance backward (smpl_bwd.cu)
 cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, cudaStream_t stream);
 // dL/dx [B][144] from dL/dverts [B][V][3], dL/djoints [B][24+E][3], dL/dfull_pose_aa [B][24][3] (each may be null).

@@ -1,0 +1,202 @@
+// Evaluation-side kernels: batched Procrustes alignment for PA-MPJPE.
+//
+// Reference: utils/pose_utils.py:11-73 compute_similarity_transform(_batch) (and :75-105 with a visibility mask) — a
+// Python loop over samples calling numpy's SVD, fed by `.cpu().numpy()` copies (test_egohmr.py:420-433).  After the
+// sampler got fast that loop dominates an evaluation run; here block = one (S1, S2) problem, the 3 x 3 algebra in
+// double precision on one thread (Jacobi eigen-decomposition of K^T K), everything else block-parallel.
+#include "kernels.cuh"
+
+namespace ehb {
+namespace {
+
+struct Mat3 {
+  double m[3][3];
+};
+
+__device__ inline void jacobi_eigen_sym3(double A[3][3], double V[3][3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (fabs(A[p][q]) < 1e-300) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) {   // A <- A J
+          const double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq;
+          A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; ++k) {   // A <- J^T A
+          const double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk;
+          A[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; ++k) {   // V <- V J
+          const double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq;
+          V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+__device__ inline double det3(const double M[3][3]) {
+  return M[0][0] * (M[1][1] * M[2][2] - M[1][2] * M[2][1]) - M[0][1] * (M[1][0] * M[2][2] - M[1][2] * M[2][0]) +
+         M[0][2] * (M[1][0] * M[2][1] - M[1][1] * M[2][0]);
+}
+
+// scale * R and t of the similarity transform that maps S1 onto S2 (pose_utils.py:25-52), from the centred moments:
+// K = X1 X2^T (3x3), var1 = sum |X1|^2, mu1, mu2.
+__device__ void solve_similarity(const double K[3][3], double var1, const double mu1[3], const double mu2[3],
+                                 double sR[3][3], double t[3]) {
+  // K = U S V^T  =>  K^T K = V S^2 V^T
+  double A[3][3], V[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double a = 0;
+      for (int k = 0; k < 3; ++k) a += K[k][i] * K[k][j];
+      A[i][j] = a;
+    }
+  jacobi_eigen_sym3(A, V);
+  int ord[3] = {0, 1, 2};   // descending eigenvalues (numpy orders singular values that way; Z acts on the smallest)
+  for (int i = 0; i < 2; ++i)
+    for (int j = i + 1; j < 3; ++j)
+      if (A[ord[j]][ord[j]] > A[ord[i]][ord[i]]) {
+        const int tmp = ord[i];
+        ord[i] = ord[j];
+        ord[j] = tmp;
+      }
+  double Vs[3][3], U[3][3], sv[3];
+  for (int c = 0; c < 3; ++c) {
+    sv[c] = sqrt(fmax(A[ord[c]][ord[c]], 0.0));
+    for (int r = 0; r < 3; ++r) Vs[r][c] = V[r][ord[c]];
+  }
+  const double tol = 1e-12 * fmax(sv[0], 1e-300);
+  for (int c = 0; c < 3; ++c) {
+    double u[3];
+    if (sv[c] > tol) {
+      for (int r = 0; r < 3; ++r) u[r] = (K[r][0] * Vs[0][c] + K[r][1] * Vs[1][c] + K[r][2] * Vs[2][c]) / sv[c];
+    } else if (c == 2) {   // rank-2 K: complete the basis (its sign is irrelevant, Z fixes det(R) = +1)
+      u[0] = U[1][0] * U[2][1] - U[2][0] * U[1][1];
+      u[1] = U[2][0] * U[0][1] - U[0][0] * U[2][1];
+      u[2] = U[0][0] * U[1][1] - U[1][0] * U[0][1];
+    } else {               // rank <= 1: any unit vector orthogonal to the previous columns
+      const double a0 = c == 0 ? 1.0 : -U[1][0], a1 = c == 0 ? 0.0 : U[0][0];
+      const double nrm = sqrt(a0 * a0 + a1 * a1);
+      u[0] = nrm > 1e-12 ? a0 / nrm : 0.0;
+      u[1] = nrm > 1e-12 ? a1 / nrm : 0.0;
+      u[2] = nrm > 1e-12 ? 0.0 : 1.0;
+    }
+    for (int r = 0; r < 3; ++r) U[r][c] = u[r];
+  }
+  double UVt[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) UVt[i][j] = U[i][0] * Vs[j][0] + U[i][1] * Vs[j][1] + U[i][2] * Vs[j][2];
+  const double d = det3(UVt);
+  const double z = d > 0 ? 1.0 : (d < 0 ? -1.0 : 0.0);   // np.sign
+  double R[3][3];                                          // R = V Z U^T
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) R[i][j] = Vs[i][0] * U[j][0] + Vs[i][1] * U[j][1] + z * Vs[i][2] * U[j][2];
+  double tr = 0;                                           // trace(R K)
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k) tr += R[i][k] * K[k][i];
+  const double scale = tr / var1;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) sR[i][j] = scale * R[i][j];
+    t[i] = mu2[i] - (sR[i][0] * mu1[0] + sR[i][1] * mu1[1] + sR[i][2] * mu1[2]);
+  }
+}
+
+constexpr int PT = 128;
+
+__device__ inline double block_sum(double v, double* red) {
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0;
+  for (int w = 0; w < PT / 32; ++w) r += red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(PT) procrustes_kernel(const float* __restrict__ S1, const float* __restrict__ S2,
+                                                        const float* __restrict__ mask, int n_pts,
+                                                        float* __restrict__ S1_hat, float* __restrict__ err) {
+  __shared__ double red[PT / 32];
+  __shared__ double sRt[12];
+  const size_t base = static_cast<size_t>(blockIdx.x) * n_pts;
+  const float* a = S1 + base * 3;
+  const float* b = S2 + base * 3;
+  const float* m = mask ? mask + base * 3 : nullptr;
+  // masked copies exactly as pose_utils.py:78-79 (S*vis_mask, the mean still divides by N)
+  double s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < n_pts; i += PT)
+    for (int k = 0; k < 3; ++k) {
+      const double w = m ? m[i * 3 + k] : 1.0;
+      s1[k] += w * a[i * 3 + k];
+      s2[k] += w * b[i * 3 + k];
+    }
+  double mu1[3], mu2[3];
+  for (int k = 0; k < 3; ++k) {
+    mu1[k] = block_sum(s1[k], red) / n_pts;
+    mu2[k] = block_sum(s2[k], red) / n_pts;
+  }
+  double Kp[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, vp = 0;
+  for (int i = threadIdx.x; i < n_pts; i += PT) {
+    double x1[3], x2[3];
+    for (int k = 0; k < 3; ++k) {
+      const double w = m ? m[i * 3 + k] : 1.0;
+      x1[k] = w * a[i * 3 + k] - mu1[k];
+      x2[k] = w * b[i * 3 + k] - mu2[k];
+      vp += x1[k] * x1[k];
+    }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) Kp[r * 3 + c] += x1[r] * x2[c];
+  }
+  double K[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) K[r][c] = block_sum(Kp[r * 3 + c], red);
+  const double var1 = block_sum(vp, red);
+  if (threadIdx.x == 0) {
+    double sR[3][3], t[3];
+    solve_similarity(K, var1, mu1, mu2, sR, t);
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) sRt[r * 3 + c] = sR[r][c];
+      sRt[9 + r] = t[r];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_pts; i += PT) {   // S1_hat = scale R S1 + t on the UNMASKED points (:100)
+    const double x = a[i * 3], y = a[i * 3 + 1], z = a[i * 3 + 2];
+    float h[3];
+    double e2 = 0;
+    for (int r = 0; r < 3; ++r) {
+      const double v = sRt[r * 3] * x + sRt[r * 3 + 1] * y + sRt[r * 3 + 2] * z + sRt[9 + r];
+      h[r] = static_cast<float>(v);
+      const double d = static_cast<double>(h[r]) - b[i * 3 + r];
+      e2 += d * d;
+    }
+    if (S1_hat) {
+      S1_hat[(base + i) * 3] = h[0];
+      S1_hat[(base + i) * 3 + 1] = h[1];
+      S1_hat[(base + i) * 3 + 2] = h[2];
+    }
+    if (err) err[base + i] = static_cast<float>(sqrt(e2));
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_procrustes(const float* S1, const float* S2, const float* mask, int n_problems, int n_pts,
+                              float* S1_hat, float* err, cudaStream_t stream) {
+  if (n_problems <= 0 || n_pts <= 0) return cudaSuccess;
+  procrustes_kernel<<<n_problems, PT, 0, stream>>>(S1, S2, mask, n_pts, S1_hat, err);
+  return cudaGetLastError();
+}
+
+}  // namespace ehb

@@ -243,6 +243,17 @@ class Engine:
                                       _dev_ptr(count, torch.int32), None, _stream()))
         return mask.bool(), count
 
+    def procrustes(self, S1, S2, mask=None):
+        """Batched similarity-transform alignment (utils/pose_utils.py:11-105): S1, S2 [P,N,3] (mask [P,N,3] optional)
+        -> (S1_hat [P,N,3], err [P,N])."""
+        P, N = S1.shape[0], S1.shape[1]
+        hat = torch.empty(P, N, 3, device=S1.device, dtype=torch.float32)
+        err = torch.empty(P, N, device=S1.device, dtype=torch.float32)
+        if P:
+            check(self.lib.ehb_procrustes_align(self._h, _dev_ptr(S1), _dev_ptr(S2), _dev_ptr(mask, allow_none=True), P, N,
+                                                _dev_ptr(hat), _dev_ptr(err), _stream()))
+        return hat, err
+
     def smpl_backward(self, x_t, betas, g_verts=None, g_joints=None, g_aa=None):
         """dL/dx_t [B,144] for the bodies of set_bodies (guide_coll's autograd.grad, egohmr.py:562)."""
         grad = torch.empty_like(x_t)

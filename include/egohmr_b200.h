@@ -171,6 +171,14 @@ int ehb_maxpool3x3s2_nhwc(ehb_ctx* ctx, const float* in, int n, int h, int w, in
 int ehb_scene_crop(ehb_ctx* ctx, const float* verts, int n_bodies, int n_verts, const float* scene, int n_pts,
                    const int32_t* img_of_body, uint8_t* mask, int32_t* count, float* bbox, void* stream);
 
+/* utils/pose_utils.py:11-73 compute_similarity_transform_batch (mask == NULL) and :62-105 the *_with_vis_mask variant
+ * (mask [n_problems][n_points][3], multiplied into both point sets before the fit, as the reference does): the
+ * similarity transform (scale, R, t) taking s1 onto s2 by orthogonal Procrustes, one problem per (sample, body).
+ * s1, s2 [n_problems][n_points][3]; s1_hat [n_problems][n_points][3] = scale R s1 + t; err [n_problems][n_points] =
+ * |s1_hat - s2| (the per-joint PA-MPJPE of reconstruction_error, :108-115).  Either output may be NULL. */
+int ehb_procrustes_align(ehb_ctx* ctx, const float* s1, const float* s2, const float* mask, int n_problems, int n_points,
+                         float* s1_hat, float* err, void* stream);
+
 /* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
  * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);

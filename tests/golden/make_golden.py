@@ -186,6 +186,27 @@ def loss_case(name, dtype, n_img=3, seed=0):
     print("wrote", name, {k: float(v) for k, v in rec.items() if v.ndim == 0})
 
 
+def procrustes_case():
+    """utils/pose_utils.py reconstruction_error / reconstruction_error_with_vis_mask straight from the reference, on
+    PA-MPJPE-shaped inputs (24 joints) including a mirrored target (det < 0 branch) and a planar point set."""
+    from utils.pose_utils import (compute_similarity_transform_batch, reconstruction_error,
+                                  reconstruction_error_with_vis_mask)
+    rng = np.random.default_rng(123)
+    P, N = 12, 24
+    S1 = rng.normal(0, 0.3, (P, N, 3)).astype(np.float32)
+    Rm = np.linalg.qr(rng.normal(0, 1, (P, 3, 3)))[0]
+    S2 = (1.7 * np.einsum("pij,pnj->pni", Rm, S1) + rng.normal(0, 1, (P, 1, 3)) + rng.normal(0, 0.02, (P, N, 3))).astype(np.float32)
+    S2[3] = S2[3] * np.array([1, 1, -1], np.float32)          # mirrored: forces the det(U V^T) < 0 correction
+    S1[5, :, 2] = 0                                           # planar source (rank-2 K)
+    S2[6] = rng.normal(0, 0.3, (N, 3)).astype(np.float32)     # unrelated target
+    vis = (rng.uniform(0, 1, (P, N, 1)) < 0.7).astype(np.float32).repeat(3, axis=2)
+    rec = {"S1": S1, "S2": S2, "vis": vis, "hat": compute_similarity_transform_batch(S1, S2),
+           "re": reconstruction_error(S1, S2, avg_joint=False), "re_avg": reconstruction_error(S1, S2),
+           "re_vis": reconstruction_error_with_vis_mask(vis, S1, S2, avg_joint=False)}
+    np.savez_compressed(os.path.join(HERE, "procrustes.npz"), **rec)
+    print("wrote procrustes", rec["re_avg"])
+
+
 def schedule_tables():
     from diffusion.model_util import create_gaussian_diffusion
     rec = {}
@@ -236,6 +257,9 @@ if __name__ == "__main__":
         run_case("ddim5_T50_hid256_maskall_f64", 50, "ddim5", 256, 2, 3, torch.float64, only_mask_img_cond=False)
         run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "procrustes":
+        procrustes_case()
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "loss":
         loss_case("val_losses_compute_loss_f32", torch.float32)
         raise SystemExit(0)
@@ -252,3 +276,4 @@ if __name__ == "__main__":
     run_case("ddim5_T50_hid256_maskall_f64", 50, "ddim5", 256, 2, 3, torch.float64, only_mask_img_cond=False)
     run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)
     loss_case("val_losses_compute_loss_f32", torch.float32)
+    procrustes_case()

@@ -479,6 +479,61 @@ def test_batched_collision_interface_equals_per_body_calls(golden_dir):
     model.engine.close()
 
 
+def test_procrustes_kernel_vs_reference_golden(full, golden_dir):
+    """ehb_procrustes_align behind the reference's utils/pose_utils.py names: golden from the reference (mirrored target,
+    planar source, unrelated target, visibility mask), the float64 oracle at the driver's shape (640 x 24 joints) and at
+    vertex scale (6890 points), numpy-in/numpy-out like the reference's call sites (test_egohmr.py:420-433)."""
+    from egohmr_b200.utils import pose_utils as pu
+    from oracle import pose_utils as o_pu
+    g = np.load(os.path.join(golden_dir, "procrustes.npz"))
+    re = pu.reconstruction_error(g["S1"], g["S2"], avg_joint=False)
+    assert isinstance(re, np.ndarray) and np.abs(re - g["re"]).max() < 2e-5
+    assert np.abs(pu.compute_similarity_transform_batch(g["S1"], g["S2"]) - g["hat"]).max() < 2e-5
+    assert np.abs(pu.reconstruction_error(g["S1"], g["S2"]) - g["re_avg"]).max() < 2e-5
+    assert np.abs(pu.reconstruction_error_with_vis_mask(g["vis"], g["S1"], g["S2"], avg_joint=False) - g["re_vis"]).max() < 2e-5
+    rng = np.random.default_rng(5)
+    for (P, N) in [(640, 24), (3, 6890), (1, 3)]:
+        S1 = rng.normal(0, 0.4, (P, N, 3)).astype(np.float32)
+        S2 = (S1[:, ::-1] * 0.8 + rng.normal(0, 0.05, (P, N, 3)) + 2.0).astype(np.float32)
+        ref, hat = o_pu.reconstruction_error(S1, S2, avg_joint=False)
+        got = pu.reconstruction_error(torch.from_numpy(S1).cuda(), torch.from_numpy(S2).cuda(), avg_joint=False)
+        assert got.is_cuda and np.abs(got.cpu().numpy() - ref).max() < 1e-5
+    assert pu.reconstruction_error(np.zeros((0, 24, 3), np.float32), np.zeros((0, 24, 3), np.float32)).shape == (0,)
+
+
+def test_reference_checkpoint_ingestion(tmp_path, small):
+    """test_egohmr.py:107-126: preprocess_stats.npz + torch.load(ckpt)['state_dict'] with the reference's key names,
+    plus the smpl.* / coap buffers its modules save, into a fresh model -> identical samples."""
+    from egohmr_b200 import EgoHMR, checkpoint
+    from egohmr_b200.testing import make_cfg
+    model, diffusion, sd, smpl_model, mean, std = small
+    run = tmp_path / "run"
+    (run / "preprocess_stats").mkdir(parents=True)
+    np.savez(run / "preprocess_stats" / "preprocess_stats.npz", Xmean=mean, Xstd=std)
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    state["smpl.v_template"] = torch.zeros(6890, 3)                        # saved by the reference's module, not ours
+    state["smpl.coap.partitioner.weight"] = torch.zeros(4)
+    torch.save({"state_dict": state, "epoch": 3}, run / "best_model_mpjpe_vis.pt")
+    m, s = checkpoint.load_preprocess_stats(str(run / "best_model_mpjpe_vis.pt"), device="cuda:0")
+    fresh = EgoHMR(cfg=make_cfg(), device="cuda:0", body_rep_mean=m, body_rep_std=s, with_focal_length=True,
+                   with_bbox_info=True, with_cam_center=True, scene_feat_dim=512, scene_type="cube", scene_cano=True,
+                   cond_mask_prob=0.0, only_mask_img_cond=True, pelvis_vis_loosen=True, diffuse_fuse=True, diffusion_blk=2,
+                   gcn_hid_dim=256, smpl_model=smpl_model)
+    rep = checkpoint.load_checkpoint(fresh, str(run / "best_model_mpjpe_vis.pt"))
+    assert len(rep["ignored_foreign"]) == 2 and not rep["unexpected"] and not rep["missing"]
+    batch = _tb(synth.make_batch(0, 3))
+    nz = torch.from_numpy(synth.make_noise(0, 1, 3, 50)[0]).cuda()
+    a = diffusion.sample_many(model, batch, 1, "", noise=nz)["pred_vertices"]
+    b = diffusion.sample_many(fresh, batch, 1, "", noise=nz)["pred_vertices"]
+    assert torch.equal(a, b)
+    bad = dict(state)
+    bad.pop("diffusion_model.gconv_output.W")
+    torch.save({"state_dict": bad}, run / "bad.pt")
+    with pytest.raises(RuntimeError):
+        checkpoint.load_checkpoint(fresh, str(run / "bad.pt"))
+    fresh.engine.close()
+
+
 def test_smpl_backward_matches_autograd_oracle(full):
     """dL/dx from arbitrary upstream gradients on vertices, joints and axis-angle pose vs torch-CPU float64 autograd over
     the oracle's restatement (all three gradient paths, 11 bodies, ragged vs every tile size)."""

@@ -75,3 +75,22 @@ def test_no_cpu_fallback_without_gpu():
     from egohmr_b200.engine import Engine
     with pytest.raises(_lib.EhbError):
         Engine(0)
+
+
+def test_preprocess_stats_loader(tmp_path):
+    """test_egohmr.py:108-111: <logdir>/preprocess_stats/preprocess_stats.npz next to the checkpoint."""
+    import numpy as np
+    import pytest
+    from egohmr_b200 import checkpoint
+    d = tmp_path / "run" / "preprocess_stats"
+    d.mkdir(parents=True)
+    mean, std = np.arange(144, dtype=np.float64), np.full(144, 0.5)
+    np.savez(d / "preprocess_stats.npz", Xmean=mean, Xstd=std)
+    m, s = checkpoint.load_preprocess_stats(str(tmp_path / "run" / "best_model_mpjpe_vis.pt"))
+    assert m.dtype.is_floating_point and m.shape == (144,) and float(m[5]) == 5.0 and float(s[0]) == 0.5
+    np.savez(d / "preprocess_stats.npz", Xmean=mean[:10], Xstd=std[:10])
+    with pytest.raises(ValueError):
+        checkpoint.load_preprocess_stats(str(tmp_path / "run" / "x.pt"))
+    np.savez(d / "preprocess_stats.npz", Xmean=mean)
+    with pytest.raises(KeyError):
+        checkpoint.load_preprocess_stats(str(tmp_path / "run" / "x.pt"))

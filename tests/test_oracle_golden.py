@@ -193,3 +193,14 @@ def test_compute_loss_golden(golden_dir):
     assert nvis == int(g["joint_vis_num_batch"]) and float(g["loss"]) == 0.0 and loss == 0.0
     for k, v in ls.items():
         assert abs(float(v) - float(g[k])) <= 2e-5 * max(1.0, abs(float(g[k]))), (k, float(v), float(g[k]))
+
+
+def test_procrustes_golden(golden_dir):
+    """oracle/pose_utils.py against utils/pose_utils.py of the reference (PA-MPJPE alignment)."""
+    from oracle import pose_utils
+    g = np.load(os.path.join(golden_dir, "procrustes.npz"))
+    re, hat = pose_utils.reconstruction_error(g["S1"], g["S2"], avg_joint=False)
+    assert np.abs(hat - g["hat"]).max() < 2e-5 and np.abs(re - g["re"]).max() < 2e-5
+    re_v, _ = pose_utils.reconstruction_error(g["S1"], g["S2"], mask=g["vis"], avg_joint=False)
+    assert np.abs(re_v - g["re_vis"]).max() < 2e-5
+    assert np.abs(pose_utils.reconstruction_error(g["S1"], g["S2"])[0] - g["re_avg"]).max() < 2e-5
