@@ -32,6 +32,12 @@ class GcnWeights(C.Structure):
                 ("mask_all_cond", C.c_int32)]
 
 
+class NonLocalWeights(C.Structure):
+    _fields_ = [("inter", C.c_int32)] + [(n, c_float_p) for n in
+                                         ("theta_w", "theta_b", "phi_w", "phi_b", "g_w", "g_b", "W_w", "W_b", "bn_weight",
+                                          "bn_bias", "bn_mean", "bn_var")] + [("bn_eps", C.c_float)]
+
+
 class PointnetWeights(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("out_dim", C.c_int32), ("fc_pos_w", c_float_p), ("fc_pos_b", c_float_p),
                 ("fc0_w", c_float_p * 4), ("fc0_b", c_float_p * 4), ("fc1_w", c_float_p * 4), ("fc1_b", c_float_p * 4),
@@ -53,6 +59,7 @@ SIGNATURES = {
     "ehb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "ehb_ctx_destroy": (None, [_vp]),
     "ehb_gcn_load": (C.c_int, [_vp, C.POINTER(GcnWeights)]),
+    "ehb_gcn_load_nonlocal": (C.c_int, [_vp, C.POINTER(NonLocalWeights)]),
     "ehb_smpl_load": (C.c_int, [_vp, C.POINTER(SmplModel)]),
     "ehb_set_norm": (C.c_int, [_vp, c_float_p, c_float_p]),
     "ehb_set_schedule": (C.c_int, [_vp, C.c_int, C.c_int, c_float_p]),

@@ -160,6 +160,12 @@ struct ehb_ctx {
   DevBuf w_img, w_rest, w_temb, wx01, cx01, mod_in, bn_scale_in, bn_shift_in;
   DevBuf wout, mod_out, bias_out;
 
+  // ---- optional non-local block (gcn_nonlocal_layer=True)
+  bool nl_loaded = false;
+  int nl_inter = 0, nl_tpg_planes = 0, nl_w_planes = 0;
+  float nl_wscale_tpg = 1.f, nl_wscale_w = 1.f;
+  DevBuf nl_wtpg_hl, nl_btpg, nl_ww_hl, nl_scale, nl_shift, nl_tpg, nl_wy, nl_y_hl;
+
   // ---- conditioning
   int n_img = 0, n_steps_cond = 0;
   DevBuf a01, be01, ct01, vis;
@@ -375,6 +381,7 @@ int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w) {
     ctx->adj_out = make_adjmix(w->adj, go.adj2);
   }
   ctx->gcn_loaded = true;
+  ctx->nl_loaded = false;   // the optional non-local block is (re)loaded separately
   ctx->n_bodies = 0;
   return 0;
 }
@@ -503,7 +510,7 @@ static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
   const bool second = (l & 1) == 1;  // gconv2 of a _ResGraphConv: residual add, block-boundary output
   p.add_res = second ? 1 : 0;
   p.write_f32 = second ? 1 : 0;
-  p.write_hl = (l != L - 1) ? 1 : 0;
+  p.write_hl = (l != L - 1 || ctx->nl_loaded) ? 1 : 0;   // the non-local block consumes the last layer's operand
   if (ctx->gemm_mode == 0) {
     EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB2, p, ctx->num_sms, 2, stream));
     ctx->launches += 1;
@@ -522,6 +529,8 @@ static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
   }
   return 0;
 }
+
+static int run_nonlocal(ehb_ctx* ctx, cudaStream_t stream);
 
 static int run_input(ehb_ctx* ctx, int step, const float* x_t, cudaStream_t stream) {
   ehb::InputLayerParams p;
@@ -591,6 +600,7 @@ int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float
   if (run_input(ctx, step, x_t, stream)) return 1;
   for (int l = 0; l < static_cast<int>(ctx->hidden.size()); ++l)
     if (run_hidden(ctx, l, stream)) return 1;
+  if (ctx->nl_loaded && run_nonlocal(ctx, stream)) return 1;
   return run_output(ctx, step, x_t, noise, grad, x_prev, x0, out_cond, out_uncond, stream);
 }
 
@@ -802,6 +812,120 @@ static float pow2_scale(float maxabs) {
 __global__ void relu_copy_kernel(const float* in, float* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = fmaxf(in[i], 0.f);
+}
+
+int ehb_gcn_load_nonlocal(ehb_ctx* ctx, const ehb_nonlocal_weights* w) {
+  if (!ctx) return fail("ehb_gcn_load_nonlocal: null ctx");
+  if (!w) {
+    ctx->nl_loaded = false;
+    return 0;
+  }
+  if (!ctx->gcn_loaded) return fail("ehb_gcn_load_nonlocal: call ehb_gcn_load first");
+  const int C = ctx->hid, I = w->inter;
+  if (I <= 0 || I % 64 != 0 || I * 2 != C) return fail("ehb_gcn_load_nonlocal: inter must be hid / 2 and a multiple of 64");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  // theta | phi | g stacked along N and padded to whole 256-column planes; B operand rows = output channels
+  const int n_tpg = 3 * I, tpg_planes = (n_tpg + 255) / 256, w_planes = (C + 255) / 256;
+  std::vector<float> wt(static_cast<size_t>(tpg_planes) * 256 * C, 0.f), bt(static_cast<size_t>(tpg_planes) * 256, 0.f);
+  const float* srcw[3] = {w->theta_w, w->phi_w, w->g_w};
+  const float* srcb[3] = {w->theta_b, w->phi_b, w->g_b};
+  float m0 = 0.f, m1 = 0.f;
+  for (int k = 0; k < 3; ++k)
+    for (int r = 0; r < I; ++r) {
+      for (int c = 0; c < C; ++c) {
+        const float v = srcw[k][static_cast<size_t>(r) * C + c];
+        wt[(static_cast<size_t>(k) * I + r) * C + c] = v;
+        m0 = std::max(m0, std::fabs(v));
+      }
+      bt[k * I + r] = srcb[k][r];
+    }
+  std::vector<float> ww(static_cast<size_t>(w_planes) * 256 * I, 0.f);
+  for (int r = 0; r < C; ++r)
+    for (int c = 0; c < I; ++c) {
+      const float v = w->W_w[static_cast<size_t>(r) * I + c];
+      ww[static_cast<size_t>(r) * I + c] = v;
+      m1 = std::max(m1, std::fabs(v));
+    }
+  if (!std::isfinite(m0) || !std::isfinite(m1)) return fail("ehb_gcn_load_nonlocal: non-finite weight");
+  ctx->nl_wscale_tpg = pow2_scale(m0);
+  ctx->nl_wscale_w = pow2_scale(m1);
+  std::vector<__half> hl;
+  split_hl(wt.data(), tpg_planes * 256, C, C, 0, ctx->nl_wscale_tpg, hl);
+  EHB_CUDA(ctx->nl_wtpg_hl.upload(hl));
+  split_hl(ww.data(), w_planes * 256, I, I, 0, ctx->nl_wscale_w, hl);
+  EHB_CUDA(ctx->nl_ww_hl.upload(hl));
+  EHB_CUDA(ctx->nl_btpg.upload(bt));
+  std::vector<float> sc(C), sh(C);
+  for (int c = 0; c < C; ++c) {
+    const double s = double(w->bn_weight[c]) / std::sqrt(double(w->bn_var[c]) + double(w->bn_eps));
+    sc[c] = float(s);
+    sh[c] = float(double(w->bn_bias[c]) + (double(w->W_b[c]) - double(w->bn_mean[c])) * s);
+  }
+  EHB_CUDA(ctx->nl_scale.upload(sc));
+  EHB_CUDA(ctx->nl_shift.upload(sh));
+  ctx->nl_inter = I;
+  ctx->nl_tpg_planes = tpg_planes;
+  ctx->nl_w_planes = w_planes;
+  ctx->nl_loaded = true;
+  return 0;
+}
+
+static int run_nonlocal(ehb_ctx* ctx, cudaStream_t stream) {
+  const int C = ctx->hid, I = ctx->nl_inter;
+  const size_t rows = static_cast<size_t>(ctx->n_mtiles) * ehb::TILE_ROWS;
+  const size_t plane = rows * 256;
+  EHB_CUDA(ctx->nl_tpg.ensure(static_cast<size_t>(ctx->nl_tpg_planes) * plane * sizeof(float)));
+  EHB_CUDA(ctx->nl_wy.ensure(static_cast<size_t>(ctx->nl_w_planes) * plane * sizeof(float)));
+  EHB_CUDA(ctx->nl_y_hl.ensure(rows * 2 * I * sizeof(__half), true));
+  const int L = static_cast<int>(ctx->hidden.size());
+  const CUtensorMap& tA = ctx->tmA[L & 1];   // the last hidden layer wrote act_hl[L & 1]
+  ehb::LinearParams lp{};
+  lp.overflow_flag = ctx->overflow.as<int>();
+  lp.M = static_cast<long long>(rows);
+  lp.act_scale = ctx->act_scale;
+  lp.n_mtiles = ctx->n_mtiles;
+  lp.pts_per_cloud = static_cast<int>(rows);
+  lp.K2 = 0;
+  // theta | phi | g = x W^T + b
+  for (int pl = 0; pl < ctx->nl_tpg_planes; ++pl) {
+    CUtensorMap tB;
+    if (make_tmap_f16(&tB, ctx->nl_wtpg_hl.as<__half>() + static_cast<size_t>(pl) * 256 * 2 * C, 256, 2 * C, 128)) return 1;
+    ehb::LinearParams q = lp;
+    q.bias = ctx->nl_btpg.as<float>() + pl * 256;
+    q.out_f32 = ctx->nl_tpg.as<float>() + static_cast<size_t>(pl) * plane;
+    q.acc_scale_inv = 1.f / (ctx->act_scale * ctx->nl_wscale_tpg);
+    q.K1 = C;
+    EHB_CUDA(ehb::launch_linear_umma(tA, tB, tA, tB, q, ctx->num_sms, stream));
+  }
+  ehb::NonLocalParams np{};
+  np.tpg = ctx->nl_tpg.as<float>();
+  np.wy = ctx->nl_wy.as<float>();
+  np.plane_stride = plane;
+  np.y_hl = ctx->nl_y_hl.as<__half>();
+  np.res = ctx->res.as<float>();
+  np.bn_scale = ctx->nl_scale.as<float>();
+  np.bn_shift = ctx->nl_shift.as<float>();
+  np.overflow_flag = ctx->overflow.as<int>();
+  np.act_scale = ctx->act_scale;
+  np.C = C;
+  np.inter = I;
+  np.n_slots = ctx->n_slots;
+  EHB_CUDA(ehb::launch_nonlocal_attention(np, stream));
+  // W y (bias and BatchNorm folded into the residual kernel's scale / shift)
+  CUtensorMap tY;
+  if (make_tmap_f16(&tY, ctx->nl_y_hl.p, rows, 2 * I, 128)) return 1;
+  for (int pl = 0; pl < ctx->nl_w_planes; ++pl) {
+    CUtensorMap tB;
+    if (make_tmap_f16(&tB, ctx->nl_ww_hl.as<__half>() + static_cast<size_t>(pl) * 256 * 2 * I, 256, 2 * I, 128)) return 1;
+    ehb::LinearParams q = lp;
+    q.out_f32 = ctx->nl_wy.as<float>() + static_cast<size_t>(pl) * plane;
+    q.acc_scale_inv = 1.f / (ctx->act_scale * ctx->nl_wscale_w);
+    q.K1 = I;
+    EHB_CUDA(ehb::launch_linear_umma(tY, tB, tY, tB, q, ctx->num_sms, stream));
+  }
+  EHB_CUDA(ehb::launch_nonlocal_residual(np, stream));
+  ctx->launches += ctx->nl_tpg_planes + ctx->nl_w_planes + 2;
+  return 0;
 }
 
 int ehb_pointnet_load(ehb_ctx* ctx, const ehb_pointnet_weights* w) {

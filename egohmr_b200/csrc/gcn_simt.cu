@@ -275,6 +275,73 @@ __global__ void __launch_bounds__(256, 2) gcn_output_kernel(const __grid_constan
   p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
 }
 
+// ------------------------------------------------------------------------------------------------ non-local block
+// NONLocalBlock2D(hid, sub_sample=False) between the last residual block and the output layer when
+// ModulatedGCN(nonlocal_layer=True) (modulated_gcn.py:93-109, nets/non_local_embedded_gaussian.py:61-85):
+//   theta, phi, g = 1x1 convs hid -> hid/2;  f = softmax_j(theta_i . phi_j);  y_i = sum_j f_ij g_j;  z = x + BN(W y)
+// The three projections and W run on the tcgen05 linear kernel (linear_umma.cu) as 256-column planes; this kernel is
+// the 24 x 24 attention of one (body, pass) slot in between: it reads the theta|phi|g planes and writes y as the fp16
+// hi/lo A operand of the W projection.
+__global__ void __launch_bounds__(256) nonlocal_attention_kernel(const __grid_constant__ NonLocalParams p) {
+  __shared__ float f[NJ][NJ + 1];
+  const int slot = blockIdx.x;
+  const size_t row0 = slot_row0(slot);
+  const int I = p.inter;
+  auto at = [&](int which, size_t row, int c) -> const float* {   // column n = which*inter + c of the projection output
+    const int n = which * I + c;
+    return p.tpg + static_cast<size_t>(n >> 8) * p.plane_stride + row * 256 + (n & 255);
+  };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pair = warp; pair < NJ * NJ; pair += 8) {
+    const int i = pair / NJ, j = pair % NJ;
+    float acc = 0.f;
+    for (int c = lane; c < I; c += 32) acc = fmaf(*at(0, row0 + i, c), *at(1, row0 + j, c), acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) f[i][j] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < NJ) {   // F.softmax(f, dim=-1)
+    const int i = threadIdx.x;
+    float mx = f[i][0];
+    for (int j = 1; j < NJ; ++j) mx = fmaxf(mx, f[i][j]);
+    float sum = 0.f;
+    for (int j = 0; j < NJ; ++j) {
+      const float e = expf(f[i][j] - mx);
+      f[i][j] = e;
+      sum += e;
+    }
+    for (int j = 0; j < NJ; ++j) f[i][j] = f[i][j] / sum;
+  }
+  __syncthreads();
+  float amax = 0.f;
+  for (int c = threadIdx.x; c < I; c += blockDim.x) {
+    float y[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) y[i] = 0.f;
+    for (int j = 0; j < NJ; ++j) {
+      const float gv = *at(2, row0 + j, c);
+#pragma unroll
+      for (int i = 0; i < NJ; ++i) y[i] = fmaf(f[i][j], gv, y[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) amax = fmaxf(amax, store_hl(p.y_hl, row0 + i, I, c, y[i], p.act_scale));
+  }
+  if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
+}
+
+// z = x + BN(W y + b): res[row][c] += wy[row][c] * scale[c] + shift[c] on the valid slot rows
+__global__ void __launch_bounds__(256) nonlocal_residual_kernel(const __grid_constant__ NonLocalParams p) {
+  const int slot = blockIdx.x;
+  const size_t row0 = slot_row0(slot);
+  for (int e = threadIdx.x; e < NJ * p.C; e += blockDim.x) {
+    const int j = e / p.C, c = e % p.C;
+    const size_t row = row0 + j;
+    const float wy = p.wy[static_cast<size_t>(c >> 8) * p.plane_stride + row * 256 + (c & 255)];
+    p.res[row * p.C + c] += fmaf(wy, p.bn_scale[c], p.bn_shift[c]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ check path
 struct HiddenSimtParams {
   AdjMix adj;
@@ -375,6 +442,18 @@ cudaError_t launch_sgemm_nn_splitk(const float* A, const float* B, float* C, int
 cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream) {
   if (p.n_slots <= 0) return cudaSuccess;
   gcn_input_kernel<<<dim3(p.n_slots, p.C / 128), 128, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nonlocal_attention(const NonLocalParams& p, cudaStream_t stream) {
+  if (p.n_slots <= 0) return cudaSuccess;
+  nonlocal_attention_kernel<<<p.n_slots, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nonlocal_residual(const NonLocalParams& p, cudaStream_t stream) {
+  if (p.n_slots <= 0) return cudaSuccess;
+  nonlocal_residual_kernel<<<p.n_slots, 256, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

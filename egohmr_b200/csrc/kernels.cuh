@@ -86,6 +86,22 @@ struct InputLayerParams {
 };
 cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream);
 
+// Non-local block between the residual blocks and the output layer (ModulatedGCN(nonlocal_layer=True)).
+struct NonLocalParams {
+  const float* tpg;       // theta|phi|g projections as 256-column fp32 planes [n_planes][rows_pad][256]
+  const float* wy;        // W projection planes [C/256 (padded)][rows_pad][256]
+  size_t plane_stride;    // rows_pad * 256
+  __half* y_hl;           // [rows_pad][hi(inter) | lo(inter)]: A operand of the W projection
+  float* res;             // [rows_pad][C] activations, updated in place
+  const float* bn_scale;  // [C]  gamma / sqrt(var + eps)
+  const float* bn_shift;  // [C]  beta + (conv bias - mean) * bn_scale
+  int* overflow_flag;
+  float act_scale;
+  int C, inter, n_slots;
+};
+cudaError_t launch_nonlocal_attention(const NonLocalParams& p, cudaStream_t stream);
+cudaError_t launch_nonlocal_residual(const NonLocalParams& p, cudaStream_t stream);
+
 // Per-step sampler coefficients (host-computed in fp32 exactly as the reference's torch ops would):
 //  DDIM (eta=0):  c[0]=sqrt_recip_alphas_cumprod, c[1]=sqrt_recipm1_alphas_cumprod, c[2]=sqrt(alpha_bar_prev),
 //                 c[3]=sqrt(1-alpha_bar_prev)

@@ -98,6 +98,33 @@ class Engine:
         check(self.lib.ehb_gcn_load(self._h, C.byref(w)))
         self.hid, self.gcn_loaded, self.n_bodies = hid, True, 0
 
+    def load_nonlocal(self, sd, prefix="diffusion_model.non_local", bn_eps=1e-5):
+        """NONLocalBlock2D parameters by their reference names (nets/non_local_embedded_gaussian.py:36-54); `sd=None`
+        switches the block off."""
+        if sd is None:
+            check(self.lib.ehb_gcn_load_nonlocal(self._h, None))
+            return
+        keep = []
+
+        def arr(name):
+            v = sd[f"{prefix}.{name}"]
+            if isinstance(v, torch.Tensor):
+                v = v.detach().cpu().numpy()
+            a = f32(np.asarray(v).reshape(v.shape[0], -1) if np.asarray(v).ndim > 1 else v)
+            keep.append(a)
+            return fptr(a)
+
+        w = _lib.NonLocalWeights()
+        w.inter = int(sd[f"{prefix}.theta.weight"].shape[0])
+        w.theta_w, w.theta_b = arr("theta.weight"), arr("theta.bias")
+        w.phi_w, w.phi_b = arr("phi.weight"), arr("phi.bias")
+        w.g_w, w.g_b = arr("g.weight"), arr("g.bias")
+        w.W_w, w.W_b = arr("W.0.weight"), arr("W.0.bias")
+        w.bn_weight, w.bn_bias = arr("W.1.weight"), arr("W.1.bias")
+        w.bn_mean, w.bn_var = arr("W.1.running_mean"), arr("W.1.running_var")
+        w.bn_eps = bn_eps
+        check(self.lib.ehb_gcn_load_nonlocal(self._h, C.byref(w)))
+
     def load_smpl(self, model):
         a = {k: f32(model[k]) for k in ("v_template", "shapedirs", "posedirs", "J_regressor", "lbs_weights")}
         parents = np.ascontiguousarray(model["parents"], dtype=np.int32)

@@ -55,14 +55,31 @@ class _ResGraphConvParams(nn.Module):
         self.gconv2 = _GraphConvParams(hid, hid)
 
 
-class ModulatedGCNParams(nn.Module):
-    """state_dict-compatible skeleton of ModulatedGCN (modulated_gcn.py:61-94)."""
+class _NonLocalParams(nn.Module):
+    """Parameter container with NONLocalBlock2D's names and shapes (nets/non_local_embedded_gaussian.py:36-54)."""
 
-    def __init__(self, in_dim, hid_dim, out_dim, num_layers):
+    def __init__(self, hid):
+        super().__init__()
+        inter = hid // 2
+        self.g = nn.Conv2d(hid, inter, 1)
+        self.W = nn.Sequential(nn.Conv2d(inter, hid, 1), nn.BatchNorm2d(hid))
+        nn.init.constant_(self.W[1].weight, 0)
+        nn.init.constant_(self.W[1].bias, 0)
+        self.theta = nn.Conv2d(hid, inter, 1)
+        self.phi = nn.Conv2d(hid, inter, 1)
+
+
+class ModulatedGCNParams(nn.Module):
+    """state_dict-compatible skeleton of ModulatedGCN (modulated_gcn.py:61-97)."""
+
+    def __init__(self, in_dim, hid_dim, out_dim, num_layers, nonlocal_layer=False):
         super().__init__()
         self.gconv_input = nn.Sequential(_GraphConvParams(in_dim, hid_dim))
         self.gconv_layers = nn.Sequential(*[_ResGraphConvParams(hid_dim) for _ in range(num_layers)])
         self.gconv_output = _GConvParams(hid_dim, out_dim)
+        self.nonlocal_layer = nonlocal_layer
+        if nonlocal_layer:
+            self.non_local = _NonLocalParams(hid_dim)
 
 
 class PositionalEncoding(nn.Module):
@@ -123,9 +140,8 @@ class EgoHMR(nn.Module):
                  gcn_nonlocal_layer=False, gcn_hid_dim=1024, pelvis_vis_loosen=False, diffuse_fuse=False,
                  smpl_model=None, collision_model=None):
         super().__init__()
-        if gcn_nonlocal_layer:
-            raise NotImplementedError("gcn_nonlocal_layer=True is never enabled by the reference's drivers "
-                                      "(egohmr.py:37, test_egohmr.py:112-118) and is not on the accelerated path")
+        if gcn_nonlocal_layer and gcn_hid_dim % 128 != 0:
+            raise ValueError("gcn_nonlocal_layer needs gcn_hid_dim to be a multiple of 128")
         self.cfg = cfg
         self.device = torch.device(device) if device is not None else torch.device("cuda", 0)
         self.with_focal_length, self.with_bbox_info, self.with_cam_center = with_focal_length, with_bbox_info, with_cam_center
@@ -148,7 +164,7 @@ class EgoHMR(nn.Module):
             (2 if with_cam_center else 0) + scene_feat_dim + 128  # egohmr.py:76-83
         self.cond_dim = ctx_dim
         self.register_buffer("adj", torch.from_numpy(synth.skeleton_adjacency()), persistent=False)  # :86-94
-        self.diffusion_model = ModulatedGCNParams(ctx_dim + 512 + 512, gcn_hid_dim, 6, diffusion_blk)
+        self.diffusion_model = ModulatedGCNParams(ctx_dim + 512 + 512, gcn_hid_dim, 6, diffusion_blk, gcn_nonlocal_layer)
         init_betas = None if smpl_model is None else smpl_model.get("init_betas")
         self.beta_layer = FCHeadBeta(ctx_dim, init_betas)
 
@@ -198,6 +214,8 @@ class EgoHMR(nn.Module):
         bn_eps = self.diffusion_model.gconv_input[0].bn.eps
         self.engine.load_gcn(sd, self.adj, self.hid, self.n_blocks, self.diffuse_fuse, self.img_dim, self.cond_dim,
                              512, 512, bn_eps=bn_eps, mask_all_cond=not self.only_mask_img_cond)
+        if self.diffusion_model.nonlocal_layer:
+            self.engine.load_nonlocal(sd, bn_eps=self.diffusion_model.non_local.W[1].eps)
         if not self.engine.smpl_loaded:
             self.engine.load_smpl(self.smpl.model)
         mean = self.body_rep_mean if self.body_rep_mean is not None else torch.zeros(144)

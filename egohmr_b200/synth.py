@@ -163,6 +163,20 @@ def make_state_dict(seed=0, hid=1024, n_blocks=4, with_encoders=True, n_betas=10
     return sd
 
 
+def add_nonlocal(sd, seed=0, hid=1024):
+    """NONLocalBlock2D parameters (`diffusion_model.non_local.*`, gcn_nonlocal_layer=True) from their own generator, so
+    the rest of `make_state_dict` is unchanged.  The reference initialises W's BatchNorm to zero (an identity block);
+    here it is random so the block does something."""
+    rng = np.random.default_rng(2500 + seed)
+    inter, p = hid // 2, "diffusion_model.non_local"
+    for name, cin, cout in (("g", hid, inter), ("theta", hid, inter), ("phi", hid, inter), ("W.0", inter, hid)):
+        sd[f"{p}.{name}.weight"] = rng.normal(0, np.sqrt(2.0 / cin) * (0.25 if name in ("theta", "phi") else 1.0),
+                                               (cout, cin, 1, 1)).astype(np.float32)
+        sd[f"{p}.{name}.bias"] = rng.normal(0, 0.05, cout).astype(np.float32)
+    _bn(rng, sd, f"{p}.W.1", hid, gamma=(0.2, 0.6))
+    return sd
+
+
 def body_rep_stats(seed=0):
     """preprocess_stats.npz stand-in (test_egohmr.py:109-111): Xmean, Xstd of the 144-d rot6d representation."""
     rng = np.random.default_rng(3000 + seed)

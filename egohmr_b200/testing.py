@@ -22,20 +22,22 @@ def torch_batch(batch_np, device):
 
 
 def build_model(hid=1024, n_blocks=4, T=50, respacing="ddim5", seed=0, device="cuda:0", diffuse_fuse=True,
-                collision=True, only_mask_img_cond=True):
+                collision=True, only_mask_img_cond=True, nonlocal_layer=False):
     """-> (model, diffusion, state_dict(numpy), smpl_model, Xmean, Xstd) with the reference's test-default flags
     (test_egohmr.py:53-78, 112-118)."""
     from .diffusion.model_util import create_gaussian_diffusion
     from .models.egohmr.egohmr import EgoHMR
     smpl_model = synth.make_smpl_model(seed)
     sd = synth.make_state_dict(seed, hid=hid, n_blocks=n_blocks, init_betas=smpl_model["init_betas"])
+    if nonlocal_layer:
+        synth.add_nonlocal(sd, seed, hid)
     mean, std = synth.body_rep_stats(seed)
     dev = torch.device(device)
     model = EgoHMR(cfg=make_cfg(), device=dev, body_rep_mean=torch.from_numpy(mean).to(dev),
                    body_rep_std=torch.from_numpy(std).to(dev), with_focal_length=True, with_bbox_info=True,
                    with_cam_center=True, scene_feat_dim=512, scene_type="cube", scene_cano=True, cond_mask_prob=0.0,
                    only_mask_img_cond=only_mask_img_cond, pelvis_vis_loosen=True, diffuse_fuse=diffuse_fuse, diffusion_blk=n_blocks,
-                   gcn_hid_dim=hid, smpl_model=smpl_model,
+                   gcn_hid_dim=hid, gcn_nonlocal_layer=nonlocal_layer, smpl_model=smpl_model,
                    collision_model=SyntheticCollision() if collision else None)
     model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
     model.eval()

@@ -56,6 +56,25 @@ typedef struct {
                               (mask_cond(force_mask=True), egohmr.py:150-158) instead of the image features only */
 } ehb_gcn_weights;
 
+/* NONLocalBlock2D(in_channels=hid, sub_sample=False) of ModulatedGCN(nonlocal_layer=True) (modulated_gcn.py:93-95,
+ * nets/non_local_embedded_gaussian.py:6-59); 1x1 convolution weights [out][in] (the trailing 1x1 dims dropped).  HOST. */
+typedef struct {
+  int32_t inter;            /* hid / 2 */
+  const float* theta_w;     /* [inter][hid]  "non_local.theta.weight" */
+  const float* theta_b;     /* [inter] */
+  const float* phi_w;       /* [inter][hid] */
+  const float* phi_b;
+  const float* g_w;         /* [inter][hid] */
+  const float* g_b;
+  const float* W_w;         /* [hid][inter]  "non_local.W.0.weight" */
+  const float* W_b;         /* [hid] */
+  const float* bn_weight;   /* [hid]  "non_local.W.1.*" (BatchNorm2d, eval) */
+  const float* bn_bias;
+  const float* bn_mean;
+  const float* bn_var;
+  float bn_eps;
+} ehb_nonlocal_weights;
+
 /* SMPL model tensors as smplx stores them (smplx/body_models.py::SMPL.__init__).  HOST. */
 typedef struct {
   int32_t n_verts;       /* 6890 */
@@ -83,6 +102,9 @@ void ehb_ctx_destroy(ehb_ctx* ctx);
 /* models/egohmr/egohmr.py:95-99 (ModulatedGCN construction) + load_state_dict (test_egohmr.py:125-126):
  * ingest the denoiser weights and repack them into kernel layouts (fp16 hi/lo split, folded BN, folded input layer). */
 int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w);
+/* Optional (gcn_nonlocal_layer=True, egohmr.py:37,99): the non-local block evaluated after the residual blocks
+ * (modulated_gcn.py:103-109).  Call after ehb_gcn_load; w == NULL switches it off again. */
+int ehb_gcn_load_nonlocal(ehb_ctx* ctx, const ehb_nonlocal_weights* w);
 /* smplx.create('data/smpl', model_type='smpl', ...) (egohmr.py:105-107, test_egohmr.py:143-145) */
 int ehb_smpl_load(ehb_ctx* ctx, const ehb_smpl_model* m);
 /* body_rep_mean / body_rep_std (test_egohmr.py:109-111; used at egohmr.py:258,528).  HOST [144] each. */

@@ -34,15 +34,31 @@ def graph_conv(x, sd, name, adj):
     return np.maximum(batchnorm_eval(y, sd, name + ".bn"), 0)
 
 
+def non_local_block(x, sd, name, eps=1e-5):
+    """NONLocalBlock2D(sub_sample=False).forward on [B, 24, C] (nets/non_local_embedded_gaussian.py:61-85; the
+    [B, C, 1, 24] layout of modulated_gcn.py:104-109 only moves axes around)."""
+    dt = x.dtype
+    conv = lambda t, n: np.matmul(t, sd[f"{name}.{n}.weight"].astype(dt).reshape(sd[f"{name}.{n}.weight"].shape[0], -1).T) \
+        + sd[f"{name}.{n}.bias"].astype(dt)
+    g_x, theta, phi = conv(x, "g"), conv(x, "theta"), conv(x, "phi")
+    f = np.matmul(theta, np.swapaxes(phi, 1, 2))                       # [B, 24, 24]
+    f = np.exp(f - f.max(axis=-1, keepdims=True))
+    f = f / f.sum(axis=-1, keepdims=True)                              # F.softmax(f, dim=-1)
+    y = np.matmul(f, g_x)
+    return batchnorm_eval(conv(y, "W.0"), sd, f"{name}.W.1", eps) + x
+
+
 def modulated_gcn(x, sd, adj, n_blocks, prefix="diffusion_model"):
-    """ModulatedGCN.forward (modulated_gcn.py:99-116) with nonlocal_layer=False (the only configuration the
-    reference's drivers use, egohmr.py:37, test_egohmr.py:112-118)."""
+    """ModulatedGCN.forward (modulated_gcn.py:99-116); the non-local block runs iff its parameters are in `sd`
+    (nonlocal_layer=True; the reference's drivers leave it off, egohmr.py:37, test_egohmr.py:112-118)."""
     out = graph_conv(x, sd, f"{prefix}.gconv_input.0", adj)
     for b in range(n_blocks):  # _ResGraphConv.forward (modulated_gcn.py:38-42)
         res = out
         out = graph_conv(out, sd, f"{prefix}.gconv_layers.{b}.gconv1", adj)
         out = graph_conv(out, sd, f"{prefix}.gconv_layers.{b}.gconv2", adj)
         out = res + out
+    if f"{prefix}.non_local.g.weight" in sd:
+        out = non_local_block(out, sd, f"{prefix}.non_local")
     g = f"{prefix}.gconv_output"
     return modulated_graph_conv(out, sd[g + ".W"], sd[g + ".M"], adj, sd[g + ".adj2"], sd[g + ".bias"])
 

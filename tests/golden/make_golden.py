@@ -52,7 +52,7 @@ class NoiseFeed:
         return self._next(x.shape)
 
 
-def build_reference(hid, n_blocks, dtype, seed=0, only_mask_img_cond=True, diffuse_fuse=True):
+def build_reference(hid, n_blocks, dtype, seed=0, only_mask_img_cond=True, diffuse_fuse=True, nonlocal_layer=False):
     smpl_model = synth.make_smpl_model(seed)
     ref_standins.install(smpl_model, smpl_model["init_betas"])
     from models.egohmr.egohmr import EgoHMR
@@ -61,8 +61,11 @@ def build_reference(hid, n_blocks, dtype, seed=0, only_mask_img_cond=True, diffu
                    body_rep_mean=torch.from_numpy(mean).to(dtype), body_rep_std=torch.from_numpy(std).to(dtype),
                    with_focal_length=True, with_bbox_info=True, with_cam_center=True, scene_feat_dim=512,
                    scene_type="cube", scene_cano=True, cond_mask_prob=0.0, only_mask_img_cond=only_mask_img_cond,
-                   pelvis_vis_loosen=True, diffuse_fuse=diffuse_fuse, diffusion_blk=n_blocks, gcn_hid_dim=hid)
+                   pelvis_vis_loosen=True, diffuse_fuse=diffuse_fuse, diffusion_blk=n_blocks, gcn_hid_dim=hid,
+                   gcn_nonlocal_layer=nonlocal_layer)
     sd = synth.make_state_dict(seed, hid=hid, n_blocks=n_blocks, init_betas=smpl_model["init_betas"])
+    if nonlocal_layer:
+        synth.add_nonlocal(sd, seed, hid)
     res = model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
     assert not res.unexpected_keys and all(k.startswith("smpl") for k in res.missing_keys), res
     # randomised adj2 must survive: the reference keeps `adj` as a plain attribute, adj2 as a parameter
@@ -77,10 +80,10 @@ def build_reference(hid, n_blocks, dtype, seed=0, only_mask_img_cond=True, diffu
 
 
 def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0, guided=False, only_mask_img_cond=True,
-             diffuse_fuse=True):
+             diffuse_fuse=True, nonlocal_layer=False):
     from diffusion.model_util import create_gaussian_diffusion
     import diffusion.gaussian_diffusion as gd
-    model, mean, std = build_reference(hid, n_blocks, dtype, seed, only_mask_img_cond, diffuse_fuse)
+    model, mean, std = build_reference(hid, n_blocks, dtype, seed, only_mask_img_cond, diffuse_fuse, nonlocal_layer)
     diffusion = create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=respacing,
                                           body_rep_mean=torch.from_numpy(mean).to(dtype),
                                           body_rep_std=torch.from_numpy(std).to(dtype))
@@ -257,6 +260,9 @@ if __name__ == "__main__":
         run_case("ddim5_T50_hid256_maskall_f64", 50, "ddim5", 256, 2, 3, torch.float64, only_mask_img_cond=False)
         run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)
         raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "nonlocal":
+        run_case("ddim5_T50_hid256_nonlocal_f64", 50, "ddim5", 256, 2, 3, torch.float64, nonlocal_layer=True)
+        raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "procrustes":
         procrustes_case()
         raise SystemExit(0)
@@ -277,3 +283,4 @@ if __name__ == "__main__":
     run_case("ddim5_T50_hid256_nofuse_f64", 50, "ddim5", 256, 2, 3, torch.float64, diffuse_fuse=False)
     loss_case("val_losses_compute_loss_f32", torch.float32)
     procrustes_case()
+    run_case("ddim5_T50_hid256_nonlocal_f64", 50, "ddim5", 256, 2, 3, torch.float64, nonlocal_layer=True)

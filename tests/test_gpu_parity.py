@@ -226,10 +226,12 @@ def test_ddpm50_sampling_vs_reference_golden(small, golden_dir):
 
 
 @pytest.mark.parametrize("case,flags", [("ddim5_T50_hid256_maskall_f64", {"only_mask_img_cond": False}),
-                                        ("ddim5_T50_hid256_nofuse_f64", {"diffuse_fuse": False})])
+                                        ("ddim5_T50_hid256_nofuse_f64", {"diffuse_fuse": False}),
+                                        ("ddim5_T50_hid256_nonlocal_f64", {"nonlocal_layer": True})])
 def test_model_flag_variants_vs_reference_golden(golden_dir, case, flags):
-    """The two non-default denoiser flags of EgoHMR.__init__ (egohmr.py:36-40): the image-masked pass dropping EVERY
-    condition (only_mask_img_cond=False, :157-158) and a single conditioned pass (diffuse_fuse=False, :239)."""
+    """The non-default denoiser flags of EgoHMR.__init__ (egohmr.py:36-40): the image-masked pass dropping EVERY
+    condition (only_mask_img_cond=False, :157-158), a single conditioned pass (diffuse_fuse=False, :239) and the
+    non-local block after the residual blocks (gcn_nonlocal_layer=True, modulated_gcn.py:103-109)."""
     from egohmr_b200.testing import build_model
     model, diffusion, sd, smpl_model, mean, std = build_model(256, 2, T=50, respacing="ddim5", collision=False, **flags)
     g64 = np.load(os.path.join(golden_dir, case + ".npz"))
@@ -240,6 +242,7 @@ def test_model_flag_variants_vs_reference_golden(golden_dir, case, flags):
     d = np.abs(np.stack(x0s) - g64["trace_x0"]).max()
     print(f"{case}: max|x0 - ref_f64| = {d:.3e}")
     assert d < X0_TOL
+    assert not model.engine.check_overflow()
     model.engine.close()
 
 

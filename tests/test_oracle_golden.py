@@ -47,11 +47,13 @@ def test_modulated_graph_conv_golden(golden_dir):
     assert np.abs(y32 - so["gconv_y32"]).max() < 2e-5
 
 
-def _run_case(golden_dir, case, dtype, **flags):
+def _run_case(golden_dir, case, dtype, nonlocal_layer=False, **flags):
     g = np.load(os.path.join(golden_dir, case + ".npz"))
     hid, nb, n_img, T, resp = int(g["hid"]), int(g["n_blocks"]), int(g["n_img"]), int(g["T"]), str(g["respacing"])
     smpl = synth.make_smpl_model(0)
     sd = synth.make_state_dict(0, hid=hid, n_blocks=nb, init_betas=smpl["init_betas"])
+    if nonlocal_layer:
+        synth.add_nonlocal(sd, 0, hid)
     b = synth.make_batch(0, n_img)
     mean, std = synth.body_rep_stats(0)
     sch = schedule.Schedule(T, resp)
@@ -112,6 +114,14 @@ def test_ddim5_no_diffuse_fuse_fp64(golden_dir):
     g, out, x0s, xts = _run_case(golden_dir, "ddim5_T50_hid256_nofuse_f64", np.float64, diffuse_fuse=False)
     assert np.abs(x0s - g["trace_x0"]).max() < 1e-12
     assert np.abs(out["pred_vertices"] - g["pred_vertices"]).max() < 5e-6
+
+
+def test_ddim5_nonlocal_layer_fp64(golden_dir):
+    """gcn_nonlocal_layer=True: NONLocalBlock2D after the residual blocks (modulated_gcn.py:103-109)."""
+    g, out, x0s, xts = _run_case(golden_dir, "ddim5_T50_hid256_nonlocal_f64", np.float64, nonlocal_layer=True)
+    assert np.abs(x0s - g["trace_x0"]).max() < 1e-12
+    _, _, x0_plain, _ = _run_case(golden_dir, "ddim5_T50_hid256_nonlocal_f64", np.float64)
+    assert np.abs(x0_plain - g["trace_x0"]).max() > 1e-3      # the block is not a no-op with these parameters
 
 
 def test_encoders_match_reference_features(golden_dir):
