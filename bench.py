@@ -29,6 +29,25 @@ METRIC = "sampled bodies/sec (batch x num_samples), DDIM-5"
 WORKLOAD = "configs[1]: DDIM-5 (T=50), batch=64 images x num_samples=10 = 640 bodies per step, 224x224 img + 1024 scene pts"
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL's version banner, cuDNN warnings) print to fd 1; the driver wants ONE JSON line there.  Point
+    fd 1 at stderr for the whole run and keep the original for `emit`."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -99,7 +118,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "bodies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def reference_cuda(n_img, n_samples, device, repeats=1):
@@ -136,13 +155,13 @@ def run_reference_cuda(args):
         v, ms = reference_cuda(args.n_img, args.num_samples, "cuda:0")
         vals.append(v)
     value = float(np.median(vals))
-    print(json.dumps({
+    emit({
         "impl": "reference-cuda", "metric": METRIC, "value": value, "unit": "bodies/s", "n_gpus": 1, "steps": len(vals),
         "warmup": 1, "ms_per_step": 1e3 * args.n_img * args.num_samples / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 (torch defaults: TF32 cuDNN convolutions, fp32 matmuls)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "what": "eager-PyTorch restatement of the reference's GPU dataflow "
-                   "(oracle/torch_eager.py, pinned on the reference's goldens); device-resident inputs"}}))
+                   "(oracle/torch_eager.py, pinned on the reference's goldens); device-resident inputs"}})
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -421,13 +440,14 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": v, "unit": "bodies/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{bodies} bodies ({args.cpu_sample_img} images x {args.cpu_sample_samples} samples) of the 64x10 workload in "
                                           f"{dt:.1f} s; oracle port with the reference's dataflow (encoders + SMPL on every step)"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     a = parse()
+    protect_stdout()
     if a.impl == "reference":
         run_reference(a)
     elif a.impl == "reference-cuda":
