@@ -286,6 +286,14 @@ def run_b200(args):
     clk = clocks.stop()
     launches = launches_per_pass * args.steps
     eager_ms = timed_steps(eager_step, args.steps) if sampler is not None else ms
+    # the same pass with cuDNN's TF32 convolutions switched off (strict fp32 ResNet-50), for transparency
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        eager_step(batch_dev)
+        strict_ms = timed_steps(eager_step, max(3, args.steps // 4)) / max(3, args.steps // 4) * args.steps
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32_was
 
     # ---- end-to-end leg: host (pinned) inputs -> public API -> host results, copies inside the timed region
     res_host = {"R": torch.empty(B, 24, 3, 3).pin_memory(), "betas": torch.empty(B, 10).pin_memory(),
@@ -401,9 +409,9 @@ def run_b200(args):
 
     # max over ranks of the device time
     if world > 1:
-        t = torch.tensor([ms, e2e_s, eager_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, eager_ms, strict_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, eager_ms = float(t[0]), float(t[1]), float(t[2])
+        ms, e2e_s, eager_ms, strict_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -421,6 +429,7 @@ def run_b200(args):
                    "execution": ("whole pass replayed as ONE CUDA graph (diffusion/graphed.py)" if sampler is not None
                                  else "eager: every launch issued from Python"),
                    "eager_value": total_bodies / (eager_ms * 1e-3),
+                   "eager_value_strict_fp32_convs": total_bodies / (strict_ms * 1e-3),
                    "encoders": "once per pass: ResPointNet on the tcgen05 linear kernel (fp16x3, fp32-class); ResNet-50 on "
                                "cuDNN in inference form with torch's default conv precision (TF32 allowed, exactly what the "
                                "reference's own CUDA path runs; the -m gpu parity tests switch TF32 off)",

@@ -20,7 +20,8 @@ constexpr int B_BYTES = BN * BK * 2 / 2;        // per CTA of the pair: half of 
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KiB
 constexpr int STAGES = 3;
 constexpr int BAR_BYTES = 256;
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES;
+constexpr int ADDV_BYTES = 2 * 256 * 4;   // per-tile additive row (bias + per-cloud row), double-buffered
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES;
 constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant: warp w and w+4 split the 256 columns
 constexpr int TMA_WARP = 8, MMA_WARP = 9;
 constexpr int NUM_THREADS = 10 * 32;
@@ -48,6 +49,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+  float* addv_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -156,16 +158,30 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     // ------------------------------------------------------------------ epilogue: thread = row, 4 x 32 columns each
     const int q = warp & 3;             // TMEM lane quadrant
     const int col_half = warp >> 2;     // columns [128*col_half, +128)
+    const int et = threadIdx.x;         // 0..255 within the epilogue warps
     int as = 0;
     uint32_t aphase = 0;
     float amax = 0.f;
     for (int u = unit0; u < n_units; u += unit_step) {
-      const long long row = static_cast<long long>(u * 2 + static_cast<int>(rank)) * BM + q * 32 + lane;
+      const long long tile_first = static_cast<long long>(u * 2 + static_cast<int>(rank)) * BM;
+      const long long row = tile_first + q * 32 + lane;
       const bool valid = row < p.M;
       const int cloud = valid ? static_cast<int>(row / p.pts_per_cloud) : 0;
       // pooling fast path: all 32 rows of this warp are valid and in one cloud
       const long long row_first = row - lane;
       const bool warp_one_cloud = (row_first + 31 < p.M) && (row_first / p.pts_per_cloud == (row_first + 31) / p.pts_per_cloud);
+      // The additive row (bias + the cloud's row vector) is the same for every row of a tile that lies inside one
+      // cloud: stage it in shared memory once per tile instead of 2 x 128 global loads per thread.
+      const long long tile_last = min(tile_first + BM, p.M) - 1;
+      const bool tile_one_cloud = tile_last >= tile_first && (tile_first / p.pts_per_cloud == tile_last / p.pts_per_cloud);
+      float* addv = addv_s + as * 256;
+      {
+        float a = p.bias ? __ldg(p.bias + et) : 0.f;
+        if (p.rowvec && tile_one_cloud) a += __ldg(p.rowvec + static_cast<size_t>(tile_first / p.pts_per_cloud) * BN + et);
+        addv[et] = a;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const bool row_from_global = p.rowvec && !tile_one_cloud;
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after_sync();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * 128;
@@ -185,9 +201,8 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
         const int c0 = col_half * 128 + ch * 32;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          float y = v[c] * p.acc_scale_inv;
-          if (p.bias) y += __ldg(p.bias + c0 + c);
-          if (p.rowvec) y += __ldg(p.rowvec + static_cast<size_t>(cloud) * BN + c0 + c);
+          float y = v[c] * p.acc_scale_inv + addv[c0 + c];
+          if (row_from_global) y += __ldg(p.rowvec + static_cast<size_t>(cloud) * BN + c0 + c);
           v[c] = y;
         }
         if (p.out_f32 && valid) {
@@ -195,30 +210,16 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
-        if (p.pool) {
-          if (warp_one_cloud) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float mx = v[c];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-              if (lane == (c & 31)) atomicMax(p.pool + static_cast<size_t>(cloud) * BN + c0 + c, encode_max(mx));
-            }
-          } else if (valid) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) atomicMax(p.pool + static_cast<size_t>(cloud) * BN + c0 + c, encode_max(v[c]));
-          }
-        }
         if (valid && (p.out_hl || p.out_hl_relu)) {
           // 32 consecutive channels of this row: 64 B of hi and 64 B of lo per destination
-          __align__(16) __half hi[32], lo[32];
+          __align__(16) __half2 hi[16], lo[16];
           if (p.out_hl) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float sv = v[c] * p.act_scale;
-              hi[c] = __float2half_rn(sv);
-              lo[c] = __float2half_rn(sv - __half2float(hi[c]));
-              amax = fmaxf(amax, fabsf(sv));
+            for (int c = 0; c < 16; ++c) {
+              const float s0 = v[2 * c] * p.act_scale, s1 = v[2 * c + 1] * p.act_scale;
+              hi[c] = __floats2half2_rn(s0, s1);
+              lo[c] = __floats2half2_rn(s0 - __low2float(hi[c]), s1 - __high2float(hi[c]));
+              amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
             }
             uint4* dh = reinterpret_cast<uint4*>(p.out_hl + row * (2 * BN) + c0);
             uint4* dl = reinterpret_cast<uint4*>(p.out_hl + row * (2 * BN) + BN + c0);
@@ -227,14 +228,30 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
               dh[c] = reinterpret_cast<const uint4*>(hi)[c];
               dl[c] = reinterpret_cast<const uint4*>(lo)[c];
             }
-          }
-          if (p.out_hl_relu) {
+            if (p.out_hl_relu) {
+              // relu(y) splits into the same (hi, lo) when y > 0 and into (0, 0) otherwise: mask the packed halves
+              const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float sv = fmaxf(v[c], 0.f) * p.act_scale;
-              hi[c] = __float2half_rn(sv);
-              lo[c] = __float2half_rn(sv - __half2float(hi[c]));
-              amax = fmaxf(amax, fabsf(sv));
+              for (int c = 0; c < 16; ++c) {
+                const __half2 pos = __hgt2(hi[c], zero);          // 1.0 where hi > 0
+                hi[c] = __hmul2(hi[c], pos);
+                lo[c] = __hmul2(lo[c], pos);
+              }
+              uint4* rh = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + c0);
+              uint4* rl = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + BN + c0);
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                rh[c] = reinterpret_cast<const uint4*>(hi)[c];
+                rl[c] = reinterpret_cast<const uint4*>(lo)[c];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              const float s0 = fmaxf(v[2 * c], 0.f) * p.act_scale, s1 = fmaxf(v[2 * c + 1], 0.f) * p.act_scale;
+              hi[c] = __floats2half2_rn(s0, s1);
+              lo[c] = __floats2half2_rn(s0 - __low2float(hi[c]), s1 - __high2float(hi[c]));
+              amax = fmaxf(amax, fmaxf(s0, s1));
             }
             uint4* dh = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + c0);
             uint4* dl = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + BN + c0);
@@ -243,6 +260,26 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
               dh[c] = reinterpret_cast<const uint4*>(hi)[c];
               dl[c] = reinterpret_cast<const uint4*>(lo)[c];
             }
+          }
+        }
+        if (p.pool) {
+          if (warp_one_cloud) {
+            // column max over the warp's 32 rows as a butterfly reduce-scatter: 31 shuffles for 32 columns instead of
+            // 160; afterwards lane l holds the maximum of column l (destroys v, hence last)
+#pragma unroll
+            for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+              const bool up = (lane & s) != 0;
+#pragma unroll
+              for (int i = 0; i < n / 2; ++i) {
+                const float send = up ? v[i] : v[i + n / 2];
+                const float keep = up ? v[i + n / 2] : v[i];
+                v[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, s));
+              }
+            }
+            atomicMax(p.pool + static_cast<size_t>(cloud) * BN + c0 + lane, encode_max(v[0]));
+          } else if (valid) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) atomicMax(p.pool + static_cast<size_t>(cloud) * BN + c0 + c, encode_max(v[c]));
           }
         }
       }

@@ -39,7 +39,8 @@ def forward(sd, adj, n_blocks, smpl_model, batch, x_t, t_orig, mean, std, cond=N
 
 
 def sample(sd, adj, n_blocks, smpl_model, batch, sch, noise, mean, std, mode="ddim", dtype=np.float32, hoist=True,
-           diffuse_fuse=True, grad_fn=None, cond_grad_weight=1.0, trace=None, only_mask_img_cond=True):
+           diffuse_fuse=True, grad_fn=None, cond_grad_weight=1.0, trace=None, only_mask_img_cond=True,
+           skip_timesteps=0, init_data=None):
     """One chain of p_sample_loop / ddim_sample_loop (gaussian_diffusion.py:391-508, 618-718).
 
     noise: [n_steps+1, B, 144] in the reference's draw order — noise[0] is `th.randn(*shape)` (:478), noise[1+k] the
@@ -47,8 +48,14 @@ def sample(sd, adj, n_blocks, smpl_model, batch, sch, noise, mean, std, mode="dd
     Returns the last step's output dict ('other_outputs', :443,780) plus 'sample'."""
     cond = encoders.conditioning(sd, batch, dtype) if hoist else None
     x = noise[0].astype(dtype)
+    if skip_timesteps and init_data is None:  # gaussian_diffusion.py:480-481
+        init_data = np.zeros_like(x)
+    first = sch.num_timesteps - skip_timesteps - 1  # :483
+    if init_data is not None:  # :485-487 q_sample(init_data, t = first kept index, noise = the initial draw)
+        c0, c1 = np.float32(sch.sqrt_alphas_cumprod[first]), np.float32(sch.sqrt_one_minus_alphas_cumprod[first])
+        x = (dtype(c0) * init_data.astype(dtype) + dtype(c1) * x).astype(dtype)
     out = None
-    for k, i in enumerate(range(sch.num_timesteps - 1, -1, -1)):
+    for k, i in enumerate(range(first, -1, -1)):
         B = x.shape[0]
         t_orig = np.full(B, sch.timestep_map[i], dtype=np.int64)  # respace.py:124-126
         last = i == 0

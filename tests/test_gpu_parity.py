@@ -277,6 +277,37 @@ def test_graphed_sampler_equals_eager(full):
     assert not model.engine.check_overflow()
 
 
+def test_bench_precision_configuration_tf32_convs(full, golden_dir):
+    """bench.py runs the ResNet-50 feature provider at torch's DEFAULT conv precision (cuDNN may use TF32), which is what
+    the reference's own CUDA path does; every other test of this module forces strict fp32.  This one measures what that
+    default costs, against the float64 reference AND against the eager-PyTorch restatement of the reference's GPU path
+    (oracle/torch_eager.py) run with the same default: the deviation of this repo's path must stay within the
+    deviation the reference's own GPU path shows, i.e. TF32 noise is the reference's, not ours."""
+    from oracle import torch_eager
+    model, diffusion, sd, smpl_model, mean, std = full
+    g64 = np.load(os.path.join(golden_dir, "ddim5_T50_hid1024_f64.npz"))
+    noise = torch.from_numpy(synth.make_noise(0, 1, 2, 5)[0]).cuda()
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        model._cond_key = None
+        ours = diffusion.sample_many(model, _tb(synth.make_batch(0, 2)), 1, "ddim5", noise=noise)
+        ref_model, sch = torch_eager.build(1024, 4, 50, "ddim5", "cuda:0")
+        ref = torch_eager.val_losses(ref_model, sch, _tb(synth.make_batch(0, 2)), [2, 144], "ddim", noise=noise)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+        model._cond_key = None
+    R64 = np.concatenate([g64["global_orient"], g64["body_pose"]], axis=1)
+    v64 = o_smpl.smpl_forward(smpl_model, R64, g64["betas"])["vertices"]
+    d_ours = np.abs(ours["pred_x_start"].cpu().numpy() - g64["pred_x_start"]).max()
+    d_ref = np.abs(ref["pred_x_start"].cpu().numpy() - g64["pred_x_start"]).max()
+    v_ours = np.abs(ours["pred_vertices"].cpu().numpy() - v64).max() * 1e3
+    v_ref = np.abs(ref["pred_vertices"].cpu().numpy() - v64).max() * 1e3
+    print(f"TF32 convs allowed: ours |x0 - f64| = {d_ours:.3e}, vertices {v_ours:.3e} mm; reference's GPU dataflow "
+          f"(eager torch, same flag) |x0 - f64| = {d_ref:.3e}, vertices {v_ref:.3e} mm")
+    assert d_ours < max(4 * d_ref, 1e-5) and v_ours < max(4 * v_ref, 0.05)
+
+
 def test_maxpool_nhwc_bit_exact(full):
     """The ResNet stem's MaxPool2d(3, 2, 1) on the library's NHWC kernel equals torch's, including odd sizes."""
     eng = full[0].engine
@@ -334,6 +365,52 @@ def test_val_losses_default_compute_loss_vs_reference_golden(small, golden_dir):
         assert abs(float(v) - float(o_ls[k])) <= 5e-5 * max(1.0, abs(ref)), (k, float(v), float(o_ls[k]))
     with pytest.raises(KeyError):   # label-free batches must say what is missing instead of failing obscurely
         diffusion.val_losses(model=model, batch=_tb(synth.make_batch(0, 3)), shape=[3, 144], timestep_respacing="ddim5")
+
+
+def test_config0_single_image_single_sample_vs_oracle(full):
+    """configs[0] of BASELINE.json: test_egohmr.py's sampling block with batch=1, num_samples=1 (DDIM-5, 224x224 image,
+    1024 scene points) — the smallest layout (2 slots, one padded CTA-pair tile) — against the float64 oracle."""
+    model, diffusion, sd, smpl_model, mean, std = full
+    b_np = synth.make_batch(9, 1)
+    noise = synth.make_noise(9, 1, 1, 5)[0]
+    out = diffusion.sample_many(model, _tb(b_np), 1, "ddim5", noise=torch.from_numpy(noise).cuda())
+    ref = o_egohmr.sample(sd, synth.skeleton_adjacency(), 4, smpl_model, b_np, schedule.Schedule(50, "ddim5"), noise, mean, std,
+                          "ddim", dtype=np.float64)
+    assert out["pred_x_start"].shape == (1, 144) and out["pred_vertices"].shape == (1, 6890, 3)
+    assert np.abs(out["pred_x_start"].cpu().numpy() - ref["pred_x_start"]).max() < X0_TOL
+    assert np.abs(out["pred_vertices"].cpu().numpy() - ref["pred_vertices"]).max() < VERT_TOL_M
+    assert np.abs(out["pred_keypoints_2d_full"].cpu().numpy() - ref["pred_keypoints_2d_full"]).max() < 1e-4
+
+
+def test_p_sample_loop_skip_init_dump_options(small):
+    """p_sample_loop's less-travelled arguments (gaussian_diffusion.py:391-446, 468-487): skip_timesteps + init_data
+    (q_sample of the initial state at the first kept step), dump_steps (returns the list of intermediate samples) and
+    progress=True, against the oracle."""
+    model, diffusion, sd, smpl_model, mean, std = small
+    b_np = synth.make_batch(0, 3)
+    noise = synth.make_noise(3, 1, 3, 50)[0]
+    init = np.random.default_rng(8).normal(0, 0.5, (3, 144)).astype(np.float32)
+    skip = 20
+    trace = []
+    ref = o_egohmr.sample(sd, synth.skeleton_adjacency(), 2, smpl_model, b_np, schedule.Schedule(50, ""), noise, mean, std,
+                          "ddpm", dtype=np.float64, skip_timesteps=skip, init_data=init, trace=trace)
+    assert len(trace) == 30 and trace[0]["t"] == 29
+    feed = iter(torch.from_numpy(noise[1:]).cuda())
+    old = torch.randn_like
+    torch.randn_like = lambda x, **k: next(feed)
+    try:
+        final = diffusion.p_sample_loop(model, _tb(b_np), [3, 144], noise=torch.from_numpy(noise[0]).cuda(), progress=True,
+                                        skip_timesteps=skip, init_data=torch.from_numpy(init).cuda())
+        feed = iter(torch.from_numpy(noise[1:]).cuda())
+        dump = diffusion.p_sample_loop(model, _tb(b_np), [3, 144], noise=torch.from_numpy(noise[0]).cuda(),
+                                       skip_timesteps=skip, init_data=torch.from_numpy(init).cuda(), dump_steps=[0, 7, 29])
+    finally:
+        torch.randn_like = old
+    assert np.abs(final["pred_xstart"].cpu().numpy() - ref["pred_x_start"]).max() < 5e-6
+    assert np.abs(final["sample"].cpu().numpy() - ref["sample"]).max() < 5e-6
+    assert isinstance(dump, list) and len(dump) == 3
+    for d, k in zip(dump, (0, 7, 29)):
+        assert np.abs(d.cpu().numpy() - trace[k]["sample"]).max() < 5e-6
 
 
 def test_sample_many_equals_sequential_chains(full):
