@@ -584,7 +584,7 @@ static int run_output(ehb_ctx* ctx, int step, const float* x_t, const float* noi
   p.C = ctx->hid;
   p.n_bodies = ctx->n_bodies;
   p.diffuse_fuse = ctx->diffuse_fuse;
-  EHB_CUDA(ehb::launch_gcn_output(p, stream));
+  EHB_CUDA(ehb::launch_gcn_output(p, ctx->num_sms, stream));
   ctx->launches += 1;
   return 0;
 }

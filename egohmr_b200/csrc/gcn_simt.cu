@@ -4,6 +4,7 @@
 //   sgemm_nn               — plain fp32 GEMM for the once-per-batch conditioning folds and for the fp32 check path
 //   gcn_hidden_epilogue    — check-path twin of the tcgen05 kernel's epilogue (reads H = X.Wcat from global)
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace ehb {
 namespace {
@@ -201,7 +202,7 @@ __global__ void sampler_update_kernel(const StepCoef coef, int kind, const float
 // (guidance_param == 0: invisible joints take the image-masked pass, visible joints the image-conditioned pass)
 // and one sampler update (gaussian_diffusion.py:298-337 p_sample, :340-388 with gradient, :511-556 ddim_sample).
 // The update replays the reference's fp32 op order with contraction disabled so equal inputs give equal bits.
-__global__ void __launch_bounds__(256, 2) gcn_output_kernel(const __grid_constant__ OutputLayerParams p) {
+__global__ void __launch_bounds__(256, 2) gcn_output_fallback_kernel(const __grid_constant__ OutputLayerParams p) {
   __shared__ float hs[2][NJ][12];
   const int body = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,6 +274,153 @@ __global__ void __launch_bounds__(256, 2) gcn_output_kernel(const __grid_constan
   if (p.out_uncond) p.out_uncond[idx] = out[1];
   p.x0[idx] = x0;
   p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
+}
+
+// ------------------------------------------------------------------------------------------------ K3 (bulk-staged)
+// Same arithmetic as gcn_output_fallback_kernel, restructured around the memory system: the activations of one
+// (body, pass) slot are ONE contiguous 24 x C fp32 block, so a producer warp streams them with 1-D bulk copies
+// (cp.async.bulk + mbarrier transaction counts) through a 6-stage shared-memory ring of 8-row chunks while 8 consumer
+// warps reduce them.  Persistent blocks (one per SM) keep ~190 KB of loads in flight per SM without spending registers
+// on them; every consumer warp owns a fixed C/8-channel slice whose [k][12] output weights stay in registers for the
+// whole launch, so the weights cost no memory traffic at all.
+constexpr int K3_STAGES = 6, K3_ROWS = 8, K3_CONSUMERS = 8, K3_KPL = 4;   // K3_KPL: channels per lane, C <= 1024
+constexpr int K3_NACC = K3_ROWS * 12;
+
+struct K3Barriers {
+  uint64_t full[K3_STAGES];
+  uint64_t empty[K3_STAGES];
+};
+
+__global__ void __launch_bounds__((K3_CONSUMERS + 1) * 32, 1) gcn_output_kernel(const __grid_constant__ OutputLayerParams p) {
+  extern __shared__ __align__(128) uint8_t k3_smem[];
+  const int C = p.C;
+  const uint32_t chunk_bytes = K3_ROWS * C * sizeof(float);
+  float* ring = reinterpret_cast<float*>(k3_smem);
+  float* part = reinterpret_cast<float*>(k3_smem + K3_STAGES * chunk_bytes);     // [2][K3_CONSUMERS][K3_NACC]
+  float* hs = part + 2 * K3_CONSUMERS * K3_NACC;                                   // [2][NJ][12]
+  K3Barriers* bars = reinterpret_cast<K3Barriers*>(hs + 2 * NJ * 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int passes = p.diffuse_fuse ? 2 : 1;
+  const int n_chunks = passes * (NJ / K3_ROWS);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < K3_STAGES; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], K3_CONSUMERS);
+    }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == K3_CONSUMERS) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int body = blockIdx.x; body < p.n_bodies; body += gridDim.x) {
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          const int slot = p.body_slot[body * 2 + ch / (NJ / K3_ROWS)];
+          const float* src = p.act + (slot_row0(slot) + static_cast<size_t>(ch % (NJ / K3_ROWS)) * K3_ROWS) * C;
+          ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars->full[stage], chunk_bytes);
+          ptx::bulk_load_1d(ring + static_cast<size_t>(stage) * K3_ROWS * C, src, chunk_bytes, &bars->full[stage]);
+          if (++stage == K3_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers
+  const int slice = C / K3_CONSUMERS;            // channels of this warp
+  const int k0 = warp * slice;
+  float w[K3_KPL][12];
+#pragma unroll
+  for (int i = 0; i < K3_KPL; ++i) {
+    const int kk = lane + 32 * i;
+#pragma unroll
+    for (int o = 0; o < 12; ++o) w[i][o] = kk < slice ? __ldg(p.wout + static_cast<size_t>(k0 + kk) * 12 + o) : 0.f;
+  }
+  // after the butterfly below lane l holds the three sums with flat index (row * 12 + out) = base .. base + 2
+  const int base = ((lane & 16) ? 48 : 0) + ((lane & 8) ? 24 : 0) + ((lane & 4) ? 12 : 0) + ((lane & 2) ? 6 : 0) + ((lane & 1) ? 3 : 0);
+  int stage = 0;
+  uint32_t phase = 0;
+  uint32_t it = 0;   // chunk counter of this block (selects the partial-sum buffer)
+  for (int body = blockIdx.x; body < p.n_bodies; body += gridDim.x) {
+    float* hsb = hs;   // rewritten per body; the tail barrier below orders reuse
+    for (int ch = 0; ch < n_chunks; ++ch, ++it) {
+      ptx::mbar_wait(&bars->full[stage], phase);
+      const float* a = ring + static_cast<size_t>(stage) * K3_ROWS * C + k0;
+      float acc[K3_NACC];
+#pragma unroll
+      for (int e = 0; e < K3_NACC; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int i = 0; i < K3_KPL; ++i) {
+        const int kk = lane + 32 * i;
+        if (kk < slice) {
+#pragma unroll
+          for (int r = 0; r < K3_ROWS; ++r) {
+            const float av = a[static_cast<size_t>(r) * C + kk];
+#pragma unroll
+            for (int o = 0; o < 12; ++o) acc[r * 12 + o] = fmaf(av, w[i][o], acc[r * 12 + o]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars->empty[stage]);   // this warp is done reading the stage
+      if (++stage == K3_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+      // sum over the warp's 32 lanes: butterfly reduce-scatter, 96 -> 3 values per lane in 93 shuffles
+#pragma unroll
+      for (int s = 16, n = K3_NACC; s >= 1; s >>= 1, n >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int e = 0; e < n / 2; ++e) {
+          const float send = up ? acc[e] : acc[e + n / 2];
+          const float keep = up ? acc[e + n / 2] : acc[e];
+          acc[e] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      float* pb = part + ((it & 1) * K3_CONSUMERS + warp) * K3_NACC;
+      pb[base] = acc[0];
+      pb[base + 1] = acc[1];
+      pb[base + 2] = acc[2];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x < K3_NACC) {   // sum over the 8 channel slices, fixed order
+        const float* q = part + (it & 1) * K3_CONSUMERS * K3_NACC + threadIdx.x;
+        float sum = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < K3_CONSUMERS; ++ww) sum += q[ww * K3_NACC];
+        const int pass = ch / (NJ / K3_ROWS), j = (ch % (NJ / K3_ROWS)) * K3_ROWS + threadIdx.x / 12;
+        hsb[(pass * NJ + j) * 12 + threadIdx.x % 12] = sum;
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x < XDIM) {
+      const int e = threadIdx.x, j = e / 6, d = e % 6;
+      float out[2] = {0.f, 0.f};
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass >= passes) continue;
+        const float* h = hsb + pass * NJ * 12;
+        float acc = p.adj.diag[j] * (p.mod[j * 6 + d] * h[j * 12 + d]);
+        for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[j][i], p.mod[i * 6 + d] * h[i * 12 + 6 + d], acc);
+        out[pass] = acc + p.bias[d];
+      }
+      const int img = p.img_of_body[body];
+      const float x0 = p.diffuse_fuse ? (p.vis[img * NJ + j] ? out[0] : out[1]) : out[0];
+      const size_t idx = static_cast<size_t>(body) * XDIM + e;
+      if (p.out_cond) p.out_cond[idx] = out[0];
+      if (p.out_uncond) p.out_uncond[idx] = out[1];
+      p.x0[idx] = x0;
+      p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // hs is rewritten by the next body's first chunk
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ non-local block
@@ -466,9 +614,22 @@ cudaError_t launch_sampler_update(const StepCoef& coef, int kind, const float* x
   return cudaGetLastError();
 }
 
-cudaError_t launch_gcn_output(const OutputLayerParams& p, cudaStream_t stream) {
+cudaError_t launch_gcn_output(const OutputLayerParams& p, int num_sms, cudaStream_t stream) {
   if (p.n_bodies <= 0) return cudaSuccess;
-  gcn_output_kernel<<<p.n_bodies, 256, 0, stream>>>(p);
+  if (p.C > 256 * K3_KPL || p.C % (8 * 4) != 0) {   // register-resident weight slices cover C <= 1024
+    gcn_output_fallback_kernel<<<p.n_bodies, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
+  const size_t smem = static_cast<size_t>(K3_STAGES) * K3_ROWS * p.C * sizeof(float) +
+                      (2 * K3_CONSUMERS * K3_NACC + 2 * NJ * 12) * sizeof(float) + sizeof(K3Barriers);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(gcn_output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr_smem = smem;
+  }
+  const int grid = p.n_bodies < num_sms ? p.n_bodies : num_sms;
+  gcn_output_kernel<<<grid, (K3_CONSUMERS + 1) * 32, smem, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -132,7 +132,7 @@ struct OutputLayerParams {
   int kind;
   int C, n_bodies, diffuse_fuse;
 };
-cudaError_t launch_gcn_output(const OutputLayerParams& p, cudaStream_t stream);
+cudaError_t launch_gcn_output(const OutputLayerParams& p, int num_sms, cudaStream_t stream);
 // x_prev = update(x_t, x0, noise, grad) elementwise over n floats (same arithmetic as the tail of launch_gcn_output)
 cudaError_t launch_sampler_update(const StepCoef& coef, int kind, const float* x_t, const float* x0,
                                   const float* noise, const float* grad, float* x_prev, size_t n,
