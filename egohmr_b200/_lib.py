@@ -38,6 +38,16 @@ class NonLocalWeights(C.Structure):
                                           "bn_bias", "bn_mean", "bn_var")] + [("bn_eps", C.c_float)]
 
 
+class ConvBN(C.Structure):
+    _fields_ = [("cout", C.c_int32), ("cin", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32),
+                ("pad", C.c_int32), ("weight", c_float_p), ("bn_weight", c_float_p), ("bn_bias", c_float_p),
+                ("bn_mean", c_float_p), ("bn_var", c_float_p), ("bn_eps", C.c_float)]
+
+
+class ResnetWeights(C.Structure):
+    _fields_ = [("convs", C.POINTER(ConvBN)), ("n_convs", C.c_int32), ("blocks", C.c_int32 * 4)]
+
+
 class PointnetWeights(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("out_dim", C.c_int32), ("fc_pos_w", c_float_p), ("fc_pos_b", c_float_p),
                 ("fc0_w", c_float_p * 4), ("fc0_b", c_float_p * 4), ("fc1_w", c_float_p * 4), ("fc1_b", c_float_p * 4),
@@ -77,6 +87,8 @@ SIGNATURES = {
     "ehb_maxpool3x3s2_nhwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "ehb_scene_crop": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "ehb_procrustes_align": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "ehb_resnet_load": (C.c_int, [_vp, C.POINTER(ResnetWeights)]),
+    "ehb_resnet_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "ehb_rotmat_to_angle_axis": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "ehb_smpl_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_debug_set_gemm_mode": (C.c_int, [_vp, C.c_int]),

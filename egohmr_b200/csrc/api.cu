@@ -195,10 +195,22 @@ struct ehb_ctx {
   DevBuf pn_pos_w, pn_pos_b, pn_fc0[4], pn_fc1[4], pn_sc[4], pn_b0[4], pn_b1[4], pn_w0b_t[4], pn_wsb_t[4], pn_fcc_t, pn_fcc_b;
   DevBuf pn_x[2], pn_y[2], pn_h, pn_pool, pn_pooled, pn_pooled_relu, pn_row0, pn_rows;
 
+  // ---- ResNet-50 image encoder (conv_umma.cu)
+  struct ConvPlan {
+    int cout = 0, cin = 0, kh = 0, kw = 0, stride = 1, pad = 0, Kp = 0;
+    float w_scale = 1.f;
+    DevBuf w_hl, bias;
+  };
+  std::vector<ConvPlan*> rn_convs;
+  int rn_blocks[4] = {0, 0, 0, 0};
+  bool rn_loaded = false;
+  DevBuf rn_col, rn_x[2], rn_y1, rn_y2, rn_idt;
+
   DevBuf overflow, splitk;
 
   ~ehb_ctx() {
     for (auto* h : hidden) delete h;
+    for (auto* c : rn_convs) delete c;
   }
 };
 
@@ -1137,6 +1149,179 @@ int ehb_procrustes_align(ehb_ctx* ctx, const float* s1, const float* s2, const f
   EHB_CUDA(cudaSetDevice(ctx->device));
   EHB_CUDA(ehb::launch_procrustes(s1, s2, mask, n_problems, n_points, s1_hat, err, static_cast<cudaStream_t>(stream_)));
   ctx->launches += n_problems > 0;
+  return 0;
+}
+
+int ehb_resnet_load(ehb_ctx* ctx, const ehb_resnet_weights* w) {
+  if (!ctx || !w || !w->convs) return fail("ehb_resnet_load: null argument");
+  int expect = 1;
+  for (int s = 0; s < 4; ++s) {
+    if (w->blocks[s] <= 0) return fail("ehb_resnet_load: blocks must be positive");
+    expect += 3 * w->blocks[s] + 1;
+  }
+  if (w->n_convs != expect) return fail("ehb_resnet_load: n_convs does not match the block counts");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  for (auto* c : ctx->rn_convs) delete c;
+  ctx->rn_convs.clear();
+  ctx->rn_loaded = false;
+  for (int i = 0; i < w->n_convs; ++i) {
+    const ehb_conv_bn& c = w->convs[i];
+    if (c.cout <= 0 || c.cout % 64 || c.cin <= 0 || c.kh <= 0 || c.kw <= 0 || c.stride <= 0 || c.pad < 0)
+      return fail("ehb_resnet_load: bad convolution shape (cout must be a multiple of 64)");
+    if (i > 0 && c.cin % 64) return fail("ehb_resnet_load: cin must be a multiple of 64 after the stem");
+    auto* pl = new ehb_ctx::ConvPlan();
+    ctx->rn_convs.push_back(pl);
+    pl->cout = c.cout; pl->cin = c.cin; pl->kh = c.kh; pl->kw = c.kw; pl->stride = c.stride; pl->pad = c.pad;
+    const int K = c.kh * c.kw * c.cin;
+    pl->Kp = (K + 63) / 64 * 64;
+    // fold BatchNorm (eval): y = conv(x; W) * s + (beta - mean * s),  s = gamma / sqrt(var + eps)
+    // GEMM weight row co: k = (ky*kw + kx)*cin + ci  (the im2col order of resnet_ops.cu)
+    std::vector<float> wf(static_cast<size_t>(c.cout) * pl->Kp, 0.f), bias(c.cout);
+    float maxabs = 0.f;
+    for (int co = 0; co < c.cout; ++co) {
+      const double s = double(c.bn_weight[co]) / std::sqrt(double(c.bn_var[co]) + double(c.bn_eps));
+      bias[co] = float(double(c.bn_bias[co]) - double(c.bn_mean[co]) * s);
+      for (int ci = 0; ci < c.cin; ++ci)
+        for (int t = 0; t < c.kh * c.kw; ++t) {
+          const float v = float(double(c.weight[(static_cast<size_t>(co) * c.cin + ci) * c.kh * c.kw + t]) * s);
+          wf[static_cast<size_t>(co) * pl->Kp + static_cast<size_t>(t) * c.cin + ci] = v;
+          maxabs = std::max(maxabs, std::fabs(v));
+        }
+    }
+    if (!std::isfinite(maxabs)) return fail("ehb_resnet_load: non-finite weight");
+    pl->w_scale = pow2_scale(maxabs);
+    std::vector<__half> hl;
+    split_hl(wf.data(), c.cout, pl->Kp, pl->Kp, 0, pl->w_scale, hl);
+    EHB_CUDA(pl->w_hl.upload(hl));
+    EHB_CUDA(pl->bias.upload(bias));
+  }
+  for (int s = 0; s < 4; ++s) ctx->rn_blocks[s] = w->blocks[s];
+  ctx->rn_loaded = true;
+  return 0;
+}
+
+// one convolution as a GEMM: A [rows_pad][2*Kp] hi/lo (activation or im2col matrix) -> out [rows_pad][2*cout]
+static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, long long rows, const __half* res, __half* out,
+                   int relu, cudaStream_t stream) {
+  const int n_mtiles = static_cast<int>((rows + 255) / 256) * 2;
+  const size_t rows_pad = static_cast<size_t>(n_mtiles) * 128;
+  const int bn = ehb::conv_gemm_tile_n(c.cout);
+  CUtensorMap tA, tB;
+  if (make_tmap_f16(&tA, A, rows_pad, 2 * static_cast<uint64_t>(c.Kp), 128)) return 1;
+  if (make_tmap_f16(&tB, c.w_hl.p, c.cout, 2 * static_cast<uint64_t>(c.Kp), bn / 2)) return 1;
+  ehb::ConvGemmParams p{};
+  p.bias = c.bias.as<float>();
+  p.res_hl = res;
+  p.out_hl = out;
+  p.out_f32 = nullptr;
+  p.overflow_flag = ctx->overflow.as<int>();
+  p.M = rows;
+  p.acc_scale_inv = 1.f / (ctx->act_scale * c.w_scale);
+  p.act_scale = ctx->act_scale;
+  p.K = c.Kp;
+  p.Cout = c.cout;
+  p.out_ld = 2 * c.cout;
+  p.n_mtiles = n_mtiles;
+  p.n_ntiles = c.cout / bn;
+  p.relu = relu;
+  EHB_CUDA(ehb::launch_conv_gemm(tA, tB, p, ctx->num_sms, stream));
+  ctx->launches += 1;
+  return 0;
+}
+
+int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, float* feats, void* stream_) {
+  if (!ctx || !img || !feats) return fail("ehb_resnet_forward: null argument");
+  if (!ctx->rn_loaded) return fail("ehb_resnet_forward: call ehb_resnet_load first");
+  if (n <= 0 || h < 32 || w < 32) return fail("ehb_resnet_forward: need n > 0 and an image of at least 32 x 32");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  auto pad_rows = [](long long r) { return static_cast<size_t>((r + 255) / 256) * 256; };
+  auto out_dim = [](int x, int k, int s, int p) { return (x + 2 * p - k) / s + 1; };
+  const auto& cv = ctx->rn_convs;
+  // ---- buffer sizes for this batch
+  const int H1 = out_dim(h, 7, 2, 3), W1 = out_dim(w, 7, 2, 3), H2 = out_dim(H1, 3, 2, 1), W2 = out_dim(W1, 3, 2, 1);
+  size_t col_bytes = pad_rows(static_cast<long long>(n) * H1 * W1) * 2 * cv[0]->Kp * sizeof(__half);
+  size_t x_bytes = pad_rows(static_cast<long long>(n) * H1 * W1) * 2 * cv[0]->cout * sizeof(__half);
+  size_t y_bytes = 0, i_bytes = 0;
+  {
+    int H = H2, W = W2, ci = 1;
+    for (int s = 0; s < 4; ++s)
+      for (int b = 0; b < ctx->rn_blocks[s]; ++b) {
+        const auto& c1 = *cv[ci];
+        const auto& c2 = *cv[ci + 1];
+        const auto& c3 = *cv[ci + 2];
+        const int Ho = out_dim(H, 3, c2.stride, 1), Wo = out_dim(W, 3, c2.stride, 1);
+        const size_t rin = pad_rows(static_cast<long long>(n) * H * W), rout = pad_rows(static_cast<long long>(n) * Ho * Wo);
+        y_bytes = std::max(y_bytes, std::max(rin * 2 * c1.cout, rout * 2 * c2.cout) * sizeof(__half));
+        col_bytes = std::max(col_bytes, rout * 2 * c2.Kp * sizeof(__half));
+        x_bytes = std::max(x_bytes, rout * 2 * c3.cout * sizeof(__half));
+        if (b == 0) {
+          const auto& cd = *cv[ci + 3];
+          i_bytes = std::max(i_bytes, rout * 2 * cd.cout * sizeof(__half));
+          if (cd.stride != 1) col_bytes = std::max(col_bytes, rout * 2 * cd.Kp * sizeof(__half));
+        }
+        ci += b == 0 ? 4 : 3;
+        H = Ho;
+        W = Wo;
+      }
+  }
+  EHB_CUDA(ctx->rn_col.ensure(col_bytes, true));
+  EHB_CUDA(ctx->rn_x[0].ensure(x_bytes, true));
+  EHB_CUDA(ctx->rn_x[1].ensure(x_bytes, true));
+  EHB_CUDA(ctx->rn_y1.ensure(y_bytes, true));
+  EHB_CUDA(ctx->rn_y2.ensure(y_bytes, true));
+  EHB_CUDA(ctx->rn_idt.ensure(i_bytes, true));
+  __half* col = ctx->rn_col.as<__half>();
+  // ---- stem: conv 7x7 / 2 + BN + ReLU, max-pool 3x3 / 2  (models/resnet.py:109-113, 140-143)
+  {
+    const auto& c0 = *cv[0];
+    if (c0.kh != 7 || c0.kw != 7 || c0.cin != 3 || c0.stride != 2 || c0.pad != 3) return fail("ehb_resnet_forward: unexpected stem");
+    EHB_CUDA(ehb::launch_im2col_stem(img, col, n, h, w, H1, W1, c0.Kp, ctx->act_scale, stream));
+    if (rn_gemm(ctx, c0, col, static_cast<long long>(n) * H1 * W1, nullptr, ctx->rn_x[1].as<__half>(), 1, stream)) return 1;
+    EHB_CUDA(ehb::launch_maxpool_hl(ctx->rn_x[1].as<__half>(), ctx->rn_x[0].as<__half>(), n, H1, W1, c0.cout, stream));
+    ctx->launches += 2;
+  }
+  int cur = 0, H = H2, W = W2, C = cv[0]->cout, ci = 1;
+  for (int s = 0; s < 4; ++s)
+    for (int b = 0; b < ctx->rn_blocks[s]; ++b) {
+      const auto& c1 = *cv[ci];
+      const auto& c2 = *cv[ci + 1];
+      const auto& c3 = *cv[ci + 2];
+      if (c1.kh != 1 || c1.cin != C || c2.kh != 3 || c2.cin != c1.cout || c3.kh != 1 || c3.cin != c2.cout)
+        return fail("ehb_resnet_forward: unexpected bottleneck layout");
+      const __half* x = ctx->rn_x[cur].as<__half>();
+      __half* xo = ctx->rn_x[cur ^ 1].as<__half>();
+      const int Ho = out_dim(H, 3, c2.stride, 1), Wo = out_dim(W, 3, c2.stride, 1);
+      const long long rin = static_cast<long long>(n) * H * W, rout = static_cast<long long>(n) * Ho * Wo;
+      if (rn_gemm(ctx, c1, x, rin, nullptr, ctx->rn_y1.as<__half>(), 1, stream)) return 1;
+      EHB_CUDA(ehb::launch_im2col_hl(ctx->rn_y1.as<__half>(), col, n, H, W, c1.cout, 3, 3, c2.stride, 1, Ho, Wo, stream));
+      if (rn_gemm(ctx, c2, col, rout, nullptr, ctx->rn_y2.as<__half>(), 1, stream)) return 1;
+      ctx->launches += 1;
+      const __half* idt = x;
+      if (b == 0) {
+        const auto& cd = *cv[ci + 3];
+        if (cd.kh != 1 || cd.cin != C || cd.cout != c3.cout || cd.stride != c2.stride)
+          return fail("ehb_resnet_forward: unexpected downsample layout");
+        const __half* a = x;
+        if (cd.stride != 1) {
+          EHB_CUDA(ehb::launch_im2col_hl(x, col, n, H, W, C, 1, 1, cd.stride, 0, Ho, Wo, stream));
+          ctx->launches += 1;
+          a = col;
+        }
+        if (rn_gemm(ctx, cd, a, rout, nullptr, ctx->rn_idt.as<__half>(), 0, stream)) return 1;
+        idt = ctx->rn_idt.as<__half>();
+      } else if (c3.cout != C || c2.stride != 1) {
+        return fail("ehb_resnet_forward: identity shortcut with a shape change");
+      }
+      if (rn_gemm(ctx, c3, ctx->rn_y2.as<__half>(), rout, idt, xo, 1, stream)) return 1;
+      ci += b == 0 ? 4 : 3;
+      cur ^= 1;
+      H = Ho;
+      W = Wo;
+      C = c3.cout;
+    }
+  EHB_CUDA(ehb::launch_avgpool_hl(ctx->rn_x[cur].as<__half>(), feats, n, H * W, C, ctx->act_scale, stream));
+  ctx->launches += 1;
   return 0;
 }
 

@@ -1,0 +1,296 @@
+// K9 — convolutions of the ResNet-50 image encoder (models/resnet.py:60-150) as GEMMs on tcgen05, fp32-class accuracy.
+//
+//   Y[M, Cout] = A[M, K] W^T + bias (+ identity) (-> ReLU),  M = images x out-pixels (NHWC rows), K = kh*kw*Cin
+//
+// A is always a plain row-major fp16 [hi(K) | lo(K)] matrix: a 1x1/stride-1 convolution reads the previous layer's
+// activation matrix as it is, everything else (3x3, strided 1x1, the 7x7 stem) reads an im2col matrix written by
+// resnet_ops.cu.  BatchNorm (eval) is folded into W and bias on the host.  Same error-compensated scheme as the GCN
+// layer kernel (hi*hi + hi*lo + lo*hi into one fp32 TMEM accumulator), same CTA-pair / TMA / mbarrier pipeline as
+// linear_umma.cu, generalised over the N tile (64 / 128 / 256 output channels per tile, so the 64- and 128-channel
+// layers do not pay for 256) and over n-tiles inside the persistent work loop.  The epilogue writes the NEXT layer's
+// operand directly: bias, residual add (identity read back from its own hi/lo operand), ReLU, fp16 hi/lo split.
+#include "epilogue.cuh"
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace ehb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 128-byte swizzled rows
+constexpr int UMMA_K = 16;
+constexpr int A_BYTES = BM * BK * 2;   // 16 KiB
+constexpr int BAR_BYTES = 256;
+constexpr int ADDV_BYTES = 2 * 256 * 4;
+constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant: warp w and w+4 split the tile's columns
+constexpr int TMA_WARP = 8, MMA_WARP = 9;
+constexpr int NUM_THREADS = 10 * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int MAX_STAGES = 4;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2 / 2;                 // per CTA of the pair: half of the tile's N rows
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 / 48 / 40 KiB
+  static constexpr int STAGES = BN == 256 ? 3 : 4;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES + NUM_EPI_WARPS * EPI_SCRATCH_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
+};
+
+struct Barriers {
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
+  uint64_t tfull[2];
+  uint64_t tempty[2];
+  uint32_t tmem_base;
+};
+static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+  float* addv_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES);
+  uint8_t* scratch_s = smem + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_units = (p.n_mtiles / 2) * p.n_ntiles;
+  const int unit0 = blockIdx.x / 2, unit_step = gridDim.x / 2;
+  const int KB = p.K / BK;
+
+  if (warp == TMA_WARP && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+  }
+  if (warp == MMA_WARP && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&bars->full[s], 1);
+      ptx::mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&bars->tfull[s], 1);
+      ptx::mbar_init(&bars->tempty[s], 2 * NUM_EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == TMA_WARP) {
+    ptx::tmem_alloc_2sm(&bars->tmem_base, TMEM_COLS);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == TMA_WARP) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = unit0; u < n_units; u += unit_step) {
+        const int m_row = ((u / p.n_ntiles) * 2 + static_cast<int>(rank)) * BM;
+        const int b_row = (u % p.n_ntiles) * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* s = smem + stage * STAGE_BYTES;
+          const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
+          if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
+          ptx::tma_load_2d_2sm(s, &tmA, lfull, kb * BK, m_row);
+          ptx::tma_load_2d_2sm(s + A_BYTES, &tmA, lfull, p.K + kb * BK, m_row);
+          ptx::tma_load_2d_2sm(s + 2 * A_BYTES, &tmB, lfull, kb * BK, b_row);
+          ptx::tma_load_2d_2sm(s + 2 * A_BYTES + B_BYTES, &tmB, lfull, p.K + kb * BK, b_row);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == MMA_WARP) {
+    if (leader) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16_f32(2 * BM, BN);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int u = unit0; u < n_units; u += unit_step) {
+        ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::mbar_wait(&bars->full[stage], phase);
+          ptx::tc_fence_after_sync();
+          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+            const uint32_t koff = ks * UMMA_K * 2;
+            const uint64_t a_hi = ptx::make_kmajor_desc<128>(sa + koff);
+            const uint64_t a_lo = ptx::make_kmajor_desc<128>(sa + A_BYTES + koff);
+            const uint64_t b_hi = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + koff);
+            const uint64_t b_lo = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + B_BYTES + koff);
+            ptx::umma_f16_2sm_elect(tacc, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
+            ptx::umma_f16_2sm_elect(tacc, a_hi, b_lo, idesc, 1u);
+            ptx::umma_f16_2sm_elect(tacc, a_lo, b_hi, idesc, 1u);
+          }
+          ptx::umma_commit_2sm_mc_elect(&bars->empty[stage], 0b11);
+          if (kb == KB - 1) ptx::umma_commit_2sm_mc_elect(&bars->tfull[as], 0b11);
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: thread = row
+    constexpr int HALF = BN / 2;          // columns per warp
+    constexpr int CHUNKS = HALF / 32;
+    const int q = warp & 3;               // TMEM lane quadrant
+    const int col_half = warp >> 2;
+    const int et = threadIdx.x;           // 0..255
+    const float inv_act = 1.f / p.act_scale;
+    uint8_t* scratch = scratch_s + warp * EPI_SCRATCH_BYTES;
+    int as = 0;
+    uint32_t aphase = 0;
+    float amax = 0.f;
+    for (int u = unit0; u < n_units; u += unit_step) {
+      const int n_tile = u % p.n_ntiles;
+      const long long row = static_cast<long long>((u / p.n_ntiles) * 2 + static_cast<int>(rank)) * BM + q * 32 + lane;
+      const bool valid = row < p.M;
+      const long long row0w = row - lane;                  // first row of this warp's 32
+      float* addv = addv_s + as * 256;
+      if (et < BN) addv[et] = __ldg(p.bias + n_tile * BN + et);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      ptx::mbar_wait(&bars->tfull[as], aphase);
+      ptx::tc_fence_after_sync();
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * HALF;
+#pragma unroll 1
+      for (int ch = 0; ch < CHUNKS; ++ch) {
+        float v[32];
+        ptx::tmem_ld_32x32b_x32(trow + ch * 32, v);
+        ptx::tmem_ld_wait();
+        if (ch == CHUNKS - 1) {
+          ptx::tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) {
+            if (leader) ptx::mbar_arrive(&bars->tempty[as]);
+            else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tempty[as]), 0));
+          }
+        }
+        const int ct = col_half * HALF + ch * 32;          // column within the tile
+        const int cg = n_tile * BN + ct;                   // output channel
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = v[c] * p.acc_scale_inv + addv[ct + c];
+        // global accesses go through the warp transposes of epilogue.cuh: 8 rows x 64 B per instruction
+        const long long rows_valid = p.M - row0w;          // rows of this warp's 32 that exist
+        if (p.res_hl) {   // identity branch of the bottleneck (models/resnet.py:93-94), stored as its own hi/lo operand
+          uint4 rh[4], rl[4];
+          warp_load_rows_64B(scratch, rh, p.res_hl + row0w * p.out_ld + cg, p.out_ld, rows_valid, lane);
+          warp_load_rows_64B(scratch, rl, p.res_hl + row0w * p.out_ld + p.Cout + cg, p.out_ld, rows_valid, lane);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const __half2* ah = reinterpret_cast<const __half2*>(&rh[g]);
+            const __half2* bh = reinterpret_cast<const __half2*>(&rl[g]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 fa = __half22float2(ah[e]), fb = __half22float2(bh[e]);
+              v[g * 8 + 2 * e] += (fa.x + fb.x) * inv_act;
+              v[g * 8 + 2 * e + 1] += (fa.y + fb.y) * inv_act;
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+        }
+        if (p.out_f32 && valid) {
+          float4* o = reinterpret_cast<float4*>(p.out_f32 + row * p.Cout + cg);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+        if (p.out_hl) {
+          __align__(16) __half2 hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            const float s0 = v[2 * c] * p.act_scale, s1 = v[2 * c + 1] * p.act_scale;
+            hi[c] = __floats2half2_rn(s0, s1);
+            lo[c] = __floats2half2_rn(s0 - __low2float(hi[c]), s1 - __high2float(hi[c]));
+            if (valid) amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
+          }
+          warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(hi), p.out_hl + row0w * p.out_ld + cg, p.out_ld,
+                              rows_valid, lane);
+          warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(lo), p.out_hl + row0w * p.out_ld + p.Cout + cg,
+                              p.out_ld, rows_valid, lane);
+        }
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == TMA_WARP) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN>
+cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
+                      cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int units = (p.n_mtiles / 2) * p.n_ntiles;
+  if (units == 0) return cudaSuccess;
+  const int grid = units * 2 < num_sms ? units * 2 : (num_sms / 2) * 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN>, tmA, tmB, p);
+}
+
+}  // namespace
+
+int conv_gemm_tile_n(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
+
+cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
+                             cudaStream_t stream) {
+  if (p.K <= 0 || p.K % BK || p.n_mtiles % 2 || p.Cout % 64) return cudaErrorInvalidValue;
+  const int bn = conv_gemm_tile_n(p.Cout);
+  if (p.n_ntiles * bn != p.Cout) return cudaErrorInvalidValue;
+  if (bn == 256) return launch_bn<256>(tmA, tmB, p, num_sms, stream);
+  if (bn == 128) return launch_bn<128>(tmA, tmB, p, num_sms, stream);
+  return launch_bn<64>(tmA, tmB, p, num_sms, stream);
+}
+
+}  // namespace ehb

@@ -188,6 +188,36 @@ cudaError_t launch_pointnet_pos(const float* pts, const float* w, const float* b
 cudaError_t launch_pool_init(int* pool, int n, cudaStream_t stream);
 cudaError_t launch_pool_decode(const int* pool, float* out, int n, cudaStream_t stream);
 
+// ---- ResNet-50 convolutions as GEMMs (conv_umma.cu) and their data movers (resnet_ops.cu)
+struct ConvGemmParams {
+  const float* bias;      // [Cout] folded BatchNorm shift
+  const __half* res_hl;   // identity branch, same layout as out_hl, or null
+  __half* out_hl;         // [M_pad][hi(Cout) | lo(Cout)] of act_scale * Y, or null
+  float* out_f32;         // [M][Cout] or null
+  int* overflow_flag;
+  long long M;            // valid rows (image pixels)
+  float acc_scale_inv;    // 1 / (act_scale * w_scale)
+  float act_scale;
+  int K;                  // kh*kw*Cin padded to a multiple of 64
+  int Cout, out_ld;       // out_ld = 2 * Cout (halves per row)
+  int n_mtiles, n_ntiles; // 128-row tiles (even) and Cout / tile_n
+  int relu;
+};
+int conv_gemm_tile_n(int cout);   // 256, 128 or 64 output channels per tile
+cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
+                             cudaStream_t stream);
+// im2col of an NHWC fp16 hi/lo activation [N][H][W][hi(C) | lo(C)] for a KHxKW / stride / pad convolution:
+// dst [N*Ho*Wo][hi(KH*KW*C) | lo(KH*KW*C)], k = (ky*KW + kx)*C + c, zero outside the image.  C % 8 == 0.
+cudaError_t launch_im2col_hl(const __half* src, __half* dst, int N, int H, int W, int C, int KH, int KW, int stride,
+                             int pad, int Ho, int Wo, cudaStream_t stream);
+// the stem's im2col straight from the fp32 NCHW image: dst [N*Ho*Wo][hi(Kp) | lo(Kp)], k = (ky*7 + kx)*3 + c < 147
+cudaError_t launch_im2col_stem(const float* img, __half* dst, int N, int H, int W, int Ho, int Wo, int Kp, float act_scale,
+                               cudaStream_t stream);
+// MaxPool2d(3, 2, 1) on an NHWC hi/lo activation (the pair with the largest hi + lo wins; exact in fp32)
+cudaError_t launch_maxpool_hl(const __half* src, __half* dst, int N, int H, int W, int C, cudaStream_t stream);
+// global average pool: [N][HW][hi(C) | lo(C)] -> fp32 [N][C]
+cudaError_t launch_avgpool_hl(const __half* src, float* dst, int N, int HW, int C, float act_scale, cudaStream_t stream);
+
 // ---- image ops (image_ops.cu): MaxPool2d(3, 2, 1) on NHWC fp32, C % 4 == 0; out is [N][(H+1)/2][(W+1)/2][C]
 cudaError_t launch_maxpool3x3s2_nhwc(const float* in, float* out, int N, int H, int W, int C, cudaStream_t stream);
 

@@ -5,6 +5,7 @@
 // Same fp16x3 error-compensated scheme, CTA pairs (cta_group::2) and TMA/mbarrier pipeline as gcn_umma.cu; two operand
 // pairs may accumulate into one TMEM accumulator, which is how a ResnetBlockFC's `shortcut(x) + fc_1(relu(h))` becomes
 // ONE launch with no fp32 round trip.  Step-invariant: runs once per image batch.
+#include "epilogue.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -21,7 +22,7 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KiB
 constexpr int STAGES = 3;
 constexpr int BAR_BYTES = 256;
 constexpr int ADDV_BYTES = 2 * 256 * 4;   // per-tile additive row (bias + per-cloud row), double-buffered
-constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES;
+constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES + 8 * EPI_SCRATCH_BYTES;
 constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant: warp w and w+4 split the 256 columns
 constexpr int TMA_WARP = 8, MMA_WARP = 9;
 constexpr int NUM_THREADS = 10 * 32;
@@ -159,6 +160,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     const int q = warp & 3;             // TMEM lane quadrant
     const int col_half = warp >> 2;     // columns [128*col_half, +128)
     const int et = threadIdx.x;         // 0..255 within the epilogue warps
+    uint8_t* scratch = smem + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES + warp * EPI_SCRATCH_BYTES;
     int as = 0;
     uint32_t aphase = 0;
     float amax = 0.f;
@@ -210,8 +212,10 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
-        if (valid && (p.out_hl || p.out_hl_relu)) {
-          // 32 consecutive channels of this row: 64 B of hi and 64 B of lo per destination
+        if (p.out_hl || p.out_hl_relu) {
+          // 32 consecutive channels of every row: 64 B of hi and 64 B of lo per destination, written through the warp
+          // transposes of epilogue.cuh (8 rows x 64 B per store instruction instead of 32 rows x 16 B)
+          const long long rows_valid = p.M - row_first;
           __align__(16) __half2 hi[16], lo[16];
           if (p.out_hl) {
 #pragma unroll
@@ -219,15 +223,12 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
               const float s0 = v[2 * c] * p.act_scale, s1 = v[2 * c + 1] * p.act_scale;
               hi[c] = __floats2half2_rn(s0, s1);
               lo[c] = __floats2half2_rn(s0 - __low2float(hi[c]), s1 - __high2float(hi[c]));
-              amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
+              if (valid) amax = fmaxf(amax, fmaxf(fabsf(s0), fabsf(s1)));
             }
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hl + row * (2 * BN) + c0);
-            uint4* dl = reinterpret_cast<uint4*>(p.out_hl + row * (2 * BN) + BN + c0);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              dh[c] = reinterpret_cast<const uint4*>(hi)[c];
-              dl[c] = reinterpret_cast<const uint4*>(lo)[c];
-            }
+            warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(hi), p.out_hl + row_first * (2 * BN) + c0,
+                                2 * BN, rows_valid, lane);
+            warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(lo), p.out_hl + row_first * (2 * BN) + BN + c0,
+                                2 * BN, rows_valid, lane);
             if (p.out_hl_relu) {
               // relu(y) splits into the same (hi, lo) when y > 0 and into (0, 0) otherwise: mask the packed halves
               const __half2 zero = __float2half2_rn(0.f);
@@ -237,13 +238,10 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
                 hi[c] = __hmul2(hi[c], pos);
                 lo[c] = __hmul2(lo[c], pos);
               }
-              uint4* rh = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + c0);
-              uint4* rl = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + BN + c0);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                rh[c] = reinterpret_cast<const uint4*>(hi)[c];
-                rl[c] = reinterpret_cast<const uint4*>(lo)[c];
-              }
+              warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(hi), p.out_hl_relu + row_first * (2 * BN) + c0,
+                                  2 * BN, rows_valid, lane);
+              warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(lo),
+                                  p.out_hl_relu + row_first * (2 * BN) + BN + c0, 2 * BN, rows_valid, lane);
             }
           } else {
 #pragma unroll
@@ -251,15 +249,12 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
               const float s0 = fmaxf(v[2 * c], 0.f) * p.act_scale, s1 = fmaxf(v[2 * c + 1], 0.f) * p.act_scale;
               hi[c] = __floats2half2_rn(s0, s1);
               lo[c] = __floats2half2_rn(s0 - __low2float(hi[c]), s1 - __high2float(hi[c]));
-              amax = fmaxf(amax, fmaxf(s0, s1));
+              if (valid) amax = fmaxf(amax, fmaxf(s0, s1));
             }
-            uint4* dh = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + c0);
-            uint4* dl = reinterpret_cast<uint4*>(p.out_hl_relu + row * (2 * BN) + BN + c0);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              dh[c] = reinterpret_cast<const uint4*>(hi)[c];
-              dl[c] = reinterpret_cast<const uint4*>(lo)[c];
-            }
+            warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(hi), p.out_hl_relu + row_first * (2 * BN) + c0,
+                                2 * BN, rows_valid, lane);
+            warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(lo),
+                                p.out_hl_relu + row_first * (2 * BN) + BN + c0, 2 * BN, rows_valid, lane);
           }
         }
         if (p.pool) {

@@ -139,6 +139,54 @@ class Engine:
         check(self.lib.ehb_smpl_load(self._h, C.byref(m)))
         self.n_verts, self.n_extra, self.n_betas, self.smpl_loaded = m.n_verts, m.n_extra, m.n_betas, True
 
+    def load_resnet(self, sd, prefix="backbone", blocks=(3, 4, 6, 3), bn_eps=1e-5):
+        """ResNet-50 parameters by their reference names (models/resnet.py:100-150) -> tcgen05 convolution GEMMs."""
+        keep, convs = [], []
+
+        def arr(name):
+            v = sd[f"{prefix}.{name}"]
+            if isinstance(v, torch.Tensor):
+                v = v.detach().cpu().numpy()
+            a = f32(v)
+            keep.append(a)
+            return a
+
+        def conv(cname, bname, stride, pad):
+            w = arr(cname + ".weight")
+            c = _lib.ConvBN()
+            c.cout, c.cin, c.kh, c.kw = (int(x) for x in w.shape)
+            c.stride, c.pad = stride, pad
+            c.weight = fptr(w)
+            c.bn_weight, c.bn_bias = fptr(arr(bname + ".weight")), fptr(arr(bname + ".bias"))
+            c.bn_mean, c.bn_var = fptr(arr(bname + ".running_mean")), fptr(arr(bname + ".running_var"))
+            c.bn_eps = bn_eps
+            convs.append(c)
+
+        conv("conv1", "bn1", 2, 3)
+        for li, nb in enumerate(blocks, start=1):
+            for bi in range(nb):
+                p = f"layer{li}.{bi}"
+                s = (1 if li == 1 else 2) if bi == 0 else 1
+                conv(p + ".conv1", p + ".bn1", 1, 0)
+                conv(p + ".conv2", p + ".bn2", s, 1)
+                conv(p + ".conv3", p + ".bn3", 1, 0)
+                if bi == 0:
+                    conv(p + ".downsample.0", p + ".downsample.1", s, 0)
+        w = _lib.ResnetWeights()
+        arr_t = (_lib.ConvBN * len(convs))(*convs)
+        w.convs, w.n_convs = arr_t, len(convs)
+        for i, nb in enumerate(blocks):
+            w.blocks[i] = nb
+        check(self.lib.ehb_resnet_load(self._h, C.byref(w)))
+        self.resnet_out = int(convs[-1].cout)
+
+    def resnet_forward(self, img):
+        """backbone(img): [n,3,H,W] fp32 NCHW -> [n, 2048] (K9, tcgen05 convolution GEMMs, fp32-class)."""
+        n, _, h, w = img.shape
+        out = torch.empty(n, self.resnet_out, device=img.device, dtype=torch.float32)
+        check(self.lib.ehb_resnet_forward(self._h, _dev_ptr(img), n, h, w, _dev_ptr(out), _stream()))
+        return out
+
     def load_pointnet(self, sd, prefix="scene_enc", hidden=256):
         """ResnetPointnet parameters by their reference names (models/respointnet.py:13-27)."""
         keep = []

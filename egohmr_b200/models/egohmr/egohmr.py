@@ -191,6 +191,7 @@ class EgoHMR(nn.Module):
         self._bodies_idx = None
         self._op2smpl_idx = None
         self._default_center = None
+        self.native_image_enc = False  # ResNet-50 on the tcgen05 convolution GEMMs (K9, fp32-class); False = cuDNN
         self.native_scene_enc = True   # ResPointNet on the tcgen05 linear kernel (K7); False = PyTorch/cuBLAS form
 
     # ------------------------------------------------------------------ weight ingestion
@@ -225,6 +226,8 @@ class EgoHMR(nn.Module):
         self._fast_backbone = FoldedResNet50(self.backbone, self.engine)
         self._fast_scene_enc = SplitPointNet(self.scene_enc)   # PyTorch form (kept for comparison / odd shapes)
         self.engine.load_pointnet({k: v for k, v in self.state_dict().items() if k.startswith("scene_enc.")})
+        self.engine.load_resnet({k: v for k, v in self.state_dict().items() if k.startswith("backbone.")},
+                                bn_eps=self.backbone.bn1.eps)
         self._weights_dirty = False
         self._cond_key = None
         self._temb_key = None
@@ -272,7 +275,8 @@ class EgoHMR(nn.Module):
         vis = vis_op.index_select(1, self._op2smpl_idx)   # device-resident index: no per-call upload, graph-capturable
         pts = batch["scene_pcd_verts_full"] - transl.unsqueeze(1) if self.scene_cano else batch["scene_pcd_verts_full"]
         if features is None:
-            img_feats = self._fast_backbone(batch["img"])
+            img_feats = (self.engine.resnet_forward(batch["img"].float().contiguous()) if self.native_image_enc
+                         else self._fast_backbone(batch["img"]))
             scene_feats = (self.engine.pointnet_forward(pts.float().contiguous()) if self.native_scene_enc
                            else self._fast_scene_enc(pts))
             transl_feat = self.transl_enc(transl)

@@ -201,6 +201,29 @@ int ehb_scene_crop(ehb_ctx* ctx, const float* verts, int n_bodies, int n_verts, 
 int ehb_procrustes_align(ehb_ctx* ctx, const float* s1, const float* s2, const float* mask, int n_problems, int n_points,
                          float* s1_hat, float* err, void* stream);
 
+/* ResNet-50 image encoder (models/resnet.py:100-150: torchvision-style v1.5 bottlenecks, global average pool, no fc),
+ * one entry per convolution with the BatchNorm2d that follows it, in network order: the stem, then for every
+ * bottleneck conv1, conv2, conv3 and — in the first block of a stage — downsample.  HOST. */
+typedef struct {
+  int32_t cout, cin, kh, kw, stride, pad;
+  const float* weight;     /* [cout][cin][kh][kw]  "...convN.weight" / "...downsample.0.weight" */
+  const float* bn_weight;  /* [cout]  "...bnN.*" / "...downsample.1.*" */
+  const float* bn_bias;
+  const float* bn_mean;
+  const float* bn_var;
+  float bn_eps;
+} ehb_conv_bn;
+typedef struct {
+  const ehb_conv_bn* convs;
+  int32_t n_convs;         /* 1 + sum_b (3 + (b is the first block of its stage)) = 53 for ResNet-50 */
+  int32_t blocks[4];       /* bottlenecks per stage: 3, 4, 6, 3 */
+} ehb_resnet_weights;
+int ehb_resnet_load(ehb_ctx* ctx, const ehb_resnet_weights* w);
+/* backbone(img) (egohmr.py:183): img [n][3][h][w] fp32 NCHW (ImageNet-normalised crops, 224 x 224) -> feats [n][2048].
+ * Every convolution is a tcgen05 GEMM with fp32-class accuracy (fp16 hi/lo operands, fp32 accumulate); BatchNorm is
+ * folded, ReLU / residual adds are fused into the GEMM epilogues. */
+int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, float* feats, void* stream);
+
 /* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
  * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);

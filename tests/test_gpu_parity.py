@@ -308,6 +308,27 @@ def test_bench_precision_configuration_tf32_convs(full, golden_dir):
     assert d_ours < max(4 * d_ref, 1e-5) and v_ours < max(4 * v_ref, 0.05)
 
 
+def test_native_resnet50_vs_module_and_float64(full):
+    """K9: ResNet-50 as tcgen05 convolution GEMMs (fp16 hi/lo operands, fp32 accumulate, BN folded, im2col for 3x3 /
+    strided / stem) against the plain nn.Module in strict fp32 and in float64 (TF32 is off in this module)."""
+    model = full[0]
+    model._sync_engine()
+    for n_img in (3, 1):
+        img = _tb(synth.make_batch(4, n_img))["img"]
+        with torch.no_grad():
+            ref32 = model.backbone(img)
+            ref64 = model.backbone.double()(img.double())
+            model.backbone.float()
+            got = model.engine.resnet_forward(img.contiguous())
+        assert not model.engine.check_overflow()
+        scale = ref64.abs().max().item()
+        d_native = (got.double() - ref64).abs().max().item()
+        d_fp32 = (ref32.double() - ref64).abs().max().item()
+        print(f"native ResNet-50 ({n_img} img): max|native - f64| = {d_native:.3e}, torch fp32 - f64 = {d_fp32:.3e} "
+              f"(max|feat| = {scale:.3f})")
+        assert d_native < 2e-5 * max(1.0, scale)
+
+
 def test_maxpool_nhwc_bit_exact(full):
     """The ResNet stem's MaxPool2d(3, 2, 1) on the library's NHWC kernel equals torch's, including odd sizes."""
     eng = full[0].engine
