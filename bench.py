@@ -286,14 +286,16 @@ def run_b200(args):
     clk = clocks.stop()
     launches = launches_per_pass * args.steps
     eager_ms = timed_steps(eager_step, args.steps) if sampler is not None else ms
-    # the same pass with cuDNN's TF32 convolutions switched off (strict fp32 ResNet-50), for transparency
-    tf32_was = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
+    # the same pass with the image encoder on cuDNN instead of the native tcgen05 convolution GEMMs, at torch's default
+    # conv precision (TF32 allowed: what the reference's own CUDA path runs) — a library baseline for that stage
+    model.native_image_enc = False
     try:
         eager_step(batch_dev)
-        strict_ms = timed_steps(eager_step, max(3, args.steps // 4)) / max(3, args.steps // 4) * args.steps
+        n_alt = max(3, args.steps // 4)
+        cudnn_ms = timed_steps(eager_step, n_alt) / n_alt * args.steps
     finally:
-        torch.backends.cudnn.allow_tf32 = tf32_was
+        model.native_image_enc = True
+        model._cond_key = None
 
     # ---- end-to-end leg: host (pinned) inputs -> public API -> host results, copies inside the timed region
     res_host = {"R": torch.empty(B, 24, 3, 3).pin_memory(), "betas": torch.empty(B, 10).pin_memory(),
@@ -409,9 +411,9 @@ def run_b200(args):
 
     # max over ranks of the device time
     if world > 1:
-        t = torch.tensor([ms, e2e_s, eager_ms, strict_ms], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, e2e_s, eager_ms, cudnn_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s, eager_ms, strict_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
+        ms, e2e_s, eager_ms, cudnn_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -429,10 +431,10 @@ def run_b200(args):
                    "execution": ("whole pass replayed as ONE CUDA graph (diffusion/graphed.py)" if sampler is not None
                                  else "eager: every launch issued from Python"),
                    "eager_value": total_bodies / (eager_ms * 1e-3),
-                   "eager_value_strict_fp32_convs": total_bodies / (strict_ms * 1e-3),
-                   "encoders": "once per pass: ResPointNet on the tcgen05 linear kernel (fp16x3, fp32-class); ResNet-50 on "
-                               "cuDNN in inference form with torch's default conv precision (TF32 allowed, exactly what the "
-                               "reference's own CUDA path runs; the -m gpu parity tests switch TF32 off)",
+                   "eager_value_with_cudnn_tf32_image_encoder": total_bodies / (cudnn_ms * 1e-3),
+                   "encoders": "once per pass, both native: ResNet-50 as tcgen05 convolution GEMMs (K9) and ResPointNet on the "
+                               "tcgen05 linear kernel (K7), fp16x3 error-compensated = fp32-class; no cuDNN / cuBLAS on the "
+                               "path (the cuDNN TF32 encoder is timed as eager_value_with_cudnn_tf32_image_encoder)",
                    "stage_ms": {"encoders_once_per_pass": enc_ms, "gcn_input_per_step": k2_ms,
                                 "gcn_hidden_layers_per_step": float(np.sum(layer_ms)), "gcn_output_per_step": k3_ms,
                                 "decode_once_per_pass": dec_ms}},

@@ -1205,7 +1205,7 @@ static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, lo
                    int relu, cudaStream_t stream) {
   const int n_mtiles = static_cast<int>((rows + 255) / 256) * 2;
   const size_t rows_pad = static_cast<size_t>(n_mtiles) * 128;
-  const int bn = ehb::conv_gemm_tile_n(c.cout);
+  const int bn = ehb::conv_gemm_tile_n(c.cout, rows, ctx->num_sms);
   CUtensorMap tA, tB;
   if (make_tmap_f16(&tA, A, rows_pad, 2 * static_cast<uint64_t>(c.Kp), 128)) return 1;
   if (make_tmap_f16(&tB, c.w_hl.p, c.cout, 2 * static_cast<uint64_t>(c.Kp), bn / 2)) return 1;

@@ -173,6 +173,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       float* addv = addv_s + as * 256;
       if (et < BN) addv[et] = __ldg(p.bias + n_tile * BN + et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      // the identity block of the first chunk is requested before the accumulator is awaited, every further chunk's
+      // while the previous one is processed: its global latency never sits on the epilogue's critical path
+      const long long rows_valid = p.M - row0w;            // rows of this warp's 32 that exist
+      uint4 raw_h[4], raw_l[4];
+      if (p.res_hl) {
+        const int cg0 = n_tile * BN + col_half * HALF;
+        warp_issue_rows_64B(raw_h, p.res_hl + row0w * p.out_ld + cg0, p.out_ld, rows_valid, lane);
+        warp_issue_rows_64B(raw_l, p.res_hl + row0w * p.out_ld + p.Cout + cg0, p.out_ld, rows_valid, lane);
+      }
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after_sync();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * HALF;
@@ -194,11 +203,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] = v[c] * p.acc_scale_inv + addv[ct + c];
         // global accesses go through the warp transposes of epilogue.cuh: 8 rows x 64 B per instruction
-        const long long rows_valid = p.M - row0w;          // rows of this warp's 32 that exist
         if (p.res_hl) {   // identity branch of the bottleneck (models/resnet.py:93-94), stored as its own hi/lo operand
           uint4 rh[4], rl[4];
-          warp_load_rows_64B(scratch, rh, p.res_hl + row0w * p.out_ld + cg, p.out_ld, rows_valid, lane);
-          warp_load_rows_64B(scratch, rl, p.res_hl + row0w * p.out_ld + p.Cout + cg, p.out_ld, rows_valid, lane);
+          warp_finish_rows_64B(scratch, raw_h, rh, lane);
+          warp_finish_rows_64B(scratch, raw_l, rl, lane);
+          if (ch + 1 < CHUNKS) {
+            warp_issue_rows_64B(raw_h, p.res_hl + row0w * p.out_ld + cg + 32, p.out_ld, rows_valid, lane);
+            warp_issue_rows_64B(raw_l, p.res_hl + row0w * p.out_ld + p.Cout + cg + 32, p.out_ld, rows_valid, lane);
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const __half2* ah = reinterpret_cast<const __half2*>(&rh[g]);
@@ -281,13 +293,22 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
 
 }  // namespace
 
-int conv_gemm_tile_n(int cout) { return cout % 256 == 0 ? 256 : (cout % 128 == 0 ? 128 : 64); }
+// Largest N tile (256 / 128 / 64) that divides Cout AND still gives every CTA pair a work unit; small-M layers (the
+// 7 x 7 stage) trade MMA width for parallelism.
+int conv_gemm_tile_n(int cout, long long rows, int num_sms) {
+  const long long m_units = (rows + 255) / 256;
+  const int pairs = num_sms / 2;
+  for (int bn : {256, 128}) {
+    if (cout % bn == 0 && m_units * (cout / bn) >= pairs) return bn;
+  }
+  return cout % 64 == 0 ? 64 : 0;
+}
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
                              cudaStream_t stream) {
-  if (p.K <= 0 || p.K % BK || p.n_mtiles % 2 || p.Cout % 64) return cudaErrorInvalidValue;
-  const int bn = conv_gemm_tile_n(p.Cout);
-  if (p.n_ntiles * bn != p.Cout) return cudaErrorInvalidValue;
+  if (p.K <= 0 || p.K % BK || p.n_mtiles % 2 || p.Cout % 64 || p.n_ntiles <= 0 || p.Cout % p.n_ntiles) return cudaErrorInvalidValue;
+  const int bn = p.Cout / p.n_ntiles;
+  if (bn != 256 && bn != 128 && bn != 64) return cudaErrorInvalidValue;
   if (bn == 256) return launch_bn<256>(tmA, tmB, p, num_sms, stream);
   if (bn == 128) return launch_bn<128>(tmA, tmB, p, num_sms, stream);
   return launch_bn<64>(tmA, tmB, p, num_sms, stream);

@@ -50,4 +50,30 @@ __device__ __forceinline__ void warp_load_rows_64B(uint8_t* scratch, uint4 (&min
   __syncwarp();
 }
 
+// Split version of the load for software pipelining: `issue` starts the coalesced global loads of a hi block and a lo
+// block (8 loads in flight, results in registers), `finish` transposes them through the scratch into per-row data.
+__device__ __forceinline__ void warp_issue_rows_64B(uint4 (&raw)[4], const __half* gbase, size_t ld, long long rows_valid,
+                                                    int lane) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    raw[i] = r < rows_valid ? __ldg(reinterpret_cast<const uint4*>(gbase + static_cast<size_t>(r) * ld + piece * 8))
+                            : make_uint4(0, 0, 0, 0);
+  }
+}
+__device__ __forceinline__ void warp_finish_rows_64B(uint8_t* scratch, const uint4 (&raw)[4], uint4 (&mine)[4], int lane) {
+  const int piece = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i * 8 + (lane >> 2);
+    *reinterpret_cast<uint4*>(scratch + r * EPI_PITCH + piece * 16) = raw[i];
+  }
+  __syncwarp();
+  const uint4* srow = reinterpret_cast<const uint4*>(scratch + lane * EPI_PITCH);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) mine[j] = srow[j];
+  __syncwarp();
+}
+
 }  // namespace ehb

@@ -203,7 +203,7 @@ struct ConvGemmParams {
   int n_mtiles, n_ntiles; // 128-row tiles (even) and Cout / tile_n
   int relu;
 };
-int conv_gemm_tile_n(int cout);   // 256, 128 or 64 output channels per tile
+int conv_gemm_tile_n(int cout, long long rows, int num_sms);   // 256, 128 or 64 output channels per tile
 cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
                              cudaStream_t stream);
 // im2col of an NHWC fp16 hi/lo activation [N][H][W][hi(C) | lo(C)] for a KHxKW / stride / pad convolution:

@@ -33,34 +33,45 @@ __global__ void __launch_bounds__(256) im2col_hl_kernel(const uint4* __restrict_
   dst[dp + K8] = lo;
 }
 
-// thread = 8 consecutive k of one output pixel of the 7x7 / stride 2 / pad 3 stem (models/resnet.py:109-110)
+// The 7x7 / stride 2 / pad 3 stem (models/resnet.py:109-110).  Block = 32 consecutive output pixels of one output row:
+// the 7 x 69 x 3 input patch they share is staged in shared memory with coalesced reads (each input value is used by
+// up to 4 x 7 outputs), then every thread emits 8 consecutive k of one pixel, so the 384-byte hi / lo row segments of a
+// pixel are written by 24 consecutive threads.
+constexpr int STEM_TW = 32;
+constexpr int STEM_PW = 2 * STEM_TW + 5;   // 69 input columns
 __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, uint4* __restrict__ dst, int N, int H,
                                                           int W, int Ho, int Wo, int Kp8, float act_scale) {
-  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const size_t total = static_cast<size_t>(N) * Ho * Wo * Kp8;
-  if (i >= total) return;
-  const int kg = static_cast<int>(i % Kp8);
-  const size_t r = i / Kp8;
-  const int wo = static_cast<int>(r % Wo);
-  const int ho = static_cast<int>((r / Wo) % Ho);
-  const int n = static_cast<int>(r / (static_cast<size_t>(Wo) * Ho));
-  __align__(16) __half hi[8], lo[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = kg * 8 + e;
-    float v = 0.f;
-    if (k < 147) {
-      const int tap = k / 3, c = k % 3;
-      const int y = ho * 2 - 3 + tap / 7, x = wo * 2 - 3 + tap % 7;
-      if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + ((static_cast<size_t>(n) * 3 + c) * H + y) * W + x);
-    }
-    const float sv = v * act_scale;
-    hi[e] = __float2half_rn(sv);
-    lo[e] = __float2half_rn(sv - __half2float(hi[e]));
+  __shared__ float patch[3][7][STEM_PW + 1];
+  const int wo0 = blockIdx.x * STEM_TW, ho = blockIdx.y, n = blockIdx.z;
+  const int y0 = ho * 2 - 3, x0 = wo0 * 2 - 3;
+  for (int e = threadIdx.x; e < 3 * 7 * STEM_PW; e += blockDim.x) {
+    const int px = e % STEM_PW, py = (e / STEM_PW) % 7, c = e / (STEM_PW * 7);
+    const int y = y0 + py, x = x0 + px;
+    patch[c][py][px] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + ((static_cast<size_t>(n) * 3 + c) * H + y) * W + x) : 0.f;
   }
-  const size_t dp = r * (2 * static_cast<size_t>(Kp8)) + kg;
-  dst[dp] = *reinterpret_cast<const uint4*>(hi);
-  dst[dp + Kp8] = *reinterpret_cast<const uint4*>(lo);
+  __syncthreads();
+  for (int item = threadIdx.x; item < STEM_TW * Kp8; item += blockDim.x) {
+    const int kg = item % Kp8, pw = item / Kp8;
+    const int wo = wo0 + pw;
+    if (wo >= Wo) continue;
+    __align__(16) __half hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kg * 8 + e;
+      float v = 0.f;
+      if (k < 147) {
+        const int tap = k / 3, c = k % 3;
+        v = patch[c][tap / 7][pw * 2 + tap % 7];
+      }
+      const float sv = v * act_scale;
+      hi[e] = __float2half_rn(sv);
+      lo[e] = __float2half_rn(sv - __half2float(hi[e]));
+    }
+    const size_t r = (static_cast<size_t>(n) * Ho + ho) * Wo + wo;
+    const size_t dp = r * (2 * static_cast<size_t>(Kp8)) + kg;
+    dst[dp] = *reinterpret_cast<const uint4*>(hi);
+    dst[dp + Kp8] = *reinterpret_cast<const uint4*>(lo);
+  }
 }
 
 // thread = 8 channels of one output pixel; the (hi, lo) pair with the largest value hi + lo wins (the sum of an fp16
@@ -139,10 +150,9 @@ cudaError_t launch_im2col_hl(const __half* src, __half* dst, int N, int H, int W
 
 cudaError_t launch_im2col_stem(const float* img, __half* dst, int N, int H, int W, int Ho, int Wo, int Kp, float act_scale,
                                cudaStream_t stream) {
-  const size_t total = static_cast<size_t>(N) * Ho * Wo * (Kp / 8);
-  if (total == 0) return cudaSuccess;
-  im2col_stem_kernel<<<blocks_for(total), 256, 0, stream>>>(img, reinterpret_cast<uint4*>(dst), N, H, W, Ho, Wo, Kp / 8,
-                                                            act_scale);
+  if (N <= 0 || Ho <= 0 || Wo <= 0) return cudaSuccess;
+  const dim3 grid((Wo + STEM_TW - 1) / STEM_TW, Ho, N);
+  im2col_stem_kernel<<<grid, 256, 0, stream>>>(img, reinterpret_cast<uint4*>(dst), N, H, W, Ho, Wo, Kp / 8, act_scale);
   return cudaGetLastError();
 }
 
