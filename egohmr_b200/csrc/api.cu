@@ -200,6 +200,7 @@ struct ehb_ctx {
     int cout = 0, cin = 0, kh = 0, kw = 0, stride = 1, pad = 0, Kp = 0;
     float w_scale = 1.f;
     DevBuf w_hl, bias;
+    std::vector<float> wf, bias_h;   // folded fp32 weights / bias (kept on the host until the scales are final)
   };
   std::vector<ConvPlan*> rn_convs;
   int rn_blocks[4] = {0, 0, 0, 0};
@@ -1190,10 +1191,32 @@ int ehb_resnet_load(ehb_ctx* ctx, const ehb_resnet_weights* w) {
     }
     if (!std::isfinite(maxabs)) return fail("ehb_resnet_load: non-finite weight");
     pl->w_scale = pow2_scale(maxabs);
+    pl->wf.swap(wf);
+    pl->bias_h.swap(bias);
+  }
+  // conv3 and the projection shortcut of a stage's first block accumulate into one TMEM accumulator: one operand scale
+  // for both, one summed bias (the projection's own bias buffer is unused)
+  {
+    int ci = 1;
+    for (int s = 0; s < 4; ++s)
+      for (int b = 0; b < w->blocks[s]; ++b) {
+        if (b == 0) {
+          auto& c3 = *ctx->rn_convs[ci + 2];
+          auto& cd = *ctx->rn_convs[ci + 3];
+          if (c3.cout != cd.cout) return fail("ehb_resnet_load: downsample / conv3 channel mismatch");
+          const float sc = std::min(c3.w_scale, cd.w_scale);
+          c3.w_scale = cd.w_scale = sc;
+          for (int co = 0; co < c3.cout; ++co) c3.bias_h[co] += cd.bias_h[co];
+        }
+        ci += b == 0 ? 4 : 3;
+      }
+  }
+  for (auto* pl : ctx->rn_convs) {
     std::vector<__half> hl;
-    split_hl(wf.data(), c.cout, pl->Kp, pl->Kp, 0, pl->w_scale, hl);
+    split_hl(pl->wf.data(), pl->cout, pl->Kp, pl->Kp, 0, pl->w_scale, hl);
     EHB_CUDA(pl->w_hl.upload(hl));
-    EHB_CUDA(pl->bias.upload(bias));
+    EHB_CUDA(pl->bias.upload(pl->bias_h));
+    std::vector<float>().swap(pl->wf);
   }
   for (int s = 0; s < 4; ++s) ctx->rn_blocks[s] = w->blocks[s];
   ctx->rn_loaded = true;
@@ -1202,13 +1225,18 @@ int ehb_resnet_load(ehb_ctx* ctx, const ehb_resnet_weights* w) {
 
 // one convolution as a GEMM: A [rows_pad][2*Kp] hi/lo (activation or im2col matrix) -> out [rows_pad][2*cout]
 static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, long long rows, const __half* res, __half* out,
-                   int relu, cudaStream_t stream) {
+                   int relu, cudaStream_t stream, const ehb_ctx::ConvPlan* c2 = nullptr, const __half* A2 = nullptr) {
   const int n_mtiles = static_cast<int>((rows + 255) / 256) * 2;
   const size_t rows_pad = static_cast<size_t>(n_mtiles) * 128;
   const int bn = ehb::conv_gemm_tile_n(c.cout, rows, ctx->num_sms);
   CUtensorMap tA, tB;
   if (make_tmap_f16(&tA, A, rows_pad, 2 * static_cast<uint64_t>(c.Kp), 128)) return 1;
   if (make_tmap_f16(&tB, c.w_hl.p, c.cout, 2 * static_cast<uint64_t>(c.Kp), bn / 2)) return 1;
+  CUtensorMap tA2 = tA, tB2 = tB;
+  if (c2) {
+    if (make_tmap_f16(&tA2, A2, rows_pad, 2 * static_cast<uint64_t>(c2->Kp), 128)) return 1;
+    if (make_tmap_f16(&tB2, c2->w_hl.p, c2->cout, 2 * static_cast<uint64_t>(c2->Kp), bn / 2)) return 1;
+  }
   ehb::ConvGemmParams p{};
   p.bias = c.bias.as<float>();
   p.res_hl = res;
@@ -1219,12 +1247,13 @@ static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, lo
   p.acc_scale_inv = 1.f / (ctx->act_scale * c.w_scale);
   p.act_scale = ctx->act_scale;
   p.K = c.Kp;
+  p.K2 = c2 ? c2->Kp : 0;
   p.Cout = c.cout;
   p.out_ld = 2 * c.cout;
   p.n_mtiles = n_mtiles;
   p.n_ntiles = c.cout / bn;
   p.relu = relu;
-  EHB_CUDA(ehb::launch_conv_gemm(tA, tB, p, ctx->num_sms, stream));
+  EHB_CUDA(ehb::launch_conv_gemm(tA, tB, tA2, tB2, p, ctx->num_sms, stream));
   ctx->launches += 1;
   return 0;
 }
@@ -1297,23 +1326,22 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
       EHB_CUDA(ehb::launch_im2col_hl(ctx->rn_y1.as<__half>(), col, n, H, W, c1.cout, 3, 3, c2.stride, 1, Ho, Wo, stream));
       if (rn_gemm(ctx, c2, col, rout, nullptr, ctx->rn_y2.as<__half>(), 1, stream)) return 1;
       ctx->launches += 1;
-      const __half* idt = x;
       if (b == 0) {
+        // relu(conv3(y2) + downsample(x)): both GEMMs accumulate into the same tile (models/resnet.py:90-96)
         const auto& cd = *cv[ci + 3];
         if (cd.kh != 1 || cd.cin != C || cd.cout != c3.cout || cd.stride != c2.stride)
           return fail("ehb_resnet_forward: unexpected downsample layout");
         const __half* a = x;
-        if (cd.stride != 1) {
+        if (cd.stride != 1) {   // strided 1x1: gather the kept pixels (the 3x3 im2col matrix in `col` has been consumed)
           EHB_CUDA(ehb::launch_im2col_hl(x, col, n, H, W, C, 1, 1, cd.stride, 0, Ho, Wo, stream));
           ctx->launches += 1;
           a = col;
         }
-        if (rn_gemm(ctx, cd, a, rout, nullptr, ctx->rn_idt.as<__half>(), 0, stream)) return 1;
-        idt = ctx->rn_idt.as<__half>();
-      } else if (c3.cout != C || c2.stride != 1) {
-        return fail("ehb_resnet_forward: identity shortcut with a shape change");
+        if (rn_gemm(ctx, c3, ctx->rn_y2.as<__half>(), rout, nullptr, xo, 1, stream, &cd, a)) return 1;
+      } else {
+        if (c3.cout != C || c2.stride != 1) return fail("ehb_resnet_forward: identity shortcut with a shape change");
+        if (rn_gemm(ctx, c3, ctx->rn_y2.as<__half>(), rout, x, xo, 1, stream)) return 1;
       }
-      if (rn_gemm(ctx, c3, ctx->rn_y2.as<__half>(), rout, idt, xo, 1, stream)) return 1;
       ci += b == 0 ? 4 : 3;
       cur ^= 1;
       H = Ho;
@@ -1322,6 +1350,32 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
     }
   EHB_CUDA(ehb::launch_avgpool_hl(ctx->rn_x[cur].as<__half>(), feats, n, H * W, C, ctx->act_scale, stream));
   ctx->launches += 1;
+  return 0;
+}
+
+__global__ void relu_inplace_kernel(float* x, size_t n) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = fmaxf(x[i], 0.f);
+}
+
+int ehb_linear_f32(ehb_ctx* ctx, const float* x, const float* w_t, const float* bias, int m, int n, int k, int relu,
+                   float* y, void* stream_) {
+  if (!ctx || !x || !w_t || !y) return fail("ehb_linear_f32: null argument");
+  if (m <= 0 || n <= 0 || k <= 0) return fail("ehb_linear_f32: sizes must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t tot = static_cast<size_t>(m) * n;
+  if (bias) {
+    fill_rows_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, stream>>>(y, bias, m, n);
+    EHB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  if (ctx_sgemm(ctx, x, w_t, y, m, n, k, k, n, n, bias ? 1 : 0, stream)) return 1;
+  if (relu) {
+    relu_inplace_kernel<<<static_cast<unsigned>((tot + 255) / 256), 256, 0, stream>>>(y, tot);
+    EHB_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+  }
   return 0;
 }
 

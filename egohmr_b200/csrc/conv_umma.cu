@@ -49,6 +49,7 @@ static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_BYTES = C::B_BYTES;
@@ -64,11 +65,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const bool leader = rank == 0;
   const int n_units = (p.n_mtiles / 2) * p.n_ntiles;
   const int unit0 = blockIdx.x / 2, unit_step = gridDim.x / 2;
-  const int KB = p.K / BK;
+  // two operand pairs may accumulate into one TMEM accumulator: conv3(y2) + downsample(x) of a stage's first bottleneck
+  // (models/resnet.py:90-94) is ONE launch, the projected identity never exists in memory
+  const int KB1 = p.K / BK, KB = KB1 + p.K2 / BK;
 
   if (warp == TMA_WARP && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (p.K2) {
+      ptx::prefetch_tensormap(&tmA2);
+      ptx::prefetch_tensormap(&tmB2);
+    }
   }
   if (warp == MMA_WARP && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -103,10 +110,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* s = smem + stage * STAGE_BYTES;
           const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
           if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
-          ptx::tma_load_2d_2sm(s, &tmA, lfull, kb * BK, m_row);
-          ptx::tma_load_2d_2sm(s + A_BYTES, &tmA, lfull, p.K + kb * BK, m_row);
-          ptx::tma_load_2d_2sm(s + 2 * A_BYTES, &tmB, lfull, kb * BK, b_row);
-          ptx::tma_load_2d_2sm(s + 2 * A_BYTES + B_BYTES, &tmB, lfull, p.K + kb * BK, b_row);
+          const bool second = kb >= KB1;
+          const CUtensorMap* ta = second ? &tmA2 : &tmA;
+          const CUtensorMap* tb = second ? &tmB2 : &tmB;
+          const int K = second ? p.K2 : p.K;
+          const int kk = (second ? kb - KB1 : kb) * BK;
+          ptx::tma_load_2d_2sm(s, ta, lfull, kk, m_row);
+          ptx::tma_load_2d_2sm(s + A_BYTES, ta, lfull, K + kk, m_row);
+          ptx::tma_load_2d_2sm(s + 2 * A_BYTES, tb, lfull, kk, b_row);
+          ptx::tma_load_2d_2sm(s + 2 * A_BYTES + B_BYTES, tb, lfull, K + kk, b_row);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -265,8 +277,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN>
-cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
-                      cudaStream_t stream) {
+cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                      const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
@@ -288,7 +300,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const Conv
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN>, tmA, tmB, p);
+  return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN>, tmA, tmB, tmA2, tmB2, p);
 }
 
 }  // namespace
@@ -304,14 +316,15 @@ int conv_gemm_tile_n(int cout, long long rows, int num_sms) {
   return cout % 64 == 0 ? 64 : 0;
 }
 
-cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
-                             cudaStream_t stream) {
-  if (p.K <= 0 || p.K % BK || p.n_mtiles % 2 || p.Cout % 64 || p.n_ntiles <= 0 || p.Cout % p.n_ntiles) return cudaErrorInvalidValue;
+cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                             const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  if (p.K <= 0 || p.K % BK || p.K2 < 0 || p.K2 % BK || p.n_mtiles % 2 || p.Cout % 64 || p.n_ntiles <= 0 || p.Cout % p.n_ntiles)
+    return cudaErrorInvalidValue;
   const int bn = p.Cout / p.n_ntiles;
   if (bn != 256 && bn != 128 && bn != 64) return cudaErrorInvalidValue;
-  if (bn == 256) return launch_bn<256>(tmA, tmB, p, num_sms, stream);
-  if (bn == 128) return launch_bn<128>(tmA, tmB, p, num_sms, stream);
-  return launch_bn<64>(tmA, tmB, p, num_sms, stream);
+  if (bn == 256) return launch_bn<256>(tmA, tmB, tmA2, tmB2, p, num_sms, stream);
+  if (bn == 128) return launch_bn<128>(tmA, tmB, tmA2, tmB2, p, num_sms, stream);
+  return launch_bn<64>(tmA, tmB, tmA2, tmB2, p, num_sms, stream);
 }
 
 }  // namespace ehb

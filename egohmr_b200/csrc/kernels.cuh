@@ -199,13 +199,14 @@ struct ConvGemmParams {
   float acc_scale_inv;    // 1 / (act_scale * w_scale)
   float act_scale;
   int K;                  // kh*kw*Cin padded to a multiple of 64
+  int K2;                 // K of an optional second operand pair accumulated into the same tile (0 = none)
   int Cout, out_ld;       // out_ld = 2 * Cout (halves per row)
   int n_mtiles, n_ntiles; // 128-row tiles (even) and Cout / tile_n
   int relu;
 };
 int conv_gemm_tile_n(int cout, long long rows, int num_sms);   // 256, 128 or 64 output channels per tile
-cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmParams& p, int num_sms,
-                             cudaStream_t stream);
+cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
+                             const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 // im2col of an NHWC fp16 hi/lo activation [N][H][W][hi(C) | lo(C)] for a KHxKW / stride / pad convolution:
 // dst [N*Ho*Wo][hi(KH*KW*C) | lo(KH*KW*C)], k = (ky*KW + kx)*C + c, zero outside the image.  C % 8 == 0.
 cudaError_t launch_im2col_hl(const __half* src, __half* dst, int N, int H, int W, int C, int KH, int KW, int stride,

@@ -42,6 +42,11 @@ constexpr int STEM_PW = 2 * STEM_TW + 5;   // 69 input columns
 __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, uint4* __restrict__ dst, int N, int H,
                                                           int W, int Ho, int Wo, int Kp8, float act_scale) {
   __shared__ float patch[3][7][STEM_PW + 1];
+  __shared__ int16_t koff[192];   // k -> offset of (c, ky, kx) inside `patch` (-1: K padding), instead of div/mod per element
+  for (int k = threadIdx.x; k < 192; k += blockDim.x) {
+    const int tap = k / 3, c = k % 3;
+    koff[k] = k < 147 ? static_cast<int16_t>((c * 7 + tap / 7) * (STEM_PW + 1) + tap % 7) : static_cast<int16_t>(-1);
+  }
   const int wo0 = blockIdx.x * STEM_TW, ho = blockIdx.y, n = blockIdx.z;
   const int y0 = ho * 2 - 3, x0 = wo0 * 2 - 3;
   for (int e = threadIdx.x; e < 3 * 7 * STEM_PW; e += blockDim.x) {
@@ -57,12 +62,8 @@ __global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restric
     __align__(16) __half hi[8], lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const int k = kg * 8 + e;
-      float v = 0.f;
-      if (k < 147) {
-        const int tap = k / 3, c = k % 3;
-        v = patch[c][tap / 7][pw * 2 + tap % 7];
-      }
+      const int off = koff[kg * 8 + e];
+      const float v = off >= 0 ? (&patch[0][0][0])[off + pw * 2] : 0.f;
       const float sv = v * act_scale;
       hi[e] = __float2half_rn(sv);
       lo[e] = __float2half_rn(sv - __half2float(hi[e]));

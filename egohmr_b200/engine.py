@@ -229,6 +229,15 @@ class Engine:
                                              _stream()))
         return out
 
+    def linear(self, x, w_t, bias=None, relu=False):
+        """nn.Linear(+ReLU) in the library's fp32 FFMA GEMM: x [M,K], w_t [K,N] (transposed weight) -> [M,N]."""
+        M, K = x.shape
+        N = w_t.shape[1]
+        y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        check(self.lib.ehb_linear_f32(self._h, _dev_ptr(x), _dev_ptr(w_t), _dev_ptr(bias, allow_none=True), M, N, K,
+                                      1 if relu else 0, _dev_ptr(y), _stream()))
+        return y
+
     def set_norm(self, mean, std):
         m, s = f32(mean).reshape(144), f32(std).reshape(144)
         check(self.lib.ehb_set_norm(self._h, fptr(m), fptr(s)))

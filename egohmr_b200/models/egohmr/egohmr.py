@@ -225,6 +225,10 @@ class EgoHMR(nn.Module):
                              torch.as_tensor(std).detach().float().cpu().numpy())
         self._fast_backbone = FoldedResNet50(self.backbone, self.engine)
         self._fast_scene_enc = SplitPointNet(self.scene_enc)   # PyTorch form (kept for comparison / odd shapes)
+        # the two small heads as (transposed weight, bias) pairs for the library's fp32 GEMM (no cuBLAS on the pass)
+        lin = lambda m: (m.weight.detach().t().contiguous().float(), m.bias.detach().contiguous().float())
+        self._heads = {"transl0": lin(self.transl_enc.layers[0]), "transl2": lin(self.transl_enc.layers[2]),
+                       "beta0": lin(self.beta_layer.layers[0]), "beta2": lin(self.beta_layer.layers[2])}
         self.engine.load_pointnet({k: v for k, v in self.state_dict().items() if k.startswith("scene_enc.")})
         self.engine.load_resnet({k: v for k, v in self.state_dict().items() if k.startswith("backbone.")},
                                 bn_eps=self.backbone.bn1.eps)
@@ -279,12 +283,14 @@ class EgoHMR(nn.Module):
                          else self._fast_backbone(batch["img"]))
             scene_feats = (self.engine.pointnet_forward(pts.float().contiguous()) if self.native_scene_enc
                            else self._fast_scene_enc(pts))
-            transl_feat = self.transl_enc(transl)
+            h = self.engine.linear(transl.float().contiguous(), *self._heads["transl0"], relu=True)
+            transl_feat = self.engine.linear(h, *self._heads["transl2"])
         else:
             img_feats, scene_feats, transl_feat = features["img_feats"], features["scene_feats"], features["transl_feat"]
         rest = torch.cat([scene_feats, transl_feat] + self._cam_feats(batch), dim=1).float().contiguous()
         img_feats = img_feats.float().contiguous()
-        betas = self.beta_layer(torch.cat([img_feats, rest], dim=1))  # :263-265
+        hb = self.engine.linear(torch.cat([img_feats, rest], dim=1).contiguous(), *self._heads["beta0"], relu=True)
+        betas = self.engine.linear(hb, *self._heads["beta2"]) + self.beta_layer.init_betas  # :263-265, :673-679
         self.engine.set_cond(img_feats, rest, vis.to(torch.uint8).contiguous())
         iob = np.repeat(np.arange(bs, dtype=np.int32), num_samples)
         if self._bodies_key != (bs, num_samples) or self.engine.n_bodies != iob.shape[0]:

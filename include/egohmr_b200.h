@@ -224,6 +224,11 @@ int ehb_resnet_load(ehb_ctx* ctx, const ehb_resnet_weights* w);
  * folded, ReLU / residual adds are fused into the GEMM epilogues. */
 int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, float* feats, void* stream);
 
+/* nn.Linear (+ ReLU) of the small step-invariant heads (FCHeadBeta egohmr.py:673-679, TranslEnc :685-691) in fp32 FFMA:
+ * y[m][n] = x[m][k] . w_t[k][n] + bias[n]; w_t is the TRANSPOSED nn.Linear weight; bias may be NULL; relu != 0 clamps. */
+int ehb_linear_f32(ehb_ctx* ctx, const float* x, const float* w_t, const float* bias, int m, int n, int k, int relu,
+                   float* y, void* stream);
+
 /* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
  * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);

@@ -25,7 +25,7 @@ KEEP = [
 
 
 def kernel_name(full):
-    m = re.search(r"(?:ehb::)?(?:\(anonymous namespace\)::|<unnamed>::)?(\w+_kernel)", full)
+    m = re.search(r"(\w+_kernel)", full) if "ehb::" in full else None
     return "ehb::" + m.group(1) if m else re.sub(r"[<(].*", "", full)[:60]
 
 
