@@ -205,6 +205,12 @@ struct ehb_ctx {
   std::vector<ConvPlan*> rn_convs;
   int rn_blocks[4] = {0, 0, 0, 0};
   bool rn_loaded = false;
+  // Operand scale of the ResNet activations.  fp16's narrow exponent makes the lo half of a small value denormal
+  // (|scale * v| < 0.125 starts losing relative precision) and ResNet activations are mostly << 1, so they are scaled
+  // by 64 (exact, a power of two) instead of the GCN's 8: values up to 1023 stay in range, the overflow flag reports
+  // beyond.  (Measured: the scale does not change the 1e-5 feature error, which grows linearly with depth — the
+  // signature of the tensor core's truncating fp32 accumulation, not of operand rounding.)
+  float rn_act_scale = 64.f;
   DevBuf rn_col, rn_x[2], rn_y1, rn_y2, rn_idt;
 
   DevBuf overflow, splitk;
@@ -1244,8 +1250,8 @@ static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, lo
   p.out_f32 = nullptr;
   p.overflow_flag = ctx->overflow.as<int>();
   p.M = rows;
-  p.acc_scale_inv = 1.f / (ctx->act_scale * c.w_scale);
-  p.act_scale = ctx->act_scale;
+  p.acc_scale_inv = 1.f / (ctx->rn_act_scale * c.w_scale);
+  p.act_scale = ctx->rn_act_scale;
   p.K = c.Kp;
   p.K2 = c2 ? c2->Kp : 0;
   p.Cout = c.cout;
@@ -1305,7 +1311,7 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
   {
     const auto& c0 = *cv[0];
     if (c0.kh != 7 || c0.kw != 7 || c0.cin != 3 || c0.stride != 2 || c0.pad != 3) return fail("ehb_resnet_forward: unexpected stem");
-    EHB_CUDA(ehb::launch_im2col_stem(img, col, n, h, w, H1, W1, c0.Kp, ctx->act_scale, stream));
+    EHB_CUDA(ehb::launch_im2col_stem(img, col, n, h, w, H1, W1, c0.Kp, ctx->rn_act_scale, stream));
     if (rn_gemm(ctx, c0, col, static_cast<long long>(n) * H1 * W1, nullptr, ctx->rn_x[1].as<__half>(), 1, stream)) return 1;
     EHB_CUDA(ehb::launch_maxpool_hl(ctx->rn_x[1].as<__half>(), ctx->rn_x[0].as<__half>(), n, H1, W1, c0.cout, stream));
     ctx->launches += 2;
@@ -1348,7 +1354,7 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
       W = Wo;
       C = c3.cout;
     }
-  EHB_CUDA(ehb::launch_avgpool_hl(ctx->rn_x[cur].as<__half>(), feats, n, H * W, C, ctx->act_scale, stream));
+  EHB_CUDA(ehb::launch_avgpool_hl(ctx->rn_x[cur].as<__half>(), feats, n, H * W, C, ctx->rn_act_scale, stream));
   ctx->launches += 1;
   return 0;
 }
