@@ -211,7 +211,7 @@ struct ehb_ctx {
   // beyond.  (Measured: the scale does not change the 1e-5 feature error, which grows linearly with depth — the
   // signature of the tensor core's truncating fp32 accumulation, not of operand rounding.)
   float rn_act_scale = 64.f;
-  DevBuf rn_col, rn_x[2], rn_y1, rn_y2, rn_idt;
+  DevBuf rn_col, rn_x[2], rn_y1, rn_y2;
 
   DevBuf overflow, splitk;
 
@@ -1277,7 +1277,7 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
   const int H1 = out_dim(h, 7, 2, 3), W1 = out_dim(w, 7, 2, 3), H2 = out_dim(H1, 3, 2, 1), W2 = out_dim(W1, 3, 2, 1);
   size_t col_bytes = pad_rows(static_cast<long long>(n) * H1 * W1) * 2 * cv[0]->Kp * sizeof(__half);
   size_t x_bytes = pad_rows(static_cast<long long>(n) * H1 * W1) * 2 * cv[0]->cout * sizeof(__half);
-  size_t y_bytes = 0, i_bytes = 0;
+  size_t y_bytes = 0;
   {
     int H = H2, W = W2, ci = 1;
     for (int s = 0; s < 4; ++s)
@@ -1292,7 +1292,6 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
         x_bytes = std::max(x_bytes, rout * 2 * c3.cout * sizeof(__half));
         if (b == 0) {
           const auto& cd = *cv[ci + 3];
-          i_bytes = std::max(i_bytes, rout * 2 * cd.cout * sizeof(__half));
           if (cd.stride != 1) col_bytes = std::max(col_bytes, rout * 2 * cd.Kp * sizeof(__half));
         }
         ci += b == 0 ? 4 : 3;
@@ -1305,7 +1304,6 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
   EHB_CUDA(ctx->rn_x[1].ensure(x_bytes, true));
   EHB_CUDA(ctx->rn_y1.ensure(y_bytes, true));
   EHB_CUDA(ctx->rn_y2.ensure(y_bytes, true));
-  EHB_CUDA(ctx->rn_idt.ensure(i_bytes, true));
   __half* col = ctx->rn_col.as<__half>();
   // ---- stem: conv 7x7 / 2 + BN + ReLU, max-pool 3x3 / 2  (models/resnet.py:109-113, 140-143)
   {

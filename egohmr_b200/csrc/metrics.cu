@@ -9,10 +9,6 @@
 namespace ehb {
 namespace {
 
-struct Mat3 {
-  double m[3][3];
-};
-
 __device__ inline void jacobi_eigen_sym3(double A[3][3], double V[3][3]) {
   for (int i = 0; i < 3; ++i)
     for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
