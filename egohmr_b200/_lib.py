@@ -93,6 +93,7 @@ SIGNATURES = {
     "ehb_rotmat_to_angle_axis": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "ehb_smpl_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_debug_set_gemm_mode": (C.c_int, [_vp, C.c_int]),
+    "ehb_debug_set_resnet_mode": (C.c_int, [_vp, C.c_int]),
     "ehb_check_overflow": (C.c_int, [_vp, _vp]),
     "ehb_time_hidden_layer": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), _vp]),
     "ehb_time_stage": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_float), _vp]),

@@ -103,13 +103,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int u = unit0; u < n_units; u += unit_step) {
-        const int m_row = ((u / p.n_ntiles) * 2 + static_cast<int>(rank)) * BM;
+        const int tile = (u / p.n_ntiles) * 2 + static_cast<int>(rank);
+        const int m_row = tile * BM;
         const int b_row = (u % p.n_ntiles) * BN + static_cast<int>(rank) * (BN / 2);
+        // implicit mode: this CTA's tile = images [n0, n0 + nb) x output rows [ho0, ho0 + th)
+        const int n0 = p.implicit ? (tile / p.tiles_per_img) * p.nb : 0;
+        const int hi0 = p.implicit ? (tile % p.tiles_per_img) * p.th * p.stride - p.pad : 0;
+        const int cpk = p.implicit ? p.Cin / BK : 1;
+        const uint32_t a_box_bytes = p.implicit ? static_cast<uint32_t>(p.nb * p.th * p.Wo) * BK * 2 : A_BYTES;
         for (int kb = 0; kb < KB; ++kb) {
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* s = smem + stage * STAGE_BYTES;
           const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
-          if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
+          if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * (2 * a_box_bytes + 2 * B_BYTES));
+          if (p.implicit) {
+            const int tap = kb / cpk, c = (kb % cpk) * BK;
+            const int wi = tap % p.kw - p.pad, hi = hi0 + tap / p.kw;
+            ptx::tma_load_4d_2sm(s, &tmA, lfull, c, wi, hi, n0);
+            ptx::tma_load_4d_2sm(s + A_BYTES, &tmA, lfull, p.Cin + c, wi, hi, n0);
+            ptx::tma_load_2d_2sm(s + 2 * A_BYTES, &tmB, lfull, kb * BK, b_row);
+            ptx::tma_load_2d_2sm(s + 2 * A_BYTES + B_BYTES, &tmB, lfull, p.K + kb * BK, b_row);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           const bool second = kb >= KB1;
           const CUtensorMap* ta = second ? &tmA2 : &tmA;
           const CUtensorMap* tb = second ? &tmB2 : &tmB;
@@ -179,15 +198,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float amax = 0.f;
     for (int u = unit0; u < n_units; u += unit_step) {
       const int n_tile = u % p.n_ntiles;
-      const long long row = static_cast<long long>((u / p.n_ntiles) * 2 + static_cast<int>(rank)) * BM + q * 32 + lane;
-      const bool valid = row < p.M;
+      const int tile = (u / p.n_ntiles) * 2 + static_cast<int>(rank);
+      long long tile_first = static_cast<long long>(tile) * BM, tile_rows = BM;
+      if (p.implicit) {   // the tile's output pixels are contiguous rows: nb whole images or th full-width rows of one
+        const int n0 = (tile / p.tiles_per_img) * p.nb, ho0 = (tile % p.tiles_per_img) * p.th;
+        tile_first = (static_cast<long long>(n0) * p.Ho + ho0) * p.Wo;
+        const int n_here = min(p.nb, p.n_img - n0), h_here = min(p.th, p.Ho - ho0);
+        tile_rows = n_here <= 0 ? 0 : (p.nb > 1 ? static_cast<long long>(n_here) * p.Ho * p.Wo : static_cast<long long>(h_here) * p.Wo);
+      }
+      tile_rows = max(0LL, min(tile_rows, p.M - tile_first));
+      const long long row = tile_first + q * 32 + lane;
+      const bool valid = q * 32 + lane < tile_rows;
       const long long row0w = row - lane;                  // first row of this warp's 32
       float* addv = addv_s + as * 256;
       if (et < BN) addv[et] = __ldg(p.bias + n_tile * BN + et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // the identity block of the first chunk is requested before the accumulator is awaited, every further chunk's
       // while the previous one is processed: its global latency never sits on the epilogue's critical path
-      const long long rows_valid = p.M - row0w;            // rows of this warp's 32 that exist
+      const long long rows_valid = tile_rows - q * 32;     // rows of this warp's 32 that exist
       uint4 raw_h[4], raw_l[4];
       if (p.res_hl) {
         const int cg0 = n_tile * BN + col_half * HALF;

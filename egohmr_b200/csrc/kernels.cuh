@@ -203,6 +203,13 @@ struct ConvGemmParams {
   int Cout, out_ld;       // out_ld = 2 * Cout (halves per row)
   int n_mtiles, n_ntiles; // 128-row tiles (even) and Cout / tile_n
   int relu;
+  // Implicit-GEMM mode (implicit != 0): tmA is a 4-D map over the NHWC input [N][H][W][hi(Cin) | lo(Cin)] and the A tile
+  // of k-block (tap, channel chunk) is the TMA box of the tile's output pixels shifted by the tap — the convolution's
+  // zero padding is TMA's out-of-bounds fill, no im2col matrix exists.  An M tile is `nb` images x `th` full output
+  // rows (th * Wo * nb <= 128); its output rows are contiguous, first row = (n0 * Ho + ho0) * Wo.
+  int implicit;
+  int Cin, kw, pad, stride;   // K = kh * kw * Cin, k = (ky * kw + kx) * Cin + c
+  int Ho, Wo, th, nb, tiles_per_img, n_img;
 };
 int conv_gemm_tile_n(int cout, long long rows, int num_sms);   // 256, 128 or 64 output channels per tile
 cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,

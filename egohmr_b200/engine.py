@@ -356,6 +356,9 @@ class Engine:
     def set_gemm_mode(self, mode):
         check(self.lib.ehb_debug_set_gemm_mode(self._h, int(mode)))
 
+    def set_resnet_mode(self, implicit_gemm):
+        check(self.lib.ehb_debug_set_resnet_mode(self._h, 1 if implicit_gemm else 0))
+
     def check_overflow(self):
         return bool(self.lib.ehb_check_overflow(self._h, _stream()))
 

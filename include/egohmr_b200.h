@@ -243,6 +243,9 @@ int ehb_smpl_backward(ehb_ctx* ctx, const float* x_t, const float* betas, const 
 /* Diagnostics.  gemm_mode 0 = tcgen05 fp16x3 kernel on CTA pairs (cta_group::2, product path), 1 = fp32 FFMA check
  * path (tests only), 2 = tcgen05 fp16x3 kernel on single CTAs (cta_group::1, bring-up comparison). */
 int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);
+/* ResNet 3x3 convolutions: 1 = implicit GEMM through 4-D TMA boxes (product path), 0 = explicit im2col matrix + the
+ * same GEMM (bring-up comparison; both must give identical bits). */
+int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm);
 /* Returns 1 (and clears it) if any fp16 operand overflowed since the last call; synchronises `stream`. */
 int ehb_check_overflow(ehb_ctx* ctx, void* stream);
 /* Runs only hidden layer `layer` (1-based index into ehb_gcn_weights.layers) `iters` times on the current

@@ -330,6 +330,14 @@ def test_native_resnet50_vs_module_and_float64(full):
         print(f"native ResNet-50 ({n_img} img): max|native - f64| = {d_native:.3e}, torch fp32 - f64 = {d_fp32:.3e} "
               f"(max|feat| = {scale:.3f})")
         assert d_native < 2e-5 * max(1.0, scale)
+        # the 3x3 convolutions as implicit GEMMs (4-D TMA boxes, zero padding = TMA out-of-bounds fill) and through an
+        # explicit im2col matrix feed the tensor core the same operands in the same order: identical bits
+        model.engine.set_resnet_mode(False)
+        try:
+            explicit = model.engine.resnet_forward(img.contiguous())
+        finally:
+            model.engine.set_resnet_mode(True)
+        assert torch.equal(explicit, got)
 
 
 def test_maxpool_nhwc_bit_exact(full):
