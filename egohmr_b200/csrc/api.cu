@@ -156,6 +156,24 @@ __global__ void denorm_kernel(const float* x, const float* mean, const float* st
 
 }  // namespace
 
+static void split_hl(const float* W, int rows, int cols, int ld, int col0, float scale, std::vector<__half>& out) {
+  // rows x cols block of W (row stride ld, first column col0) -> [rows][hi(cols) | lo(cols)] fp16 of scale*W
+  out.assign(static_cast<size_t>(rows) * 2 * cols, __half());
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < cols; ++c) {
+      const float sv = W[static_cast<size_t>(r) * ld + col0 + c] * scale;
+      const __half hi = __float2half_rn(sv);
+      out[static_cast<size_t>(r) * 2 * cols + c] = hi;
+      out[static_cast<size_t>(r) * 2 * cols + cols + c] = __float2half_rn(sv - __half2float(hi));
+    }
+}
+static float pow2_scale(float maxabs) {
+  if (!(maxabs > 0.f)) return 1.f;
+  float s = std::exp2(std::floor(std::log2(16384.f / maxabs)));
+  if (maxabs * s >= 16384.f) s *= 0.5f;
+  return s;
+}
+
 struct ehb_ctx {
   int device = 0;
   int num_sms = 0;
@@ -205,6 +223,8 @@ struct ehb_ctx {
   ehb::SmplDevice smpl{};
   DevBuf s_vt, s_sd, s_pd, s_w, s_jt, s_jsd, s_ex;
   DevBuf sc_R, sc_A, sc_j24, sc_pf, sc_p6, sc_dvp, sc_dA, sc_dpf;
+  DevBuf s_pdT_hl, s_zero_bias, sc_pf_hl, sc_Y;   // tensor-core pose blend: posedirs^T operand, pose-feature operand, Y
+  float s_pd_scale = 1.f;
 
   // ---- ResPointNet
   bool pn_loaded = false;
@@ -783,6 +803,19 @@ int ehb_smpl_load(ehb_ctx* ctx, const ehb_smpl_model* m) {
   std::vector<int32_t> ex(m->extra_vertex_ids, m->extra_vertex_ids + m->n_extra);
   if (ex.empty()) ex.push_back(0);
   EHB_CUDA(ctx->s_ex.upload(ex));
+  {
+    // A operand of the pose-blend GEMM: row r = 3*v + k holds posedirs[:, r] (K = 207 padded to 256) as fp16 hi | lo
+    const size_t rows = static_cast<size_t>(V) * 3, rows_pad = (rows + 255) / 256 * 256;
+    float mx = 0.f;
+    for (size_t i = 0; i < static_cast<size_t>(207) * rows; ++i) mx = std::max(mx, std::fabs(m->posedirs[i]));
+    ctx->s_pd_scale = pow2_scale(mx);
+    std::vector<float> pt(rows_pad * 256, 0.f);
+    for (int k = 0; k < 207; ++k)
+      for (size_t r = 0; r < rows; ++r) pt[r * 256 + k] = m->posedirs[static_cast<size_t>(k) * rows + r];
+    std::vector<__half> hl;
+    split_hl(pt.data(), static_cast<int>(rows_pad), 256, 256, 0, ctx->s_pd_scale, hl);
+    EHB_CUDA(ctx->s_pdT_hl.upload(hl));
+  }
   ehb::SmplDevice& d = ctx->smpl;
   d.v_template = ctx->s_vt.as<float>();
   d.shapedirs = ctx->s_sd.as<float>();
@@ -807,7 +840,37 @@ static int smpl_run(ehb_ctx* ctx, int n, const float* R, const float* betas, con
   EHB_CUDA(ehb::launch_smpl_pose(ctx->smpl, R, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_j24.as<float>(),
                                  ctx->sc_pf.as<float>(), n, stream));
   ctx->launches += 1;
-  if (verts) {
+  if (verts && n >= 64) {
+    // pose blend on the tensor cores: Y[3V][n_pad] = posedirs^T . pose_feature^T (conv_umma.cu, fp16x3), then skinning
+    const int n_pad = (n + 63) / 64 * 64;
+    const long long rows = static_cast<long long>(ctx->smpl.V) * 3;
+    const int n_mtiles = static_cast<int>((rows + 255) / 256) * 2;
+    const float pf_scale = 4096.f;   // |R - I| <= 2  ->  operand magnitude <= 8192
+    EHB_CUDA(ctx->sc_pf_hl.ensure(static_cast<size_t>(n_pad) * 512 * sizeof(__half)));
+    EHB_CUDA(ctx->sc_Y.ensure(static_cast<size_t>(n_mtiles) * 128 * n_pad * sizeof(float)));
+    if (ctx->s_zero_bias.bytes < n_pad * sizeof(float)) EHB_CUDA(ctx->s_zero_bias.ensure(n_pad * sizeof(float), true));
+    EHB_CUDA(ehb::launch_smpl_pf_operand(ctx->sc_pf.as<float>(), ctx->sc_pf_hl.as<__half>(), n, n_pad, pf_scale, stream));
+    const int bn = ehb::conv_gemm_tile_n(n_pad, rows, ctx->num_sms);
+    CUtensorMap tA, tB;
+    if (make_tmap_f16(&tA, ctx->s_pdT_hl.p, static_cast<uint64_t>(n_mtiles) * 128, 512, 128)) return 1;
+    if (make_tmap_f16(&tB, ctx->sc_pf_hl.p, n_pad, 512, bn / 2)) return 1;
+    ehb::ConvGemmParams p{};
+    p.bias = ctx->s_zero_bias.as<float>();
+    p.out_f32 = ctx->sc_Y.as<float>();
+    p.overflow_flag = ctx->overflow.as<int>();
+    p.M = rows;
+    p.acc_scale_inv = 1.f / (ctx->s_pd_scale * pf_scale);
+    p.act_scale = 1.f;
+    p.K = 256;
+    p.Cout = n_pad;
+    p.out_ld = 2 * n_pad;
+    p.n_mtiles = n_mtiles;
+    p.n_ntiles = n_pad / bn;
+    EHB_CUDA(ehb::launch_conv_gemm(tA, tB, tA, tB, p, ctx->num_sms, stream));
+    EHB_CUDA(ehb::launch_smpl_skin_tiled(ctx->smpl, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_Y.as<float>(), n_pad,
+                                         transl, verts, n, stream));
+    ctx->launches += 3;
+  } else if (verts) {
     EHB_CUDA(ehb::launch_smpl_skin(ctx->smpl, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_pf.as<float>(), transl,
                                    verts, n, stream));
     ctx->launches += 1;
@@ -827,24 +890,6 @@ int ehb_smpl_forward(ehb_ctx* ctx, int n, const float* R, const float* betas, co
   if (n <= 0) return fail("ehb_smpl_forward: n must be positive");
   EHB_CUDA(cudaSetDevice(ctx->device));
   return smpl_run(ctx, n, R, betas, nullptr, transl, verts, joints, static_cast<cudaStream_t>(stream_));
-}
-
-static void split_hl(const float* W, int rows, int cols, int ld, int col0, float scale, std::vector<__half>& out) {
-  // rows x cols block of W (row stride ld, first column col0) -> [rows][hi(cols) | lo(cols)] fp16 of scale*W
-  out.assign(static_cast<size_t>(rows) * 2 * cols, __half());
-  for (int r = 0; r < rows; ++r)
-    for (int c = 0; c < cols; ++c) {
-      const float sv = W[static_cast<size_t>(r) * ld + col0 + c] * scale;
-      const __half hi = __float2half_rn(sv);
-      out[static_cast<size_t>(r) * 2 * cols + c] = hi;
-      out[static_cast<size_t>(r) * 2 * cols + cols + c] = __float2half_rn(sv - __half2float(hi));
-    }
-}
-static float pow2_scale(float maxabs) {
-  if (!(maxabs > 0.f)) return 1.f;
-  float s = std::exp2(std::floor(std::log2(16384.f / maxabs)));
-  if (maxabs * s >= 16384.f) s *= 0.5f;
-  return s;
 }
 
 __global__ void relu_copy_kernel(const float* in, float* out, int n) {

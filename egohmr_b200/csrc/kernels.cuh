@@ -162,6 +162,13 @@ cudaError_t launch_smpl_pose(const SmplDevice& m, const float* R, const float* b
 cudaError_t launch_smpl_skin(const SmplDevice& m, const float* betas, const int32_t* beta_index, const float* A,
                              const float* posefeat, const float* transl /*[B][3] or null*/, float* verts,
                              int n_bodies, cudaStream_t stream);
+// tensor-core route of the pose blend: pose features -> GEMM B operand [n_pad][hi(256) | lo(256)] (K = 207 zero-padded),
+// and skinning from the GEMM's Y[3V][ldy] = posedirs^T . pose_feature^T
+cudaError_t launch_smpl_pf_operand(const float* posefeat, __half* pf_hl, int n_bodies, int n_pad, float scale,
+                                   cudaStream_t stream);
+cudaError_t launch_smpl_skin_tiled(const SmplDevice& m, const float* betas, const int32_t* beta_index, const float* A,
+                                   const float* Y, int ldy, const float* transl, float* verts, int n_bodies,
+                                   cudaStream_t stream);
 cudaError_t launch_smpl_joints(const SmplDevice& m, const float* joints24, const float* verts, const float* transl,
                                float* joints /*[B][24+n_extra][3]*/, int n_bodies, cudaStream_t stream);
 

@@ -77,10 +77,12 @@ def test_rot6d_empty_input():
     assert rot6d_to_rotmat(torch.zeros(0, 144, device="cuda")).shape == (0, 3, 3)
 
 
-def test_smpl_forward_matches_oracle(full):
+@pytest.mark.parametrize("n", [37, 64, 139])
+def test_smpl_forward_matches_oracle(full, n):
+    """n = 37: SIMT pose blend (ragged vs its 8-body tile); n >= 64: pose blend as a tcgen05 GEMM + tiled skinning (64 is
+    exactly one operand tile, 139 is ragged vs the 64-body operand padding and the 16-body skinning tile)."""
     model, _, _, smpl_model, _, _ = full
     rng = np.random.default_rng(3)
-    n = 37   # ragged vs the 8-body skinning tile
     R = geometry.rot6d_to_rotmat(rng.normal(0, 1, (n, 144))).reshape(n, 24, 3, 3)
     betas = rng.normal(0, 1, (n, 10))
     transl = rng.normal(0, 1, (n, 3))
@@ -92,6 +94,7 @@ def test_smpl_forward_matches_oracle(full):
     assert np.abs(out.vertices.cpu().numpy() - ref["vertices"]).max() < 3e-6
     assert np.abs(out.joints.cpu().numpy() - ref["joints"]).max() < 3e-6
     assert torch.equal(out.full_pose, Rt)
+    assert not model.engine.check_overflow()
 
 
 def test_smpl_known_answers(full):
