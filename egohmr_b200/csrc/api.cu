@@ -223,7 +223,7 @@ struct ehb_ctx {
   ehb::SmplDevice smpl{};
   DevBuf s_vt, s_sd, s_pd, s_w, s_jt, s_jsd, s_ex;
   DevBuf sc_R, sc_A, sc_j24, sc_pf, sc_p6, sc_dvp, sc_dA, sc_dpf;
-  DevBuf s_pdT_hl, s_zero_bias, sc_pf_hl, sc_Y;   // tensor-core pose blend: posedirs^T operand, pose-feature operand, Y
+  DevBuf s_pdT_hl, s_zero_bias, sc_pf_hl, sc_Y, s_w4, s_j4;   // tensor-core pose blend: posedirs^T operand, pose-feature operand, Y
   float s_pd_scale = 1.f;
 
   // ---- ResPointNet
@@ -817,6 +817,35 @@ int ehb_smpl_load(ehb_ctx* ctx, const ehb_smpl_model* m) {
     EHB_CUDA(ctx->s_pdT_hl.upload(hl));
   }
   ehb::SmplDevice& d = ctx->smpl;
+  {
+    // compact skinning weights: SMPL vertices follow at most four joints
+    std::vector<float> w4(static_cast<size_t>(V) * 4, 0.f);
+    std::vector<uint8_t> j4(static_cast<size_t>(V) * 4, 0);
+    bool sparse = true;
+    for (int v = 0; v < V && sparse; ++v) {
+      int q = 0;
+      for (int j = 0; j < ehb::NJ; ++j) {
+        const float wv = m->lbs_weights[static_cast<size_t>(v) * ehb::NJ + j];
+        if (wv != 0.f) {
+          if (q == 4) {
+            sparse = false;
+            break;
+          }
+          w4[v * 4 + q] = wv;
+          j4[v * 4 + q] = static_cast<uint8_t>(j);
+          ++q;
+        }
+      }
+    }
+    d.skin_w4 = nullptr;
+    d.skin_j4 = nullptr;
+    if (sparse) {
+      EHB_CUDA(ctx->s_w4.upload(w4));
+      EHB_CUDA(ctx->s_j4.upload(j4));
+      d.skin_w4 = ctx->s_w4.as<float>();
+      d.skin_j4 = ctx->s_j4.as<uint8_t>();
+    }
+  }
   d.v_template = ctx->s_vt.as<float>();
   d.shapedirs = ctx->s_sd.as<float>();
   d.posedirs = ctx->s_pd.as<float>();
@@ -840,7 +869,7 @@ static int smpl_run(ehb_ctx* ctx, int n, const float* R, const float* betas, con
   EHB_CUDA(ehb::launch_smpl_pose(ctx->smpl, R, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_j24.as<float>(),
                                  ctx->sc_pf.as<float>(), n, stream));
   ctx->launches += 1;
-  if (verts && n >= 64) {
+  if (verts && n >= 64 && ctx->smpl.NB <= 10 && ctx->smpl.skin_w4) {
     // pose blend on the tensor cores: Y[3V][n_pad] = posedirs^T . pose_feature^T (conv_umma.cu, fp16x3), then skinning
     const int n_pad = (n + 63) / 64 * 64;
     const long long rows = static_cast<long long>(ctx->smpl.V) * 3;

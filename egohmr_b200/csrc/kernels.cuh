@@ -147,6 +147,8 @@ struct SmplDevice {
   const float* j_template;   // [24][3]    J_regressor . v_template
   const float* j_shapedirs;  // [24][3][NB] J_regressor . shapedirs
   const int32_t* extra_vids; // [n_extra]
+  const float* skin_w4;      // [V][4] non-zero skinning weights in ascending joint order (0-padded), or null if a
+  const uint8_t* skin_j4;    // [V][4] vertex has more than four non-zero weights (then only the dense route is used)
   int parents[NJ];
   int V, NB, n_extra;
 };
