@@ -397,8 +397,9 @@ def run_b200(args):
         hbm("gcn_input_kernel (K2)", k2_bytes, k2_ms, "writes fp32 + fp16 hi/lo activations of every slot: 393 KB/body"),
         hbm("gcn_output_kernel (K3: output layer + fuse-select + sampler update)", k3_bytes, k3_ms,
             "reads the fp32 activations of both passes: 196.6 KB/body"),
-        hbm("ehb_decode (K4 rot6d + K5 SMPL pose/skin/joints, 5 launches)", dec_bytes, dec_ms,
-            "84.1 KB/body out + 19.3 MB model constants; the skinning kernel is FFMA-co-bound (7.7 MMAC/body)"),
+        hbm("ehb_decode (K4 rot6d + K5 SMPL: chain, pose-blend GEMM on tcgen05, tiled skinning, joints; 7 launches)",
+            dec_bytes + 2 * B * V * 12, dec_ms,
+            "84.1 KB/body out + the fp32 pose offsets written and re-read once (2 x 82.7 KB/body) + 19.3 MB constants"),
     ]
 
     ref_cuda = None
