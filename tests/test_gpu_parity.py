@@ -190,6 +190,11 @@ def test_ddim5_sampling_vs_reference_golden(full, golden_dir):
     dv = np.abs(oo["pred_vertices"].cpu().numpy() - v64).max()
     print(f"max vertex error vs float64 = {dv * 1e3:.3e} mm")
     assert dv < VERT_TOL_M
+    j64 = o_smpl.smpl_forward(smpl_model, R64, g64["betas"])["joints"][:, :24]
+    jo = oo["pred_keypoints_3d"].cpu().numpy()[:, :24]
+    mpjpe_delta = np.sqrt(((jo - j64) ** 2).sum(-1)).mean() * 1e3
+    print(f"MPJPE between this path and the float64 reference = {mpjpe_delta:.3e} mm")
+    assert mpjpe_delta < 5e-3
     assert np.abs(oo["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < VERT_TOL_M
     assert np.abs(oo["pred_keypoints_2d_full"].cpu().numpy() - g64["pred_keypoints_2d_full"]).max() < 1e-4
     assert np.abs(oo["pred_smpl_params"]["betas"].cpu().numpy() - g64["betas"]).max() < 1e-5

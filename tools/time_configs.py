@@ -3,7 +3,9 @@
   guided   cfg 3: DDPM-100 + collision-guided gradient, 32 images x 10 samples (per-body and batched collision interface)
   ddpm1000 cfg 5's per-GPU share: DDPM-1000, 64 images x 10 samples (512 x 10 over 8 GPUs)
   strong   cfg 4's per-GPU share: DDIM-5, 32 images x 10 samples (256 x 10 over 8 GPUs), graph replay
-Usage: python tools/time_configs.py [dropin guided ddpm1000 strong]"""
+  realpts  the step-invariant encoders at the real dataset's shape: 64 images, 20 000-point scene clouds
+           (dataloaders/egobody_dataset.py:213-225) instead of the 1 024 points of the benchmark configs
+Usage: python tools/time_configs.py [dropin guided ddpm1000 strong realpts]"""
 import json
 import os
 import sys
@@ -17,7 +19,7 @@ from egohmr_b200 import synth  # noqa: E402
 from egohmr_b200.diffusion.model_util import create_gaussian_diffusion  # noqa: E402
 from egohmr_b200.testing import BatchedSyntheticCollision, SyntheticCollision, build_model, torch_batch  # noqa: E402
 
-which = sys.argv[1:] or ["dropin", "guided", "ddpm1000", "strong"]
+which = sys.argv[1:] or ["dropin", "guided", "ddpm1000", "strong", "realpts"]
 dev = "cuda:0"
 model, diffusion, sd, smpl_model, mean, std = build_model(1024, 4, T=50, respacing="ddim5")
 mk = lambda T, r: create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=r,
@@ -88,3 +90,16 @@ if "strong" in which:
         diffusion.sample_many(model, batch, 10, "ddim5")
     ms, wall = timed(run, 20, warm=3)
     emit("cfg4 per-GPU share: DDIM-5, 32 images x 10 samples, eager launches", 320, ms, wall)
+
+if "realpts" in which:
+    import numpy as np
+    b_np = synth.make_batch(104, 64, 20000)
+    batch = torch_batch(b_np, dev)
+
+    def run():
+        model._cond_key = None
+        model.prepare(batch, 10)
+    ms, wall = timed(run, 5, warm=2)
+    pts = batch["scene_pcd_verts_full"].float().contiguous()
+    ms_pn, _ = timed(lambda: model.engine.pointnet_forward(pts), 5, warm=1)
+    emit("encoders at the real data shape: 64 images + 64 x 20000-point clouds (prepare())", 64, ms, wall, pointnet_ms=ms_pn)
