@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--num-samples", type=int, default=N_SAMPLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-img", type=int, default=8, help="images in the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-sample-samples", type=int, default=3, help="samples per image in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample-samples", type=int, default=4, help="samples per image in the CPU-baseline sample")
     return ap.parse_args()
 
 

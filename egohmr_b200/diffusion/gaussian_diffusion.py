@@ -224,6 +224,13 @@ class GaussianDiffusion:
                 eng.denoise_step(i, x, step_noise if kind == self.DDPM else None, grad, x_next, x0)
                 is_last = i == last
                 other = model.assemble_outputs(batch, x0, cond) if is_last else {"pred_x_start": x0}
+                if is_last and getattr(model, "check_overflow_each_call", True) and not th.cuda.is_current_stream_capturing():
+                    # the fp16 hi/lo operands have a finite range (|activation| < 8188 in the GCN, < 1023 in the image
+                    # encoder); a checkpoint that exceeds it must fail loudly, not return Inf/NaN.  One flag read-back
+                    # per sampling call (the caller consumes the outputs on the host right after anyway).
+                    if eng.check_overflow():
+                        raise FloatingPointError("fp16 operand overflow inside the tensor-core kernels: an activation left "
+                                                 "the representable range of the hi/lo operand format (see DESIGN.md, K1 numerics)")
                 yield {"sample": x_next, "pred_xstart": x0, "other_outputs": other}
                 if not is_last:
                     x, x_next = x_next, th.empty_like(x)

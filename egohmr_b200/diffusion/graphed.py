@@ -92,6 +92,11 @@ class GraphedSampler:
                 _get(self._staging, path).copy_(_get(batch, path), non_blocking=True)
             self._staged_evt.record()
 
+    def check_overflow(self):
+        """True if an fp16 operand overflowed in any replay since the last check (synchronises; replays themselves
+        cannot read the flag back)."""
+        return self.model.engine.check_overflow()
+
     def _version(self):
         return sum(p._version for p in self.model.parameters())
 

@@ -191,6 +191,7 @@ class EgoHMR(nn.Module):
         self._bodies_idx = None
         self._op2smpl_idx = None
         self._default_center = None
+        self.check_overflow_each_call = True   # read the fp16-overflow flag back at the end of every eager sampling call
         self.native_image_enc = True   # ResNet-50 on the tcgen05 convolution GEMMs (K9, fp32-class); False = cuDNN
         self.native_scene_enc = True   # ResPointNet on the tcgen05 linear kernel (K7); False = PyTorch/cuBLAS form
 

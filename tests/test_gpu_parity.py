@@ -453,6 +453,19 @@ def test_p_sample_loop_skip_init_dump_options(small):
         assert np.abs(d.cpu().numpy() - trace[k]["sample"]).max() < 5e-6
 
 
+def test_operand_overflow_fails_loudly(small):
+    """Activations beyond the fp16 hi/lo operand range must raise, not return Inf/NaN: scale one hidden layer's BatchNorm
+    so that its output leaves the range."""
+    from egohmr_b200.testing import build_model
+    model, diffusion, *_ = build_model(256, 2, T=50, respacing="ddim5", collision=False)
+    with torch.no_grad():
+        model.diffusion_model.gconv_layers[0].gconv1.bn.weight.mul_(1e6)
+    model.load_state_dict(model.state_dict(), strict=False)     # marks the kernels' weight copies dirty
+    with pytest.raises(FloatingPointError):
+        diffusion.sample_many(model, _tb(synth.make_batch(0, 2)), 1, "ddim5")
+    model.engine.close()
+
+
 def test_sample_many_equals_sequential_chains(full):
     """Flattening the num_samples loop (test_egohmr.py:251-255) into one batch changes nothing: chain (img i, sample n)
     of the flattened run equals the n-th sequential call when both see the same noise."""
