@@ -231,7 +231,7 @@ struct ehb_ctx {
   int pn_hidden = 0, pn_out = 0;
   float pn_wscale[4][2] = {};   // [block][0 = fc_0, 1 = fc_1 + shortcut (shared)]
   DevBuf pn_pos_w, pn_pos_b, pn_fc0[4], pn_fc1[4], pn_sc[4], pn_b0[4], pn_b1[4], pn_w0b_t[4], pn_wsb_t[4], pn_fcc_t, pn_fcc_b;
-  DevBuf pn_x[2], pn_y[2], pn_h, pn_pool, pn_pooled, pn_pooled_relu, pn_row0, pn_rows;
+  DevBuf pn_x[2], pn_y[2], pn_h, pn_pool, pn_pooled, pn_pooled_relu, pn_row0, pn_rows, pn_fold_w, pn_fold_b;
 
   // ---- ResNet-50 image encoder (conv_umma.cu)
   struct ConvPlan {
@@ -1056,6 +1056,22 @@ int ehb_pointnet_load(ehb_ctx* ctx, const ehb_pointnet_weights* w) {
       for (int d = 0; d < 3; ++d) t[static_cast<size_t>(d) * H2 + c] = w->fc_pos_w[static_cast<size_t>(c) * 3 + d];
     EHB_CUDA(ctx->pn_pos_w.upload(t));
     EHB_CUDA(up(ctx->pn_pos_b, w->fc_pos_b, H2));
+    // block_0's shortcut acts on x = fc_pos_0(p), a K = 3 linear map, so shortcut(x) = p . (Wpos^T Ws^T) + bpos . Ws^T is
+    // a K = 3 linear map too: it is added in the epilogue of the fc_1 GEMM straight from the point coordinates and the
+    // un-activated operand of x is never written or read (respointnet.py:35-36, 88-97)
+    std::vector<float> fw(3 * static_cast<size_t>(H)), fb(H);
+    for (int r = 0; r < H; ++r) {
+      double acc[3] = {0, 0, 0}, accb = 0;
+      for (int c = 0; c < H2; ++c) {
+        const double ws = w->shortcut_w[0][static_cast<size_t>(r) * H2 + c];
+        for (int d = 0; d < 3; ++d) acc[d] += double(w->fc_pos_w[static_cast<size_t>(c) * 3 + d]) * ws;
+        accb += double(w->fc_pos_b[c]) * ws;
+      }
+      for (int d = 0; d < 3; ++d) fw[static_cast<size_t>(d) * H + r] = float(acc[d]);
+      fb[r] = float(accb + double(w->fc1_b[0][r]));
+    }
+    EHB_CUDA(ctx->pn_fold_w.upload(fw));
+    EHB_CUDA(ctx->pn_fold_b.upload(fb));
   }
   for (int b = 0; b < 4; ++b) {
     const int kin = b == 0 ? H2 : H;   // per-point K of fc_0 / shortcut (the pooled half is a per-cloud row term)
@@ -1125,7 +1141,7 @@ int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts
   EHB_CUDA(ctx->pn_rows.ensure(pc * sizeof(float)));
   int* ovf = ctx->overflow.as<int>();
 
-  EHB_CUDA(ehb::launch_pointnet_pos(pts, ctx->pn_pos_w.as<float>(), ctx->pn_pos_b.as<float>(), ctx->pn_x[0].as<__half>(),
+  EHB_CUDA(ehb::launch_pointnet_pos(pts, ctx->pn_pos_w.as<float>(), ctx->pn_pos_b.as<float>(), nullptr,
                                     ctx->pn_x[1].as<__half>(), M, H2, act_scale, ovf, stream));
   ctx->launches += 1;
   // current block input: plain / relu'd fp16 operands with K = kin
@@ -1184,14 +1200,16 @@ int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts
     q.act_scale = act_scale;
     q.n_mtiles = n_mtiles;
     q.pts_per_cloud = n_pts;
-    q.bias = b == 0 ? ctx->pn_b1[b].as<float>() : nullptr;
+    q.bias = b == 0 ? ctx->pn_fold_b.as<float>() : nullptr;   // block_0: fc_1 bias + the folded shortcut's constant
     q.rowvec = rows_s;
+    q.pts = b == 0 ? pts : nullptr;
+    q.ptw = b == 0 ? ctx->pn_fold_w.as<float>() : nullptr;
     q.out_hl = last ? nullptr : y_plain;
     q.out_hl_relu = last ? nullptr : y_relu;
     q.pool = ctx->pn_pool.as<int>();
     q.acc_scale_inv = 1.f / (act_scale * ctx->pn_wscale[b][1]);
     q.K1 = H;
-    q.K2 = kin;
+    q.K2 = b == 0 ? 0 : kin;   // block_0's shortcut is the K = 3 epilogue term above
     EHB_CUDA(ehb::launch_linear_umma(tA_h, tB1, tA_plain, tBs, q, ctx->num_sms, stream));
     EHB_CUDA(ehb::launch_pool_decode(ctx->pn_pool.as<int>(), ctx->pn_pooled.as<float>(), static_cast<int>(pc), stream));
     relu_copy_kernel<<<static_cast<unsigned>((pc + 255) / 256), 256, 0, stream>>>(ctx->pn_pooled.as<float>(),

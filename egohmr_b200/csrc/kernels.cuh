@@ -182,6 +182,8 @@ struct LinearParams {
   __half* out_hl;         // [M_pad][hi(256) | lo(256)] of act_scale * Y, or null
   __half* out_hl_relu;    // same for relu(Y), or null
   int* pool;              // [n_clouds][256] order-preserving-int column max over the cloud's points, or null
+  const float* pts;       // [M][3] or null: adds pts[row] . ptw to every row (a K = 3 linear term folded into the epilogue)
+  const float* ptw;       // [3][256]
   int* overflow_flag;
   long long M;            // valid rows
   float acc_scale_inv;    // 1 / (act_scale * w_scale)

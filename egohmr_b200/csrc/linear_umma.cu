@@ -21,7 +21,7 @@ constexpr int B_BYTES = BN * BK * 2 / 2;        // per CTA of the pair: half of 
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // 64 KiB
 constexpr int STAGES = 3;
 constexpr int BAR_BYTES = 256;
-constexpr int ADDV_BYTES = 2 * 256 * 4;   // per-tile additive row (bias + per-cloud row), double-buffered
+constexpr int ADDV_BYTES = (2 + 3) * 256 * 4;   // per-tile additive row (bias + per-cloud row), double-buffered; + ptw[3][256]
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES + 8 * EPI_SCRATCH_BYTES;
 constexpr int NUM_EPI_WARPS = 8;  // two per TMEM lane quadrant: warp w and w+4 split the 256 columns
 constexpr int TMA_WARP = 8, MMA_WARP = 9;
@@ -164,6 +164,10 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     float amax = 0.f;
+    float* ptw_s = addv_s + 2 * 256;
+    if (p.pts) {   // staged once per launch; the first per-tile barrier below orders it before any use
+      for (int e = et; e < 3 * 256; e += 256) ptw_s[e] = __ldg(p.ptw + e);
+    }
     for (int u = unit0; u < n_units; u += unit_step) {
       const long long tile_first = static_cast<long long>(u * 2 + static_cast<int>(rank)) * BM;
       const long long row = tile_first + q * 32 + lane;
@@ -184,6 +188,12 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       const bool row_from_global = p.rowvec && !tile_one_cloud;
+      float px = 0.f, py = 0.f, pz = 0.f;
+      if (p.pts && valid) {
+        px = __ldg(p.pts + row * 3);
+        py = __ldg(p.pts + row * 3 + 1);
+        pz = __ldg(p.pts + row * 3 + 2);
+      }
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after_sync();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * 128;
@@ -205,6 +215,7 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
         for (int c = 0; c < 32; ++c) {
           float y = v[c] * p.acc_scale_inv + addv[c0 + c];
           if (row_from_global) y += __ldg(p.rowvec + static_cast<size_t>(cloud) * BN + c0 + c);
+          if (p.pts) y += fmaf(pz, ptw_s[512 + c0 + c], fmaf(py, ptw_s[256 + c0 + c], px * ptw_s[c0 + c]));
           v[c] = y;
         }
         if (p.out_f32 && valid) {
@@ -295,34 +306,53 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   }
 }
 
-// fc_pos_0 (3 -> 2*hidden, models/respointnet.py:21,35): K = 3 is not a tensor-core shape; this writes the two fp16
-// hi/lo operands block_0 consumes — relu(net) for fc_0 and net itself for the shortcut (:88-97).
+// fc_pos_0 (3 -> 2*hidden, models/respointnet.py:21,35): K = 3 is not a tensor-core shape; this writes the fp16 hi/lo
+// operand block_0's fc_0 consumes, relu(net).  (net itself, the shortcut's input, is optional: block_0's shortcut is
+// folded into a K = 3 epilogue term of the fc_1 GEMM, see ehb_pointnet_load.)
 __global__ void __launch_bounds__(256) pointnet_pos_kernel(const float* __restrict__ pts, const float* __restrict__ w /*[3][C]*/,
                                                            const float* __restrict__ b, __half* __restrict__ out_hl,
                                                            __half* __restrict__ out_hl_relu, long long M, int C,
                                                            float act_scale, int* overflow_flag) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long total = M * (C / 8);
-  if (i >= total) return;
-  const long long row = i / (C / 8);
-  const int c0 = static_cast<int>(i % (C / 8)) * 8;
-  const float x = pts[row * 3 + 0], y = pts[row * 3 + 1], z = pts[row * 3 + 2];
-  __align__(16) __half hi[8], lo[8], rhi[8], rlo[8];
-  float amax = 0.f;
+  // thread = 8 channels, kept in registers with their weights while the thread walks POS_ROWS rows; the C/8 threads of
+  // a row write C * 2 contiguous bytes per operand half
+  constexpr int POS_ROWS = 16;
+  const int groups = C / 8;                         // channel groups per row
+  const int rows_per_block = 256 / groups;          // row lanes of this block
+  const int cgp = threadIdx.x % groups, rl = threadIdx.x / groups;
+  if (rl >= rows_per_block) return;
+  const int c0 = cgp * 8;
+  float wx[8], wy[8], wz[8], bb[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const float v = fmaf(z, w[2 * C + c0 + c], fmaf(y, w[C + c0 + c], fmaf(x, w[c0 + c], b[c0 + c])));
-    const float sv = v * act_scale, rv = fmaxf(v, 0.f) * act_scale;
-    hi[c] = __float2half_rn(sv);
-    lo[c] = __float2half_rn(sv - __half2float(hi[c]));
-    rhi[c] = __float2half_rn(rv);
-    rlo[c] = __float2half_rn(rv - __half2float(rhi[c]));
-    amax = fmaxf(amax, fabsf(sv));
+    wx[c] = w[c0 + c];
+    wy[c] = w[C + c0 + c];
+    wz[c] = w[2 * C + c0 + c];
+    bb[c] = b[c0 + c];
   }
-  *reinterpret_cast<uint4*>(out_hl + row * (2 * C) + c0) = *reinterpret_cast<const uint4*>(hi);
-  *reinterpret_cast<uint4*>(out_hl + row * (2 * C) + C + c0) = *reinterpret_cast<const uint4*>(lo);
-  *reinterpret_cast<uint4*>(out_hl_relu + row * (2 * C) + c0) = *reinterpret_cast<const uint4*>(rhi);
-  *reinterpret_cast<uint4*>(out_hl_relu + row * (2 * C) + C + c0) = *reinterpret_cast<const uint4*>(rlo);
+  float amax = 0.f;
+  const long long row_begin = static_cast<long long>(blockIdx.x) * rows_per_block * POS_ROWS;
+  for (int i = 0; i < POS_ROWS; ++i) {
+    const long long row = row_begin + static_cast<long long>(i) * rows_per_block + rl;
+    if (row >= M) break;
+    const float x = pts[row * 3 + 0], y = pts[row * 3 + 1], z = pts[row * 3 + 2];
+    __align__(16) __half hi[8], lo[8], rhi[8], rlo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float v = fmaf(z, wz[c], fmaf(y, wy[c], fmaf(x, wx[c], bb[c])));
+      const float sv = v * act_scale, rv = fmaxf(v, 0.f) * act_scale;
+      hi[c] = __float2half_rn(sv);
+      lo[c] = __float2half_rn(sv - __half2float(hi[c]));
+      rhi[c] = __float2half_rn(rv);
+      rlo[c] = __float2half_rn(rv - __half2float(rhi[c]));
+      amax = fmaxf(amax, fabsf(sv));
+    }
+    if (out_hl) {
+      *reinterpret_cast<uint4*>(out_hl + row * (2 * C) + c0) = *reinterpret_cast<const uint4*>(hi);
+      *reinterpret_cast<uint4*>(out_hl + row * (2 * C) + C + c0) = *reinterpret_cast<const uint4*>(lo);
+    }
+    *reinterpret_cast<uint4*>(out_hl_relu + row * (2 * C) + c0) = *reinterpret_cast<const uint4*>(rhi);
+    *reinterpret_cast<uint4*>(out_hl_relu + row * (2 * C) + C + c0) = *reinterpret_cast<const uint4*>(rlo);
+  }
   if (!(amax <= 65504.f)) atomicExch(overflow_flag, 1);
 }
 
@@ -369,10 +399,11 @@ cudaError_t launch_linear_umma(const CUtensorMap& tmA1, const CUtensorMap& tmB1,
 
 cudaError_t launch_pointnet_pos(const float* pts, const float* w, const float* b, __half* out_hl, __half* out_hl_relu,
                                 long long M, int C, float act_scale, int* overflow_flag, cudaStream_t stream) {
-  const long long total = M * (C / 8);
-  if (total <= 0) return cudaSuccess;
-  pointnet_pos_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(pts, w, b, out_hl, out_hl_relu, M, C,
-                                                                                     act_scale, overflow_flag);
+  if (M <= 0) return cudaSuccess;
+  if (C % 8 != 0 || C / 8 > 256) return cudaErrorInvalidValue;
+  const long long rows_per_block = static_cast<long long>(256 / (C / 8)) * 16;
+  pointnet_pos_kernel<<<static_cast<unsigned>((M + rows_per_block - 1) / rows_per_block), 256, 0, stream>>>(
+      pts, w, b, out_hl, out_hl_relu, M, C, act_scale, overflow_flag);
   return cudaGetLastError();
 }
 
