@@ -556,10 +556,10 @@ cudaError_t launch_sgemm_nn(const float* A, const float* B, float* C, int M, int
 }
 
 int sgemm_splitk_plan(int M, int N, int K, int num_sms) {
-  // skinny problems only (few output tiles, long K): enough K chunks for ~4 blocks per SM, each at least 32 deep
+  // skinny problems only (few output tiles, long K): enough K chunks for ~8 blocks per SM (the loads of a block are latency-bound), each at least 32 deep
   const long long tiles = static_cast<long long>((N + 31) / 32) * ((M + 31) / 32);
   if (tiles >= 2LL * num_sms || K < 128) return 1;
-  long long want = (4LL * num_sms + tiles - 1) / tiles;
+  long long want = (8LL * num_sms + tiles - 1) / tiles;
   long long cap = K / 32;
   long long s = want < cap ? want : cap;
   return static_cast<int>(s < 1 ? 1 : (s > 64 ? 64 : s));
