@@ -9,6 +9,9 @@
 // linear_umma.cu, generalised over the N tile (64 / 128 / 256 output channels per tile, so the 64- and 128-channel
 // layers do not pay for 256) and over n-tiles inside the persistent work loop.  The epilogue writes the NEXT layer's
 // operand directly: bias, residual add (identity read back from its own hi/lo operand), ReLU, fp16 hi/lo split.
+#include <cstdio>
+#include <cstdlib>
+
 #include "epilogue.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -333,15 +336,31 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 
 }  // namespace
 
-// Largest N tile (256 / 128 / 64) that divides Cout AND still gives every CTA pair a work unit; small-M layers (the
-// 7 x 7 stage) trade MMA width for parallelism.
+// N tile (256 / 128 / 64 output channels) of one layer: the one with the lowest estimated time = rounds of work units
+// over the CTA pairs x relative cost of a unit (narrower tiles re-read A and run the MMA less efficiently).  Small-M
+// layers (the 14 x 14 and 7 x 7 stages) trade MMA width for parallelism.
 int conv_gemm_tile_n(int cout, long long rows, int num_sms) {
+  static float cost[3] = {1.0f, 0.6f, 0.4f};   // swept on B200: 2.83 ms for ResNet-50 x 64 images (always-largest tile: 2.98)
+  static bool init = false;
+  if (!init) {   // bring-up override: EHB_CONV_COST="c256,c128,c64"
+    if (const char* e = getenv("EHB_CONV_COST")) sscanf(e, "%f,%f,%f", &cost[0], &cost[1], &cost[2]);
+    init = true;
+  }
   const long long m_units = (rows + 255) / 256;
   const int pairs = num_sms / 2;
-  for (int bn : {256, 128}) {
-    if (cout % bn == 0 && m_units * (cout / bn) >= pairs) return bn;
+  const int bns[3] = {256, 128, 64};
+  int best = 0;
+  float best_t = 1e30f;
+  for (int i = 0; i < 3; ++i) {
+    if (cout % bns[i]) continue;
+    const long long units = m_units * (cout / bns[i]);
+    const float t = static_cast<float>((units + pairs - 1) / pairs) * cost[i];
+    if (t < best_t) {
+      best_t = t;
+      best = bns[i];
+    }
   }
-  return cout % 64 == 0 ? 64 : 0;
+  return best;
 }
 
 cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
