@@ -223,7 +223,7 @@ struct ehb_ctx {
   ehb::SmplDevice smpl{};
   DevBuf s_vt, s_sd, s_pd, s_w, s_jt, s_jsd, s_ex;
   DevBuf sc_R, sc_A, sc_j24, sc_pf, sc_p6, sc_dvp, sc_dA, sc_dpf;
-  DevBuf s_pdT_hl, s_zero_bias, sc_pf_hl, sc_Y, s_w4, s_j4;   // tensor-core pose blend: posedirs^T operand, pose-feature operand, Y
+  DevBuf s_pdT_hl, s_zero_bias, sc_pf_hl, sc_Y, s_w4, s_j4, s_sdT;   // tensor-core pose blend: posedirs^T operand, pose-feature operand, Y
   float s_pd_scale = 1.f;
 
   // ---- ResPointNet
@@ -837,6 +837,12 @@ int ehb_smpl_load(ehb_ctx* ctx, const ehb_smpl_model* m) {
         }
       }
     }
+    std::vector<float> sdt(static_cast<size_t>(3) * NB * V);
+    for (int v = 0; v < V; ++v)
+      for (int k = 0; k < 3; ++k)
+        for (int l = 0; l < NB; ++l) sdt[(static_cast<size_t>(k) * NB + l) * V + v] = m->shapedirs[(static_cast<size_t>(v) * 3 + k) * NB + l];
+    EHB_CUDA(ctx->s_sdT.upload(sdt));
+    d.shapedirs_t = ctx->s_sdT.as<float>();
     d.skin_w4 = nullptr;
     d.skin_j4 = nullptr;
     if (sparse) {
@@ -870,34 +876,37 @@ static int smpl_run(ehb_ctx* ctx, int n, const float* R, const float* betas, con
                                  ctx->sc_pf.as<float>(), n, stream));
   ctx->launches += 1;
   if (verts && n >= 64 && ctx->smpl.NB <= 10 && ctx->smpl.skin_w4) {
-    // pose blend on the tensor cores: Y[3V][n_pad] = posedirs^T . pose_feature^T (conv_umma.cu, fp16x3), then skinning
-    const int n_pad = (n + 63) / 64 * 64;
-    const long long rows = static_cast<long long>(ctx->smpl.V) * 3;
-    const int n_mtiles = static_cast<int>((rows + 255) / 256) * 2;
+    // pose blend on the tensor cores, body-major: Y[n_pad][3V pad] = pose_feature . posedirs (conv_umma.cu, fp16x3) —
+    // A = the pose features of this call, "weights" = posedirs^T (constant) — then skinning
+    const long long cols = static_cast<long long>(ctx->smpl.V) * 3;
+    const int cols_pad = static_cast<int>((cols + 255) / 256 * 256);      // rows of the posedirs^T operand
+    const int n_mtiles = static_cast<int>((n + 255) / 256) * 2;
+    const size_t n_pad = static_cast<size_t>(n_mtiles) * 128;
     const float pf_scale = 4096.f;   // |R - I| <= 2  ->  operand magnitude <= 8192
-    EHB_CUDA(ctx->sc_pf_hl.ensure(static_cast<size_t>(n_pad) * 512 * sizeof(__half)));
-    EHB_CUDA(ctx->sc_Y.ensure(static_cast<size_t>(n_mtiles) * 128 * n_pad * sizeof(float)));
-    if (ctx->s_zero_bias.bytes < n_pad * sizeof(float)) EHB_CUDA(ctx->s_zero_bias.ensure(n_pad * sizeof(float), true));
-    EHB_CUDA(ehb::launch_smpl_pf_operand(ctx->sc_pf.as<float>(), ctx->sc_pf_hl.as<__half>(), n, n_pad, pf_scale, stream));
-    const int bn = ehb::conv_gemm_tile_n(n_pad, rows, ctx->num_sms);
+    EHB_CUDA(ctx->sc_pf_hl.ensure(n_pad * 512 * sizeof(__half)));
+    EHB_CUDA(ctx->sc_Y.ensure(n_pad * cols_pad * sizeof(float)));
+    EHB_CUDA(ctx->s_zero_bias.ensure(static_cast<size_t>(cols_pad) * sizeof(float), true));
+    EHB_CUDA(ehb::launch_smpl_pf_operand(ctx->sc_pf.as<float>(), ctx->sc_pf_hl.as<__half>(), n, static_cast<int>(n_pad),
+                                         pf_scale, stream));
+    const int bn = ehb::conv_gemm_tile_n(cols_pad, n, ctx->num_sms);
     CUtensorMap tA, tB;
-    if (make_tmap_f16(&tA, ctx->s_pdT_hl.p, static_cast<uint64_t>(n_mtiles) * 128, 512, 128)) return 1;
-    if (make_tmap_f16(&tB, ctx->sc_pf_hl.p, n_pad, 512, bn / 2)) return 1;
+    if (make_tmap_f16(&tA, ctx->sc_pf_hl.p, n_pad, 512, 128)) return 1;
+    if (make_tmap_f16(&tB, ctx->s_pdT_hl.p, cols_pad, 512, bn / 2)) return 1;
     ehb::ConvGemmParams p{};
     p.bias = ctx->s_zero_bias.as<float>();
     p.out_f32 = ctx->sc_Y.as<float>();
     p.overflow_flag = ctx->overflow.as<int>();
-    p.M = rows;
+    p.M = n;
     p.acc_scale_inv = 1.f / (ctx->s_pd_scale * pf_scale);
     p.act_scale = 1.f;
     p.K = 256;
-    p.Cout = n_pad;
-    p.out_ld = 2 * n_pad;
+    p.Cout = cols_pad;
+    p.out_ld = 2 * cols_pad;
     p.n_mtiles = n_mtiles;
-    p.n_ntiles = n_pad / bn;
+    p.n_ntiles = cols_pad / bn;
     EHB_CUDA(ehb::launch_conv_gemm(tA, tB, tA, tB, p, ctx->num_sms, stream));
-    EHB_CUDA(ehb::launch_smpl_skin_tiled(ctx->smpl, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_Y.as<float>(), n_pad,
-                                         transl, verts, n, stream));
+    EHB_CUDA(ehb::launch_smpl_skin_tiled(ctx->smpl, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_Y.as<float>(),
+                                         static_cast<size_t>(cols_pad), transl, verts, n, stream));
     ctx->launches += 3;
   } else if (verts) {
     EHB_CUDA(ehb::launch_smpl_skin(ctx->smpl, betas, beta_index, ctx->sc_A.as<float>(), ctx->sc_pf.as<float>(), transl,

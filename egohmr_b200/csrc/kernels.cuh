@@ -147,6 +147,7 @@ struct SmplDevice {
   const float* j_template;   // [24][3]    J_regressor . v_template
   const float* j_shapedirs;  // [24][3][NB] J_regressor . shapedirs
   const int32_t* extra_vids; // [n_extra]
+  const float* shapedirs_t;  // [3 * NB][V]  shapedirs transposed (coalesced along the vertex axis)
   const float* skin_w4;      // [V][4] non-zero skinning weights in ascending joint order (0-padded), or null if a
   const uint8_t* skin_j4;    // [V][4] vertex has more than four non-zero weights (then only the dense route is used)
   int parents[NJ];
@@ -164,12 +165,12 @@ cudaError_t launch_smpl_pose(const SmplDevice& m, const float* R, const float* b
 cudaError_t launch_smpl_skin(const SmplDevice& m, const float* betas, const int32_t* beta_index, const float* A,
                              const float* posefeat, const float* transl /*[B][3] or null*/, float* verts,
                              int n_bodies, cudaStream_t stream);
-// tensor-core route of the pose blend: pose features -> GEMM B operand [n_pad][hi(256) | lo(256)] (K = 207 zero-padded),
-// and skinning from the GEMM's Y[3V][ldy] = posedirs^T . pose_feature^T
+// tensor-core route of the pose blend: pose features -> GEMM A operand [n_pad][hi(256) | lo(256)] (K = 207 zero-padded),
+// and skinning from the GEMM's body-major Y[n_pad][ldy] = pose_feature . posedirs (ldy = 3V padded to a tile multiple)
 cudaError_t launch_smpl_pf_operand(const float* posefeat, __half* pf_hl, int n_bodies, int n_pad, float scale,
                                    cudaStream_t stream);
 cudaError_t launch_smpl_skin_tiled(const SmplDevice& m, const float* betas, const int32_t* beta_index, const float* A,
-                                   const float* Y, int ldy, const float* transl, float* verts, int n_bodies,
+                                   const float* Y, size_t ldy, const float* transl, float* verts, int n_bodies,
                                    cudaStream_t stream);
 cudaError_t launch_smpl_joints(const SmplDevice& m, const float* joints24, const float* verts, const float* transl,
                                float* joints /*[B][24+n_extra][3]*/, int n_bodies, cudaStream_t stream);

@@ -266,15 +266,16 @@ __global__ void __launch_bounds__(256) smpl_pf_operand_kernel(const float* __res
 // ... and this one skins: thread = vertex, block = 128 vertices x 32 bodies.  SMPL's skinning weights are sparse (at most
 // four joints per vertex), so the model carries a compact (joint, weight) list per vertex, in ascending joint order: the
 // blend sums exactly the terms the dense loop of smpl_skin_kernel keeps, in the same order (identical bits), with 4
-// instead of 24 warp-divergent iterations.  The vertex's constants sit in registers for all 32 bodies, the bodies'
-// skinning transforms are staged in shared memory with one linear copy, the three Y rows of the vertex are read as
-// 64-byte runs along the body axis, the vertices of one body leave as 384 contiguous bytes per warp.
-constexpr int SKT_V = 128, SKT_B = 32, SKT_C = 16;
+// instead of 24 warp-divergent iterations.  Every global access is coalesced along the vertex axis: the GEMM writes the
+// pose offsets body-major (Y[b][3v + k]), the blend-shape basis is read from a transposed copy ([3 * NB][V]), a body's
+// vertices leave as 384 contiguous bytes per warp; the vertex's constants sit in registers for all 32 bodies and the
+// bodies' skinning transforms are staged in shared memory with one linear copy.
+constexpr int SKT_V = 128, SKT_B = 32;
 __global__ void __launch_bounds__(SKT_V) smpl_skin_tiled_kernel(const __grid_constant__ SmplDevice m,
                                                                 const float* __restrict__ betas,
                                                                 const int32_t* __restrict__ beta_index,
                                                                 const float* __restrict__ A, const float* __restrict__ Y,
-                                                                int ldy, const float* __restrict__ transl,
+                                                                size_t ldy, const float* __restrict__ transl,
                                                                 float* __restrict__ verts, int n_bodies) {
   __shared__ __align__(16) float A_s[SKT_B][NJ][12];
   __shared__ float beta_s[SKT_B][10];
@@ -298,67 +299,54 @@ __global__ void __launch_bounds__(SKT_V) smpl_skin_tiled_kernel(const __grid_con
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
-    for (int l = 0; l < 10; ++l) sd[k][l] = l < m.NB ? __ldg(m.shapedirs + (static_cast<size_t>(v) * 3 + k) * m.NB + l) : 0.f;
+    for (int l = 0; l < 10; ++l) sd[k][l] = l < m.NB ? __ldg(m.shapedirs_t + static_cast<size_t>(k * m.NB + l) * m.V + v) : 0.f;
   const float4 wq = __ldg(reinterpret_cast<const float4*>(m.skin_w4) + v);
   const uchar4 jq = __ldg(reinterpret_cast<const uchar4*>(m.skin_j4) + v);
   const float w4[4] = {wq.x, wq.y, wq.z, wq.w};
   const int j4[4] = {jq.x, jq.y, jq.z, jq.w};
   const float t0 = m.v_template[v * 3 + 0], t1 = m.v_template[v * 3 + 1], t2 = m.v_template[v * 3 + 2];
-  for (int c0 = 0; c0 < nb; c0 += SKT_C) {
-    // pose offsets of this vertex for 16 bodies: three 64-byte runs of Y (ldy % 16 == 0, b % 16 == 0)
-    float yo[3][SKT_C];
+#pragma unroll 4
+  for (int bb = 0; bb < nb; ++bb) {
+    const int b = b_begin + bb;
+    const float* yp = Y + static_cast<size_t>(b) * ldy + static_cast<size_t>(v) * 3;   // pose offsets of (body, vertex)
+    const float y0 = __ldg(yp), y1 = __ldg(yp + 1), y2 = __ldg(yp + 2);
+    float vs0 = 0.f, vs1 = 0.f, vs2 = 0.f;   // same summation order as smpl_skin_kernel
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float4* yp = reinterpret_cast<const float4*>(Y + (static_cast<size_t>(v) * 3 + k) * ldy + b_begin + c0);
+    for (int l = 0; l < 10; ++l) {
+      const float be = beta_s[bb][l];
+      vs0 = fmaf(sd[0][l], be, vs0);
+      vs1 = fmaf(sd[1][l], be, vs1);
+      vs2 = fmaf(sd[2][l], be, vs2);
+    }
+    const float px = y0 + (t0 + vs0);
+    const float py = y1 + (t1 + vs1);
+    const float pz = y2 + (t2 + vs2);
+    float T[12];
 #pragma unroll
-      for (int g = 0; g < SKT_C / 4; ++g) {
-        const float4 t = __ldg(yp + g);
-        yo[k][4 * g] = t.x; yo[k][4 * g + 1] = t.y; yo[k][4 * g + 2] = t.z; yo[k][4 * g + 3] = t.w;
+    for (int e = 0; e < 12; ++e) T[e] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (w4[q] != 0.f) {
+        const float4* ap = reinterpret_cast<const float4*>(&A_s[bb][j4[q]][0]);
+        const float4 r0 = ap[0], r1 = ap[1], r2 = ap[2];
+        T[0] = fmaf(w4[q], r0.x, T[0]); T[1] = fmaf(w4[q], r0.y, T[1]); T[2] = fmaf(w4[q], r0.z, T[2]);
+        T[3] = fmaf(w4[q], r0.w, T[3]); T[4] = fmaf(w4[q], r1.x, T[4]); T[5] = fmaf(w4[q], r1.y, T[5]);
+        T[6] = fmaf(w4[q], r1.z, T[6]); T[7] = fmaf(w4[q], r1.w, T[7]); T[8] = fmaf(w4[q], r2.x, T[8]);
+        T[9] = fmaf(w4[q], r2.y, T[9]); T[10] = fmaf(w4[q], r2.z, T[10]); T[11] = fmaf(w4[q], r2.w, T[11]);
       }
     }
-#pragma unroll
-    for (int bc = 0; bc < SKT_C; ++bc) {
-      const int bb = c0 + bc;
-      if (bb >= nb) break;
-      float vs0 = 0.f, vs1 = 0.f, vs2 = 0.f;   // same summation order as smpl_skin_kernel
-#pragma unroll
-      for (int l = 0; l < 10; ++l) {
-        const float be = beta_s[bb][l];
-        vs0 = fmaf(sd[0][l], be, vs0);
-        vs1 = fmaf(sd[1][l], be, vs1);
-        vs2 = fmaf(sd[2][l], be, vs2);
-      }
-      const float px = yo[0][bc] + (t0 + vs0);
-      const float py = yo[1][bc] + (t1 + vs1);
-      const float pz = yo[2][bc] + (t2 + vs2);
-      float T[12];
-#pragma unroll
-      for (int e = 0; e < 12; ++e) T[e] = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (w4[q] != 0.f) {
-          const float4* ap = reinterpret_cast<const float4*>(&A_s[bb][j4[q]][0]);
-          const float4 r0 = ap[0], r1 = ap[1], r2 = ap[2];
-          T[0] = fmaf(w4[q], r0.x, T[0]); T[1] = fmaf(w4[q], r0.y, T[1]); T[2] = fmaf(w4[q], r0.z, T[2]);
-          T[3] = fmaf(w4[q], r0.w, T[3]); T[4] = fmaf(w4[q], r1.x, T[4]); T[5] = fmaf(w4[q], r1.y, T[5]);
-          T[6] = fmaf(w4[q], r1.z, T[6]); T[7] = fmaf(w4[q], r1.w, T[7]); T[8] = fmaf(w4[q], r2.x, T[8]);
-          T[9] = fmaf(w4[q], r2.y, T[9]); T[10] = fmaf(w4[q], r2.z, T[10]); T[11] = fmaf(w4[q], r2.w, T[11]);
-        }
-      }
-      float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
-      float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
-      float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
-      const int b = b_begin + bb;
-      if (transl) {
-        ox += transl[b * 3 + 0];
-        oy += transl[b * 3 + 1];
-        oz += transl[b * 3 + 2];
-      }
-      float* o = verts + (static_cast<size_t>(b) * m.V + v) * 3;
-      o[0] = ox;
-      o[1] = oy;
-      o[2] = oz;
+    float ox = T[0] * px + T[1] * py + T[2] * pz + T[3];
+    float oy = T[4] * px + T[5] * py + T[6] * pz + T[7];
+    float oz = T[8] * px + T[9] * py + T[10] * pz + T[11];
+    if (transl) {
+      ox += transl[b * 3 + 0];
+      oy += transl[b * 3 + 1];
+      oz += transl[b * 3 + 2];
     }
+    float* o = verts + (static_cast<size_t>(b) * m.V + v) * 3;
+    o[0] = ox;
+    o[1] = oy;
+    o[2] = oz;
   }
 }
 
@@ -423,10 +411,10 @@ cudaError_t launch_smpl_pf_operand(const float* posefeat, __half* pf_hl, int n_b
 }
 
 cudaError_t launch_smpl_skin_tiled(const SmplDevice& m, const float* betas, const int32_t* beta_index, const float* A,
-                                   const float* Y, int ldy, const float* transl, float* verts, int n_bodies,
+                                   const float* Y, size_t ldy, const float* transl, float* verts, int n_bodies,
                                    cudaStream_t stream) {
   if (n_bodies <= 0) return cudaSuccess;
-  if (m.NB > 10 || ldy % SKT_C != 0 || !m.skin_w4) return cudaErrorInvalidValue;
+  if (m.NB > 10 || !m.skin_w4 || !m.shapedirs_t) return cudaErrorInvalidValue;
   dim3 grid((m.V + SKT_V - 1) / SKT_V, (n_bodies + SKT_B - 1) / SKT_B);
   smpl_skin_tiled_kernel<<<grid, SKT_V, 0, stream>>>(m, betas, beta_index, A, Y, ldy, transl, verts, n_bodies);
   return cudaGetLastError();
