@@ -30,6 +30,14 @@ def shard_batch(batch, rank, world):
     return out
 
 
+def shard_noise(noise, n_img_total, num_samples, rank, world):
+    """Slice a globally pre-drawn noise tensor [n_steps+1, n_img_total*num_samples, 144] (reference draw order, body =
+    image*num_samples + n) to the bodies of this rank's images, so that a sharded run reproduces the single-GPU chains
+    bit for bit: feed the result to `sample_many(..., noise=...)` / `GraphedSampler(external_noise=True)`."""
+    lo, hi = shard_bounds(n_img_total, rank, world)
+    return noise[:, lo * num_samples: hi * num_samples].contiguous()
+
+
 def pack_results(out):
     """[B, 226]: what test_egohmr.py keeps per sample (pred_smpl_params, :260-266)."""
     p = out["pred_smpl_params"]

@@ -21,6 +21,20 @@ def test_shard_bounds_cover_and_balance():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_noise_partitions_the_global_draw():
+    """Concatenating every rank's noise slice in rank order gives back the global tensor, ragged shards included."""
+    import torch
+    from egohmr_b200 import sharding
+    n_img, S = 7, 3
+    noise = torch.arange(6 * n_img * S * 144, dtype=torch.float32).reshape(6, n_img * S, 144)
+    for world in (1, 2, 3, 8):
+        parts = [sharding.shard_noise(noise, n_img, S, r, world) for r in range(world)]
+        assert torch.equal(torch.cat(parts, dim=1), noise)
+        for r, p in enumerate(parts):
+            lo, hi = sharding.shard_bounds(n_img, r, world)
+            assert p.shape == (6, (hi - lo) * S, 144)
+
+
 def test_pack_unpack_roundtrip():
     rng = np.random.default_rng(0)
     out = {"pred_smpl_params": {"global_orient": torch.from_numpy(rng.normal(size=(6, 1, 3, 3)).astype(np.float32)),
