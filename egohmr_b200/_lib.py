@@ -90,6 +90,7 @@ SIGNATURES = {
     "ehb_resnet_load": (C.c_int, [_vp, C.POINTER(ResnetWeights)]),
     "ehb_resnet_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "ehb_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "ehb_nn_dist_sq": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "ehb_rotmat_to_angle_axis": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "ehb_smpl_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_debug_set_gemm_mode": (C.c_int, [_vp, C.c_int]),

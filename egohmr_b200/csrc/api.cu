@@ -1553,6 +1553,17 @@ int ehb_linear_f32(ehb_ctx* ctx, const float* x, const float* w_t, const float* 
   return 0;
 }
 
+int ehb_nn_dist_sq(ehb_ctx* ctx, const float* q, const int32_t* q_index, int n_q, const float* r, const int32_t* r_index,
+                   int n_r, int n_pairs, float* out, void* stream_) {
+  if (!ctx || !q || !r || !out) return fail("ehb_nn_dist_sq: null argument");
+  if (n_q <= 0 || n_r <= 0 || n_pairs < 0) return fail("ehb_nn_dist_sq: point counts must be positive");
+  if (n_pairs > 65535) return fail("ehb_nn_dist_sq: at most 65535 cloud pairs per call");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_nn_dist_sq(q, q_index, n_q, r, r_index, n_r, n_pairs, out, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += n_pairs > 0;
+  return 0;
+}
+
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream_) {
   if (!ctx || !R || !aa) return fail("ehb_rotmat_to_angle_axis: null argument");
   if (n < 0) return fail("ehb_rotmat_to_angle_axis: negative n");

@@ -251,6 +251,11 @@ cudaError_t launch_scene_crop(const float* verts, int n_bodies, int V, const flo
 cudaError_t launch_procrustes(const float* S1, const float* S2, const float* mask, int n_problems, int n_pts,
                               float* S1_hat, float* err, cudaStream_t stream);
 
+// squared distance of every query point to its nearest reference point, per (query cloud, reference cloud) pair:
+// pair i uses q[q_index ? q_index[i] : i] ([n_q][3]) and r[r_index ? r_index[i] : i] ([n_r][3]); out [n_pairs][n_q]
+cudaError_t launch_nn_dist_sq(const float* q, const int32_t* q_index, int n_q, const float* r, const int32_t* r_index,
+                              int n_r, int n_pairs, float* out, cudaStream_t stream);
+
 // ---- guidance backward (smpl_bwd.cu)
 cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, cudaStream_t stream);
 // dL/dx [B][144] from dL/dverts [B][V][3], dL/djoints [B][24+E][3], dL/dfull_pose_aa [B][24][3] (each may be null).

@@ -196,3 +196,53 @@ cudaError_t launch_procrustes(const float* S1, const float* S2, const float* mas
 }
 
 }  // namespace ehb
+
+// ------------------------------------------------------------------------------------------------ 1-NN distances
+// The contact score of the evaluation driver (test_egohmr.py:496-506) takes, for every predicted body, the squared
+// distance from each vertex to its nearest scene point: `chamfer_distance(verts, scene)` of
+// utils/pytorch3d_chamfer_distance.py:69-222, whose arithmetic is pytorch3d's brute-force `knn_points(K=1)` (third-party
+// CUDA, not vendored in the reference).  Block = (pair, 128 query points); the reference cloud streams through shared
+// memory in 1024-point tiles, every thread keeps the running minimum of its query point.  Compute-bound (8 flop per
+// point pair); the clouds may be indexed (all samples of an image share one scene cloud — no `.repeat`).
+namespace ehb {
+namespace {
+
+constexpr int NN_Q = 128, NN_TILE = 1024;
+
+__global__ void __launch_bounds__(NN_Q) nn_dist_sq_kernel(const float* __restrict__ q, const int32_t* __restrict__ q_index,
+                                                          int n_q, const float* __restrict__ r,
+                                                          const int32_t* __restrict__ r_index, int n_r,
+                                                          float* __restrict__ out) {
+  __shared__ float rs[NN_TILE * 3];
+  const int pair = blockIdx.y;
+  const float* qc = q + static_cast<size_t>(q_index ? q_index[pair] : pair) * n_q * 3;
+  const float* rc = r + static_cast<size_t>(r_index ? r_index[pair] : pair) * n_r * 3;
+  const int i = blockIdx.x * NN_Q + threadIdx.x;
+  const bool live = i < n_q;
+  const float x = live ? qc[i * 3] : 0.f, y = live ? qc[i * 3 + 1] : 0.f, z = live ? qc[i * 3 + 2] : 0.f;
+  float best = INFINITY;
+  for (int t0 = 0; t0 < n_r; t0 += NN_TILE) {
+    const int nt = min(NN_TILE, n_r - t0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < nt * 3; e += NN_Q) rs[e] = rc[static_cast<size_t>(t0) * 3 + e];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < nt; ++j) {
+      const float dx = x - rs[j * 3], dy = y - rs[j * 3 + 1], dz = z - rs[j * 3 + 2];
+      best = fminf(best, fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    }
+  }
+  if (live) out[static_cast<size_t>(pair) * n_q + i] = best;
+}
+
+}  // namespace
+
+cudaError_t launch_nn_dist_sq(const float* q, const int32_t* q_index, int n_q, const float* r, const int32_t* r_index,
+                              int n_r, int n_pairs, float* out, cudaStream_t stream) {
+  if (n_pairs <= 0 || n_q <= 0) return cudaSuccess;
+  dim3 grid((n_q + NN_Q - 1) / NN_Q, n_pairs);
+  nn_dist_sq_kernel<<<grid, NN_Q, 0, stream>>>(q, q_index, n_q, r, r_index, n_r, out);
+  return cudaGetLastError();
+}
+
+}  // namespace ehb

@@ -338,6 +338,18 @@ class Engine:
                                                 _dev_ptr(hat), _dev_ptr(err), _stream()))
         return hat, err
 
+    def nn_dist_sq(self, q, r, q_index=None, r_index=None, n_pairs=None):
+        """Squared 1-NN distances: q [Nq_clouds,Pq,3] vs r [Nr_clouds,Pr,3], pair i = (q[q_index[i]], r[r_index[i]])
+        (identity when the index is None) -> [n_pairs, Pq]."""
+        if n_pairs is None:
+            n_pairs = (q_index if q_index is not None else (r_index if r_index is not None else q)).shape[0]
+        out = torch.empty(n_pairs, q.shape[1], device=q.device, dtype=torch.float32)
+        if n_pairs:
+            check(self.lib.ehb_nn_dist_sq(self._h, _dev_ptr(q), _dev_ptr(q_index, torch.int32, allow_none=True), q.shape[1],
+                                          _dev_ptr(r), _dev_ptr(r_index, torch.int32, allow_none=True), r.shape[1], n_pairs,
+                                          _dev_ptr(out), _stream()))
+        return out
+
     def smpl_backward(self, x_t, betas, g_verts=None, g_joints=None, g_aa=None):
         """dL/dx_t [B,144] for the bodies of set_bodies (guide_coll's autograd.grad, egohmr.py:562)."""
         grad = torch.empty_like(x_t)

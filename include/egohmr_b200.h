@@ -229,6 +229,13 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
 int ehb_linear_f32(ehb_ctx* ctx, const float* x, const float* w_t, const float* bias, int m, int n, int k, int relu,
                    float* y, void* stream);
 
+/* The 1-nearest-neighbour squared distances behind utils/pytorch3d_chamfer_distance.py::chamfer_distance (:160-164,
+ * pytorch3d knn_points(K=1); contact score of test_egohmr.py:496-506): for pair i, every point of query cloud
+ * q[q_index ? q_index[i] : i] ([n_q][3]) against reference cloud r[r_index ? r_index[i] : i] ([n_r][3]);
+ * out [n_pairs][n_q].  Index arrays are device int32 [n_pairs] or NULL. */
+int ehb_nn_dist_sq(ehb_ctx* ctx, const float* q, const int32_t* q_index, int n_q, const float* r, const int32_t* r_index,
+                   int n_r, int n_pairs, float* out, void* stream);
+
 /* utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis: R [n][3][3] -> aa [n][3] (guide_coll / eval_coll feed
  * `full_pose` to the collision model as axis-angle, egohmr.py:495,540). */
 int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, void* stream);

@@ -27,3 +27,16 @@ def reconstruction_error(S1, S2, mask=None, avg_joint=True, dtype=np.float64):
                     for i in range(S1.shape[0])])
     re = np.sqrt(((hat - S2.astype(dtype)) ** 2).sum(axis=-1))
     return (re.mean(axis=-1) if avg_joint else re), hat
+
+
+def nn_dist_sq(x, y):
+    """Squared distance of every point of x [N,P1,3] to its nearest point of y [N,P2,3]: what
+    utils/pytorch3d_chamfer_distance.py:160-164 gets from pytorch3d's knn_points(K=1).dists[..., 0].  PARITY UNPINNED:
+    pytorch3d is a third-party dependency that is not vendored in the reference and not installed here; this is the
+    definition (brute force), evaluated in float64."""
+    x, y = x.astype(np.float64), y.astype(np.float64)
+    out = np.empty(x.shape[:2])
+    for n in range(x.shape[0]):
+        d = ((x[n][:, None, :] - y[n][None, :, :]) ** 2).sum(-1)
+        out[n] = d.min(axis=1)
+    return out

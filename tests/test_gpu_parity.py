@@ -687,6 +687,28 @@ def test_reference_checkpoint_ingestion(tmp_path, small):
     fresh.engine.close()
 
 
+def test_chamfer_contact_distances_vs_oracle(full):
+    """chamfer_distance(verts, scene) of the contact score (test_egohmr.py:496-506) on the 1-NN kernel: unreduced squared
+    nearest-neighbour distances both ways, with repeated clouds and with the shared-cloud index, against brute force."""
+    from egohmr_b200.utils.pytorch3d_chamfer_distance import chamfer_distance
+    from oracle import pose_utils as o_pu
+    rng = np.random.default_rng(17)
+    n_img, S, P1, P2 = 3, 2, 701, 2500          # ragged vs the 128-point blocks and the 1024-point tiles
+    x = rng.normal(0, 0.5, (n_img * S, P1, 3)).astype(np.float32)
+    scene = rng.normal(0, 0.7, (n_img, P2, 3)).astype(np.float32)
+    y_rep = np.repeat(scene, S, axis=0)
+    ref_x, ref_y = o_pu.nn_dist_sq(x, y_rep), o_pu.nn_dist_sq(y_rep, x)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y_rep).cuda()
+    cx, cy, cn = chamfer_distance(xt.contiguous(), yt.contiguous())
+    assert cn is None and cx.shape == (n_img * S, P1) and cy.shape == (n_img * S, P2)
+    assert np.abs(cx.cpu().numpy() - ref_x).max() < 1e-6 and np.abs(cy.cpu().numpy() - ref_y).max() < 1e-6
+    idx = torch.arange(n_img, device="cuda").repeat_interleave(S)
+    cx2, cy2, _ = chamfer_distance(xt, torch.from_numpy(scene).cuda(), y_index=idx)
+    assert torch.equal(cx2, cx) and torch.equal(cy2, cy)
+    contact = (cx.min(dim=-1)[0] < 0.02).reshape(n_img, S)            # the driver's contact flag
+    assert np.array_equal(contact.cpu().numpy(), (ref_x.min(-1) < 0.02).reshape(n_img, S))
+
+
 def test_smpl_backward_matches_autograd_oracle(full):
     """dL/dx from arbitrary upstream gradients on vertices, joints and axis-angle pose vs torch-CPU float64 autograd over
     the oracle's restatement (all three gradient paths, 11 bodies, ragged vs every tile size)."""

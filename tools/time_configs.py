@@ -19,7 +19,7 @@ from egohmr_b200 import synth  # noqa: E402
 from egohmr_b200.diffusion.model_util import create_gaussian_diffusion  # noqa: E402
 from egohmr_b200.testing import BatchedSyntheticCollision, SyntheticCollision, build_model, torch_batch  # noqa: E402
 
-which = sys.argv[1:] or ["dropin", "guided", "ddpm1000", "strong", "realpts"]
+which = sys.argv[1:] or ["dropin", "guided", "ddpm1000", "strong", "realpts", "metrics"]
 dev = "cuda:0"
 model, diffusion, sd, smpl_model, mean, std = build_model(1024, 4, T=50, respacing="ddim5")
 mk = lambda T, r: create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=r,
@@ -103,3 +103,17 @@ if "realpts" in which:
     pts = batch["scene_pcd_verts_full"].float().contiguous()
     ms_pn, _ = timed(lambda: model.engine.pointnet_forward(pts), 5, warm=1)
     emit("encoders at the real data shape: 64 images + 64 x 20000-point clouds (prepare())", 64, ms, wall, pointnet_ms=ms_pn)
+
+if "metrics" in which:
+    from egohmr_b200.utils import pose_utils
+    from egohmr_b200.utils.pytorch3d_chamfer_distance import chamfer_distance
+    verts = torch.randn(640, 6890, 3, device=dev) * 0.4 + torch.tensor([0.0, 0.0, 3.0], device=dev)
+    scene = torch_batch(synth.make_batch(105, 64, 20000), dev)["scene_pcd_verts_full"].float().contiguous()
+    idx = torch.arange(64, device=dev).repeat_interleave(10)
+    ms, wall = timed(lambda: chamfer_distance(verts, scene, y_index=idx, compute_y=False), 3, warm=1)
+    emit("contact score: 640 bodies x 6890 vertices vs 20000-point scene clouds, vertex -> scene 1-NN", 640, ms, wall)
+    ms, wall = timed(lambda: chamfer_distance(verts, scene, y_index=idx), 2, warm=0)
+    emit("chamfer_distance both ways (as the reference's driver calls it)", 640, ms, wall)
+    a, b = torch.randn(640, 24, 3, device=dev), torch.randn(640, 24, 3, device=dev)
+    ms, wall = timed(lambda: pose_utils.reconstruction_error(a, b, avg_joint=False), 20, warm=2)
+    emit("PA-MPJPE: Procrustes alignment of 640 x 24 joints", 640, ms, wall)
