@@ -78,6 +78,13 @@ if "ddpm1000" in which:
         d1000.sample_many(model, batch, 10, "")
     ms, wall = timed(run, 1)
     emit("cfg5 per-GPU share: DDPM-1000, 64 images x 10 samples (eager loop)", 640, ms, wall)
+    t0 = time.perf_counter()
+    sampler = d1000.capture_sample_many(model, batch, 10, "")
+    cap_s = time.perf_counter() - t0
+    ms, wall = timed(lambda: sampler(batch), 2, warm=1)
+    emit("cfg5 per-GPU share: DDPM-1000, 64 images x 10 samples (one CUDA graph of the 1000-step pass)", 640, ms, wall,
+         capture_s=cap_s, launches_per_replay=sampler.launches_per_replay)
+    del sampler
 
 if "strong" in which:
     batch = torch_batch(synth.make_batch(103, 32), dev)
