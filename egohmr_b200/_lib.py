@@ -79,6 +79,7 @@ SIGNATURES = {
     "ehb_denoise_step": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_denoise_step_debug": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_sampler_update": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_sampler_update_ex": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_rot6d_to_rotmat": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp]),
     "ehb_decode": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_smpl_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -95,7 +96,11 @@ SIGNATURES = {
     "ehb_smpl_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_debug_set_gemm_mode": (C.c_int, [_vp, C.c_int]),
     "ehb_debug_set_resnet_mode": (C.c_int, [_vp, C.c_int]),
+    "ehb_debug_set_conv_kc": (C.c_int, [_vp, C.c_int]),
+    "ehb_debug_gemm_hl": (C.c_int, [_vp, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
+                                    c_float_p]),
     "ehb_check_overflow": (C.c_int, [_vp, _vp]),
+    "ehb_overflow_flag_async": (C.c_int, [_vp, _vp, _vp]),
     "ehb_time_hidden_layer": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_float), _vp]),
     "ehb_time_stage": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, C.POINTER(C.c_float), _vp]),
     "ehb_debug_get_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(C.c_uint64)]),

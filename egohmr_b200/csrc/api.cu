@@ -207,7 +207,7 @@ struct ehb_ctx {
   DevBuf a01, be01, ct01, vis;
 
   // ---- chains
-  int n_bodies = 0, n_slots = 0, n_mtiles = 0;
+  int n_bodies = 0, n_slots = 0, n_mtiles = 0, max_img_of_body = 0;
   DevBuf img_of_body, slot_body, slot_cond, body_slot;
   DevBuf act_hl[2], res, mid, h_tmp;
   CUtensorMap tmA[2];
@@ -250,6 +250,9 @@ struct ehb_ctx {
   // signature of the tensor core's truncating fp32 accumulation, not of operand rounding.)
   float rn_act_scale = 64.f;
   int rn_implicit = 1;   // 3x3 convolutions as implicit GEMMs through 4-D TMA boxes (0: explicit im2col matrix)
+  // k-blocks (of 64) chained into one TMEM accumulation; longer contractions are summed chunk by chunk in fp32 registers
+  // by the epilogue warps (0 = never split).  See DESIGN.md "K9 numerics".
+  int rn_kc = 4;
   DevBuf rn_col, rn_x[2], rn_y1, rn_y2;
 
   DevBuf overflow, splitk;
@@ -441,6 +444,8 @@ int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w) {
   ctx->gcn_loaded = true;
   ctx->nl_loaded = false;   // the optional non-local block is (re)loaded separately
   ctx->n_bodies = 0;
+  ctx->n_slots = 0;
+  ctx->n_mtiles = 0;        // activation buffers / tensor maps are rebuilt for the new `hid` by the next ehb_set_bodies
   return 0;
 }
 
@@ -523,8 +528,12 @@ int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body) {
       scnd[s] = p == 0 ? 1 : 0;  // pass 0 = image-conditioned, pass 1 = image-masked
       bs[b * 2 + p] = s;
     }
-  for (int b = 0; b < n_bodies; ++b)
+  int max_img = 0;
+  for (int b = 0; b < n_bodies; ++b) {
     if (iob[b] < 0) return fail("ehb_set_bodies: negative image index");
+    max_img = std::max(max_img, iob[b]);
+  }
+  ctx->max_img_of_body = max_img;
   EHB_CUDA(ctx->img_of_body.upload(iob));
   EHB_CUDA(ctx->slot_body.upload(sb));
   EHB_CUDA(ctx->slot_cond.upload(scnd));
@@ -651,6 +660,9 @@ int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float
                            float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream_) {
   if (!ctx || !x_t || !x_prev || !x0) return fail("ehb_denoise_step: null argument");
   if (!ctx->gcn_loaded || ctx->n_bodies <= 0 || ctx->n_img <= 0) return fail("ehb_denoise_step: context not set up");
+  if (ctx->max_img_of_body >= ctx->n_img)
+    return fail("ehb_denoise_step: a body refers to image " + std::to_string(ctx->max_img_of_body) + " but ehb_set_cond holds " +
+                std::to_string(ctx->n_img) + " images");
   if (step < 0 || step >= static_cast<int>(ctx->coef.size()) || step >= ctx->n_steps_cond)
     return fail("ehb_denoise_step: step out of range of the schedule / conditioning tables");
   EHB_CUDA(cudaSetDevice(ctx->device));
@@ -662,12 +674,27 @@ int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float
   return run_output(ctx, step, x_t, noise, grad, x_prev, x0, out_cond, out_uncond, stream);
 }
 
+namespace {
+struct EventPair {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t create() {
+    cudaError_t e = cudaEventCreate(&e0);
+    return e != cudaSuccess ? e : cudaEventCreate(&e1);
+  }
+  ~EventPair() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+}  // namespace
+
 /* stage 0 = folded input layer (K2), 1 .. 2*n_blocks = hidden layers (K1), 2*n_blocks + 1 = output layer + sampler
  * update (K3); runs it `iters` times on the context's current activations and returns the mean device time. */
 int ehb_time_stage(ehb_ctx* ctx, int stage, int step, const float* x_t, float* x_prev, float* x0, int iters, float* ms,
                    void* stream_) {
   if (!ctx || !ms || !x_t || !x_prev || !x0) return fail("ehb_time_stage: null argument");
   if (!ctx->gcn_loaded || ctx->n_bodies <= 0 || ctx->n_img <= 0) return fail("ehb_time_stage: context not set up");
+  if (ctx->max_img_of_body >= ctx->n_img) return fail("ehb_time_stage: a body refers to an image ehb_set_cond does not hold");
   const int L = static_cast<int>(ctx->hidden.size());
   if (stage < 0 || stage > L + 1) return fail("ehb_time_stage: bad stage");
   if (step < 0 || step >= static_cast<int>(ctx->coef.size()) || step >= ctx->n_steps_cond)
@@ -675,10 +702,9 @@ int ehb_time_stage(ehb_ctx* ctx, int stage, int step, const float* x_t, float* x
   if (iters <= 0) return fail("ehb_time_stage: iters must be positive");
   EHB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  cudaEvent_t e0, e1;
-  EHB_CUDA(cudaEventCreate(&e0));
-  EHB_CUDA(cudaEventCreate(&e1));
-  EHB_CUDA(cudaEventRecord(e0, stream));
+  EventPair ev;   // destroyed on every return path
+  EHB_CUDA(ev.create());
+  EHB_CUDA(cudaEventRecord(ev.e0, stream));
   for (int i = 0; i < iters; ++i) {
     int rc;
     if (stage == 0) rc = run_input(ctx, step, x_t, stream);
@@ -686,12 +712,10 @@ int ehb_time_stage(ehb_ctx* ctx, int stage, int step, const float* x_t, float* x
     else rc = run_output(ctx, step, x_t, nullptr, nullptr, x_prev, x0, nullptr, nullptr, stream);
     if (rc) return 1;
   }
-  EHB_CUDA(cudaEventRecord(e1, stream));
-  EHB_CUDA(cudaEventSynchronize(e1));
+  EHB_CUDA(cudaEventRecord(ev.e1, stream));
+  EHB_CUDA(cudaEventSynchronize(ev.e1));
   float t = 0.f;
-  EHB_CUDA(cudaEventElapsedTime(&t, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  EHB_CUDA(cudaEventElapsedTime(&t, ev.e0, ev.e1));
   *ms = t / iters;
   return 0;
 }
@@ -711,6 +735,12 @@ int ehb_check_overflow(ehb_ctx* ctx, void* stream_) {
   return flag;
 }
 
+int ehb_overflow_flag_async(ehb_ctx* ctx, int32_t* host_flag, void* stream_) {
+  if (!ctx || !host_flag) return fail("ehb_overflow_flag_async: null argument");
+  EHB_CUDA(cudaMemcpyAsync(host_flag, ctx->overflow.p, sizeof(int), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream_)));
+  return 0;
+}
+
 int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* stream_) {
   if (!ctx || !ms) return fail("ehb_time_hidden_layer: null argument");
   if (!ctx->gcn_loaded || ctx->n_bodies <= 0) return fail("ehb_time_hidden_layer: context not set up");
@@ -718,32 +748,34 @@ int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* s
   if (iters <= 0) return fail("ehb_time_hidden_layer: iters must be positive");
   EHB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  cudaEvent_t e0, e1;
-  EHB_CUDA(cudaEventCreate(&e0));
-  EHB_CUDA(cudaEventCreate(&e1));
-  EHB_CUDA(cudaEventRecord(e0, stream));
+  EventPair ev;
+  EHB_CUDA(ev.create());
+  EHB_CUDA(cudaEventRecord(ev.e0, stream));
   for (int i = 0; i < iters; ++i)
     if (run_hidden(ctx, layer - 1, stream)) return 1;
-  EHB_CUDA(cudaEventRecord(e1, stream));
-  EHB_CUDA(cudaEventSynchronize(e1));
+  EHB_CUDA(cudaEventRecord(ev.e1, stream));
+  EHB_CUDA(cudaEventSynchronize(ev.e1));
   float t = 0.f;
-  EHB_CUDA(cudaEventElapsedTime(&t, e0, e1));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  EHB_CUDA(cudaEventElapsedTime(&t, ev.e0, ev.e1));
   *ms = t / iters;
+  return 0;
+}
+
+int ehb_sampler_update_ex(ehb_ctx* ctx, int step, int n, const float* x_t, const float* x0, const float* noise,
+                          const float* grad, float* x_prev, float* x0_out, void* stream_) {
+  if (!ctx || !x_t || !x0 || !x_prev) return fail("ehb_sampler_update: null argument");
+  if (step < 0 || step >= static_cast<int>(ctx->coef.size())) return fail("ehb_sampler_update: step out of range");
+  if (n <= 0) return fail("ehb_sampler_update: n must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_sampler_update(ctx->coef[step], ctx->kind, x_t, x0, noise, grad, x_prev, x0_out,
+                                      static_cast<size_t>(n) * ehb::XDIM, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += 1;
   return 0;
 }
 
 int ehb_sampler_update(ehb_ctx* ctx, int step, int n, const float* x_t, const float* x0, const float* noise,
                        const float* grad, float* x_prev, void* stream_) {
-  if (!ctx || !x_t || !x0 || !x_prev) return fail("ehb_sampler_update: null argument");
-  if (step < 0 || step >= static_cast<int>(ctx->coef.size())) return fail("ehb_sampler_update: step out of range");
-  if (n <= 0) return fail("ehb_sampler_update: n must be positive");
-  EHB_CUDA(cudaSetDevice(ctx->device));
-  EHB_CUDA(ehb::launch_sampler_update(ctx->coef[step], ctx->kind, x_t, x0, noise, grad, x_prev,
-                                      static_cast<size_t>(n) * ehb::XDIM, static_cast<cudaStream_t>(stream_)));
-  ctx->launches += 1;
-  return 0;
+  return ehb_sampler_update_ex(ctx, step, n, x_t, x0, noise, grad, x_prev, nullptr, stream_);
 }
 
 int ehb_debug_get_buffer(ehb_ctx* ctx, int which, void** ptr, uint64_t* bytes) {
@@ -1354,7 +1386,9 @@ static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, lo
                    int relu, cudaStream_t stream, const ehb_ctx::ConvPlan* c2 = nullptr, const __half* A2 = nullptr) {
   const int n_mtiles = static_cast<int>((rows + 255) / 256) * 2;
   const size_t rows_pad = static_cast<size_t>(n_mtiles) * 128;
-  const int bn = ehb::conv_gemm_tile_n(c.cout, rows, ctx->num_sms);
+  const int kb_total = (c.Kp + (c2 ? c2->Kp : 0)) / 64;
+  const bool chunked = ctx->rn_kc > 0 && kb_total > ctx->rn_kc;
+  const int bn = ehb::conv_gemm_tile_n(c.cout, rows, ctx->num_sms, chunked ? 128 : 256);
   CUtensorMap tA, tB;
   if (make_tmap_f16(&tA, A, rows_pad, 2 * static_cast<uint64_t>(c.Kp), 128)) return 1;
   if (make_tmap_f16(&tB, c.w_hl.p, c.cout, 2 * static_cast<uint64_t>(c.Kp), bn / 2)) return 1;
@@ -1379,6 +1413,7 @@ static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, lo
   p.n_mtiles = n_mtiles;
   p.n_ntiles = c.cout / bn;
   p.relu = relu;
+  p.kc = ctx->rn_kc;
   EHB_CUDA(ehb::launch_conv_gemm(tA, tB, tA2, tB2, p, ctx->num_sms, stream));
   ctx->launches += 1;
   return 0;
@@ -1399,7 +1434,8 @@ static int rn_gemm_implicit(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __ha
   const long long rows = static_cast<long long>(n) * Ho * Wo;
   int n_tiles = ((n + nb - 1) / nb) * tpi;
   n_tiles = (n_tiles + 1) / 2 * 2;
-  const int bn = ehb::conv_gemm_tile_n(c.cout, static_cast<long long>(n_tiles) * 128, ctx->num_sms);
+  const bool chunked = ctx->rn_kc > 0 && c.Kp / 64 > ctx->rn_kc;
+  const int bn = ehb::conv_gemm_tile_n(c.cout, static_cast<long long>(n_tiles) * 128, ctx->num_sms, chunked ? 128 : 256);
   CUtensorMap tA, tB;
   if (make_tmap_f16_nhwc(&tA, x, n, H, W, 2 * static_cast<uint64_t>(c.cin), nb, th, Wo, c.stride)) return 1;
   if (make_tmap_f16(&tB, c.w_hl.p, c.cout, 2 * static_cast<uint64_t>(c.Kp), bn / 2)) return 1;
@@ -1416,6 +1452,7 @@ static int rn_gemm_implicit(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __ha
   p.n_mtiles = n_tiles;
   p.n_ntiles = c.cout / bn;
   p.relu = relu;
+  p.kc = ctx->rn_kc;
   p.implicit = 1;
   p.Cin = c.cin; p.kw = c.kw; p.pad = c.pad; p.stride = c.stride;
   p.Ho = Ho; p.Wo = Wo; p.th = th; p.nb = nb; p.tiles_per_img = tpi; p.n_img = n;
@@ -1427,6 +1464,54 @@ static int rn_gemm_implicit(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __ha
 int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm) {
   if (!ctx) return fail("null ctx");
   ctx->rn_implicit = implicit_gemm ? 1 : 0;
+  return 0;
+}
+
+int ehb_debug_set_conv_kc(ehb_ctx* ctx, int kc) {
+  if (!ctx) return fail("null ctx");
+  if (kc < 0) return fail("ehb_debug_set_conv_kc: kc must be >= 0");
+  ctx->rn_kc = kc;
+  return 0;
+}
+
+int ehb_debug_gemm_hl(ehb_ctx* ctx, const float* a, const float* w, int m, int n, int k, float a_scale, float w_scale,
+                      int kc, float* out) {
+  if (!ctx || !a || !w || !out) return fail("ehb_debug_gemm_hl: null argument");
+  if (m <= 0 || n <= 0 || n % 64 || k <= 0 || k % 64) return fail("ehb_debug_gemm_hl: need m > 0, n % 64 == 0, k % 64 == 0");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  const int n_mtiles = (m + 255) / 256 * 2;
+  const size_t rows_pad = static_cast<size_t>(n_mtiles) * 128;
+  std::vector<__half> ah, wh;
+  split_hl(a, m, k, k, 0, a_scale, ah);
+  ah.resize(rows_pad * 2 * k, __half());
+  split_hl(w, n, k, k, 0, w_scale, wh);
+  std::vector<float> zero(n, 0.f);
+  DevBuf dA, dW, dB, dO;
+  EHB_CUDA(dA.upload(ah));
+  EHB_CUDA(dW.upload(wh));
+  EHB_CUDA(dB.upload(zero));
+  EHB_CUDA(dO.ensure(static_cast<size_t>(m) * n * sizeof(float)));
+  const bool chunked = kc > 0 && k / 64 > kc;
+  const int bn = ehb::conv_gemm_tile_n(n, m, ctx->num_sms, chunked ? 128 : 256);
+  CUtensorMap tA, tB;
+  if (make_tmap_f16(&tA, dA.p, rows_pad, 2 * static_cast<uint64_t>(k), 128)) return 1;
+  if (make_tmap_f16(&tB, dW.p, n, 2 * static_cast<uint64_t>(k), bn / 2)) return 1;
+  ehb::ConvGemmParams p{};
+  p.bias = dB.as<float>();
+  p.out_f32 = dO.as<float>();
+  p.overflow_flag = ctx->overflow.as<int>();
+  p.M = m;
+  p.acc_scale_inv = 1.f / (a_scale * w_scale);
+  p.act_scale = a_scale;
+  p.K = k;
+  p.Cout = n;
+  p.out_ld = 2 * n;
+  p.n_mtiles = n_mtiles;
+  p.n_ntiles = n / bn;
+  p.kc = kc;
+  EHB_CUDA(ehb::launch_conv_gemm(tA, tB, tA, tB, p, ctx->num_sms, nullptr));
+  ctx->launches += 1;
+  EHB_CUDA(cudaMemcpy(out, dO.p, static_cast<size_t>(m) * n * sizeof(float), cudaMemcpyDeviceToHost));
   return 0;
 }
 

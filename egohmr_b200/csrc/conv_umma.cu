@@ -71,6 +71,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // two operand pairs may accumulate into one TMEM accumulator: conv3(y2) + downsample(x) of a stage's first bottleneck
   // (models/resnet.py:90-94) is ONE launch, the projected identity never exists in memory
   const int KB1 = p.K / BK, KB = KB1 + p.K2 / BK;
+  constexpr bool CHUNKED = BN <= 128;   // running sums live in registers: 64 / 32 per epilogue thread
+  const int kc = (CHUNKED && p.kc > 0 && p.kc < KB) ? p.kc : KB;   // k-blocks per accumulation chunk
 
   if (warp == TMA_WARP && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -155,35 +157,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int u = unit0; u < n_units; u += unit_step) {
-        ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
-        ptx::tc_fence_after_sync();
-        const uint32_t tacc = tmem_base + as * BN;
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::mbar_wait(&bars->full[stage], phase);
+        // chunked accumulation: every `kc` k-blocks the accumulator is handed to the epilogue warps, which sum the chunks
+        // in fp32 registers (round-to-nearest) — the tensor core's own fp32 accumulation truncates, a bias that grows
+        // with the number of MMAs chained into one accumulator (DESIGN.md, K9 numerics)
+        for (int kb0 = 0; kb0 < KB; kb0 += kc) {
+          ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
           ptx::tc_fence_after_sync();
-          const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t tacc = tmem_base + as * BN;
+          const int kend = min(KB, kb0 + kc);
+          for (int kb = kb0; kb < kend; ++kb) {
+            ptx::mbar_wait(&bars->full[stage], phase);
+            ptx::tc_fence_after_sync();
+            const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
 #pragma unroll
-          for (int ks = 0; ks < BK / UMMA_K; ++ks) {
-            const uint32_t koff = ks * UMMA_K * 2;
-            const uint64_t a_hi = ptx::make_kmajor_desc<128>(sa + koff);
-            const uint64_t a_lo = ptx::make_kmajor_desc<128>(sa + A_BYTES + koff);
-            const uint64_t b_hi = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + koff);
-            const uint64_t b_lo = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + B_BYTES + koff);
-            ptx::umma_f16_2sm_elect(tacc, a_hi, b_hi, idesc, (kb | ks) != 0 ? 1u : 0u);
-            ptx::umma_f16_2sm_elect(tacc, a_hi, b_lo, idesc, 1u);
-            ptx::umma_f16_2sm_elect(tacc, a_lo, b_hi, idesc, 1u);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint32_t koff = ks * UMMA_K * 2;
+              const uint64_t a_hi = ptx::make_kmajor_desc<128>(sa + koff);
+              const uint64_t a_lo = ptx::make_kmajor_desc<128>(sa + A_BYTES + koff);
+              const uint64_t b_hi = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + koff);
+              const uint64_t b_lo = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + B_BYTES + koff);
+              ptx::umma_f16_2sm_elect(tacc, a_hi, b_hi, idesc, (kb > kb0 || ks != 0) ? 1u : 0u);
+              ptx::umma_f16_2sm_elect(tacc, a_hi, b_lo, idesc, 1u);
+              ptx::umma_f16_2sm_elect(tacc, a_lo, b_hi, idesc, 1u);
+            }
+            ptx::umma_commit_2sm_mc_elect(&bars->empty[stage], 0b11);
+            if (kb == kend - 1) ptx::umma_commit_2sm_mc_elect(&bars->tfull[as], 0b11);
+            __syncwarp();
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-          ptx::umma_commit_2sm_mc_elect(&bars->empty[stage], 0b11);
-          if (kb == KB - 1) ptx::umma_commit_2sm_mc_elect(&bars->tfull[as], 0b11);
-          __syncwarp();
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
+          if (++as == 2) {
+            as = 0;
+            aphase ^= 1;
           }
-        }
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
         }
       }
     }
@@ -197,8 +205,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float inv_act = 1.f / p.act_scale;
     uint8_t* scratch = scratch_s + warp * EPI_SCRATCH_BYTES;
     int as = 0;
-    uint32_t aphase = 0;
+    uint32_t aphase = 0, tpar = 0;
     float amax = 0.f;
+    const int n_chunks = (KB + kc - 1) / kc;
+    float acc[CHUNKED ? HALF : 1];        // fp32 running sum of the first n_chunks - 1 accumulation chunks
     for (int u = unit0; u < n_units; u += unit_step) {
       const int n_tile = u % p.n_ntiles;
       const int tile = (u / p.n_ntiles) * 2 + static_cast<int>(rank);
@@ -213,7 +223,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long row = tile_first + q * 32 + lane;
       const bool valid = q * 32 + lane < tile_rows;
       const long long row0w = row - lane;                  // first row of this warp's 32
-      float* addv = addv_s + as * 256;
+      float* addv = addv_s + tpar * 256;
+      tpar ^= 1;
       if (et < BN) addv[et] = __ldg(p.bias + n_tile * BN + et);
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // the identity block of the first chunk is requested before the accumulator is awaited, every further chunk's
@@ -225,10 +236,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         warp_issue_rows_64B(raw_h, p.res_hl + row0w * p.out_ld + cg0, p.out_ld, rows_valid, lane);
         warp_issue_rows_64B(raw_l, p.res_hl + row0w * p.out_ld + p.Cout + cg0, p.out_ld, rows_valid, lane);
       }
+      if constexpr (CHUNKED) {
+        if (n_chunks > 1) {
+#pragma unroll
+          for (int c = 0; c < HALF; ++c) acc[c] = 0.f;
+          for (int c0 = 0; c0 + 1 < n_chunks; ++c0) {
+            ptx::mbar_wait(&bars->tfull[as], aphase);
+            ptx::tc_fence_after_sync();
+            const uint32_t tr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * HALF;
+#pragma unroll
+            for (int ch = 0; ch < CHUNKS; ++ch) {
+              float v[32];
+              ptx::tmem_ld_32x32b_x32(tr + ch * 32, v);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) acc[ch * 32 + c] += v[c];
+            }
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) ptx::mbar_arrive(&bars->tempty[as]);
+              else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tempty[as]), 0));
+            }
+            if (++as == 2) {
+              as = 0;
+              aphase ^= 1;
+            }
+          }
+        }
+      }
       ptx::mbar_wait(&bars->tfull[as], aphase);
       ptx::tc_fence_after_sync();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * HALF;
-#pragma unroll 1
+#pragma unroll(CHUNKED ? CHUNKS : 1)
       for (int ch = 0; ch < CHUNKS; ++ch) {
         float v[32];
         ptx::tmem_ld_32x32b_x32(trow + ch * 32, v);
@@ -239,6 +279,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (lane == 0) {
             if (leader) ptx::mbar_arrive(&bars->tempty[as]);
             else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tempty[as]), 0));
+          }
+        }
+        if constexpr (CHUNKED) {
+          if (n_chunks > 1) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] += acc[ch * 32 + c];
           }
         }
         const int ct = col_half * HALF + ch * 32;          // column within the tile
@@ -339,7 +385,7 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
 // N tile (256 / 128 / 64 output channels) of one layer: the one with the lowest estimated time = rounds of work units
 // over the CTA pairs x relative cost of a unit (narrower tiles re-read A and run the MMA less efficiently).  Small-M
 // layers (the 14 x 14 and 7 x 7 stages) trade MMA width for parallelism.
-int conv_gemm_tile_n(int cout, long long rows, int num_sms) {
+int conv_gemm_tile_n(int cout, long long rows, int num_sms, int max_bn) {
   static float cost[3] = {1.0f, 0.6f, 0.4f};   // swept on B200: 2.83 ms for ResNet-50 x 64 images (always-largest tile: 2.98)
   static bool init = false;
   if (!init) {   // bring-up override: EHB_CONV_COST="c256,c128,c64"
@@ -352,7 +398,7 @@ int conv_gemm_tile_n(int cout, long long rows, int num_sms) {
   int best = 0;
   float best_t = 1e30f;
   for (int i = 0; i < 3; ++i) {
-    if (cout % bns[i]) continue;
+    if (cout % bns[i] || bns[i] > max_bn) continue;
     const long long units = m_units * (cout / bns[i]);
     const float t = static_cast<float>((units + pairs - 1) / pairs) * cost[i];
     if (t < best_t) {

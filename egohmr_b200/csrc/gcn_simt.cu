@@ -177,12 +177,21 @@ __global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ 
   if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);
 }
 
-// One element of the reverse-diffusion update, in the reference's fp32 op order with contraction disabled.
-__device__ __forceinline__ float sampler_update_one(const StepCoef& coef, int kind, float x, float x0, const float* noise,
+// One element of the reverse-diffusion update, in the reference's fp32 op order with contraction disabled.  `x0` is
+// in/out: the guided DDIM step (ddim_sample_with_grad, gaussian_diffusion.py:579-592) replaces pred_xstart.
+__device__ __forceinline__ float sampler_update_one(const StepCoef& coef, int kind, float x, float& x0, const float* noise,
                                                     const float* grad, size_t idx) {
   if (kind == SAMPLER_DDIM) {
-    const float eps = __fdiv_rn(__fsub_rn(__fmul_rn(coef.c[0], x), x0), coef.c[1]);
-    return __fadd_rn(__fmul_rn(x0, coef.c[2]), __fmul_rn(coef.c[3], eps));
+    const float cx = __fmul_rn(coef.c[0], x);
+    float eps = __fdiv_rn(__fsub_rn(cx, x0), coef.c[1]);                       // _predict_eps_from_xstart (:286-290)
+    if (grad && coef.c[5] != 0.f) {
+      eps = __fsub_rn(eps, __fmul_rn(__fmul_rn(coef.c[5], grad[idx]), 1.0f));  // eps - sqrt(1 - alpha_bar) * grad * scale
+      x0 = __fsub_rn(cx, __fmul_rn(coef.c[1], eps));                           // _predict_xstart_from_eps (:277-283)
+      eps = __fdiv_rn(__fsub_rn(cx, x0), coef.c[1]);
+    }
+    const float mean = __fadd_rn(__fmul_rn(x0, coef.c[2]), __fmul_rn(coef.c[3], eps));
+    // nonzero_mask * sigma * noise (:552-555); sigma = 0 for eta = 0, where the draw is not even read
+    return (noise && coef.c[4] != 0.f) ? __fadd_rn(mean, __fmul_rn(coef.c[4], noise[idx])) : mean;
   }
   float mean = __fadd_rn(__fmul_rn(coef.c[0], x0), __fmul_rn(coef.c[1], x));
   if (grad) mean = __fadd_rn(mean, __fmul_rn(coef.c[3], grad[idx]));
@@ -192,9 +201,14 @@ __device__ __forceinline__ float sampler_update_one(const StepCoef& coef, int ki
 
 __global__ void sampler_update_kernel(const StepCoef coef, int kind, const float* __restrict__ x_t,
                                       const float* __restrict__ x0, const float* __restrict__ noise,
-                                      const float* __restrict__ grad, float* __restrict__ x_prev, size_t n) {
+                                      const float* __restrict__ grad, float* __restrict__ x_prev,
+                                      float* __restrict__ x0_out, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) x_prev[i] = sampler_update_one(coef, kind, x_t[i], x0[i], noise, grad, i);
+  if (i < n) {
+    float v0 = x0[i];
+    x_prev[i] = sampler_update_one(coef, kind, x_t[i], v0, noise, grad, i);
+    if (x0_out) x0_out[i] = v0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K3
@@ -272,8 +286,8 @@ __global__ void __launch_bounds__(256, 2) gcn_output_fallback_kernel(const __gri
   const size_t idx = static_cast<size_t>(body) * XDIM + e;
   if (p.out_cond) p.out_cond[idx] = out[0];
   if (p.out_uncond) p.out_uncond[idx] = out[1];
-  p.x0[idx] = x0;
   p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
+  p.x0[idx] = x0;
 }
 
 // ------------------------------------------------------------------------------------------------ K3 (bulk-staged)
@@ -412,12 +426,12 @@ __global__ void __launch_bounds__((K3_CONSUMERS + 1) * 32, 1) gcn_output_kernel(
         out[pass] = acc + p.bias[d];
       }
       const int img = p.img_of_body[body];
-      const float x0 = p.diffuse_fuse ? (p.vis[img * NJ + j] ? out[0] : out[1]) : out[0];
+      float x0 = p.diffuse_fuse ? (p.vis[img * NJ + j] ? out[0] : out[1]) : out[0];
       const size_t idx = static_cast<size_t>(body) * XDIM + e;
       if (p.out_cond) p.out_cond[idx] = out[0];
       if (p.out_uncond) p.out_uncond[idx] = out[1];
-      p.x0[idx] = x0;
       p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
+      p.x0[idx] = x0;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");   // hs is rewritten by the next body's first chunk
   }
@@ -606,11 +620,11 @@ cudaError_t launch_nonlocal_residual(const NonLocalParams& p, cudaStream_t strea
 }
 
 cudaError_t launch_sampler_update(const StepCoef& coef, int kind, const float* x_t, const float* x0,
-                                  const float* noise, const float* grad, float* x_prev, size_t n,
+                                  const float* noise, const float* grad, float* x_prev, float* x0_out, size_t n,
                                   cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   sampler_update_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(coef, kind, x_t, x0, noise, grad,
-                                                                                    x_prev, n);
+                                                                                    x_prev, x0_out, n);
   return cudaGetLastError();
 }
 

@@ -103,8 +103,9 @@ cudaError_t launch_nonlocal_attention(const NonLocalParams& p, cudaStream_t stre
 cudaError_t launch_nonlocal_residual(const NonLocalParams& p, cudaStream_t stream);
 
 // Per-step sampler coefficients (host-computed in fp32 exactly as the reference's torch ops would):
-//  DDIM (eta=0):  c[0]=sqrt_recip_alphas_cumprod, c[1]=sqrt_recipm1_alphas_cumprod, c[2]=sqrt(alpha_bar_prev),
-//                 c[3]=sqrt(1-alpha_bar_prev)
+//  DDIM:          c[0]=sqrt_recip_alphas_cumprod, c[1]=sqrt_recipm1_alphas_cumprod, c[2]=sqrt(alpha_bar_prev),
+//                 c[3]=sqrt(1-alpha_bar_prev-sigma^2), c[4]=(t!=0)*sigma (eta), c[5]=sqrt(1-alpha_bar) on the steps where
+//                 ddim_sample_with_grad applies the collision gradient (respaced t <= 3), else 0
 //  DDPM:          c[0]=posterior_mean_coef1, c[1]=posterior_mean_coef2, c[2]=(t!=0)*exp(0.5*log_var),
 //                 c[3]=gradient scale (cond_grad_weight*variance, or cond_grad_weight*0.01), 0 when unguided
 struct StepCoef {
@@ -133,9 +134,10 @@ struct OutputLayerParams {
   int C, n_bodies, diffuse_fuse;
 };
 cudaError_t launch_gcn_output(const OutputLayerParams& p, int num_sms, cudaStream_t stream);
-// x_prev = update(x_t, x0, noise, grad) elementwise over n floats (same arithmetic as the tail of launch_gcn_output)
+// x_prev = update(x_t, x0, noise, grad) elementwise over n floats (same arithmetic as the tail of launch_gcn_output);
+// x0_out (optional) receives the pred_xstart the step ends with (the guided DDIM step re-derives it)
 cudaError_t launch_sampler_update(const StepCoef& coef, int kind, const float* x_t, const float* x0,
-                                  const float* noise, const float* grad, float* x_prev, size_t n,
+                                  const float* noise, const float* grad, float* x_prev, float* x0_out, size_t n,
                                   cudaStream_t stream);
 
 // ---- SMPL ----
@@ -215,6 +217,8 @@ struct ConvGemmParams {
   int Cout, out_ld;       // out_ld = 2 * Cout (halves per row)
   int n_mtiles, n_ntiles; // 128-row tiles (even) and Cout / tile_n
   int relu;
+  int kc;                 // k-blocks (of 64) chained into one TMEM accumulation before the epilogue warps take the partial
+                          // sum over in fp32 registers; <= 0 or >= K/64: the whole K in one accumulator (tile_n <= 128 only)
   // Implicit-GEMM mode (implicit != 0): tmA is a 4-D map over the NHWC input [N][H][W][hi(Cin) | lo(Cin)] and the A tile
   // of k-block (tap, channel chunk) is the TMA box of the tile's output pixels shifted by the tap — the convolution's
   // zero padding is TMA's out-of-bounds fill, no im2col matrix exists.  An M tile is `nb` images x `th` full output
@@ -223,7 +227,7 @@ struct ConvGemmParams {
   int Cin, kw, pad, stride;   // K = kh * kw * Cin, k = (ky * kw + kx) * Cin + c
   int Ho, Wo, th, nb, tiles_per_img, n_img;
 };
-int conv_gemm_tile_n(int cout, long long rows, int num_sms);   // 256, 128 or 64 output channels per tile
+int conv_gemm_tile_n(int cout, long long rows, int num_sms, int max_bn = 256);   // 256, 128 or 64 output channels per tile
 cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
                              const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 // im2col of an NHWC fp16 hi/lo activation [N][H][W][hi(C) | lo(C)] for a KHxKW / stride / pad convolution:

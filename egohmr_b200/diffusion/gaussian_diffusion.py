@@ -82,19 +82,23 @@ class GaussianDiffusion:
             self.timestep_map = list(range(self.num_timesteps))
 
     # ------------------------------------------------------------------ per-step scalar coefficients
-    def step_coefficients(self, kind, guided=False, cond_grad_weight=1.0, ddim_guided=False):
+    def step_coefficients(self, kind, guided=False, cond_grad_weight=1.0, eta=0.0):
         """[num_timesteps, 8] fp32 rows for `ehb_set_schedule`.  Every scalar is produced by the same fp32 torch ops the
         reference applies to its [bs,144]-expanded coefficient tensors, so the device update is bit-compatible."""
         f = lambda a: th.from_numpy(np.asarray(a)).float()
         T = self.num_timesteps
         c = th.zeros(T, 8)
         if kind == self.DDIM:
+            t = th.arange(T)
             ab, abp = f(self.alphas_cumprod), f(self.alphas_cumprod_prev)
-            sigma = 0.0 * th.sqrt((1 - abp) / (1 - ab)) * th.sqrt(1 - ab / abp)  # eta = 0  (:541-545)
+            sigma = eta * th.sqrt((1 - abp) / (1 - ab)) * th.sqrt(1 - ab / abp)  # :541-545
             c[:, 0] = f(self.sqrt_recip_alphas_cumprod)
             c[:, 1] = f(self.sqrt_recipm1_alphas_cumprod)
             c[:, 2] = th.sqrt(abp)
             c[:, 3] = th.sqrt(1 - abp - sigma ** 2)
+            c[:, 4] = (t != 0).float() * sigma                                    # :552-555 (0 for eta = 0: noise unused)
+            if guided:  # ddim_sample_with_grad (:559-614): eps -= sqrt(1 - alpha_bar) * grad for respaced t <= 3
+                c[:, 5] = th.where(t <= 3, (1 - ab).sqrt(), th.zeros(T))
         else:
             t = th.arange(T)
             c[:, 0] = f(self.posterior_mean_coef1)
@@ -119,10 +123,13 @@ class GaussianDiffusion:
                 + _extract_into_tensor(self.sqrt_one_minus_alphas_cumprod, t, x_start.shape) * noise)
 
     def _scale_timesteps(self, t):
+        """gaussian_diffusion.py:292-295."""
         return t.float() * (1000.0 / self.num_timesteps) if self.rescale_timesteps else t
 
     def _map_timesteps(self, t):
-        return t
+        """What the model receives for sampler index t: identity here; SpacedDiffusion maps to the original timestep first
+        and only then rescales (respace.py:124-129)."""
+        return self._scale_timesteps(t)
 
     # ------------------------------------------------------------------ model evaluation
     @staticmethod
@@ -134,7 +141,7 @@ class GaussianDiffusion:
         B = x.shape[0]
         assert t.shape == (B,)
         batch["x_t"] = x
-        output_dict = model(batch, self._map_timesteps(self._scale_timesteps(t)))
+        output_dict = model(batch, self._map_timesteps(t))
         pred_xstart = output_dict["pred_x_start"]
         var = _extract_into_tensor(self.posterior_variance, t, x.shape)
         logvar = _extract_into_tensor(self.posterior_log_variance_clipped, t, x.shape)
@@ -143,22 +150,27 @@ class GaussianDiffusion:
         return {"mean": mean, "variance": var, "log_variance": logvar, "pred_xstart": pred_xstart,
                 "other_outputs": output_dict}
 
-    def _generic_step(self, kind, model, batch, x, t, guided, cond_grad_weight):
+    GUIDE_MAX_T = {0: 3, 1: 10}   # respaced-index threshold of the guided variants: ddim :579, ddpm :378
+
+    def _generic_step(self, kind, model, batch, x, t, guided, cond_grad_weight, eta=0.0, noise_fn=None):
         """One reverse step for a foreign model: model call + CUDA sampler update."""
         if not x.is_cuda:
             raise RuntimeError("egohmr_b200 samplers run on CUDA tensors only (no CPU fallback)")
         i = int(t[0])
         out = self.p_mean_variance(model, batch, x, t)
-        noise = th.randn_like(x)
+        noise = (noise_fn or th.randn_like)(x)
         grad = None
-        if guided and kind == self.DDPM and i <= 10:
+        if guided and i <= self.GUIDE_MAX_T[kind]:
             grad = model.guide_coll(batch, out["other_outputs"], t, compute_grad="x_t").float().contiguous()
         eng = _generic_engine(x.device)
-        eng.set_schedule(kind, self.step_coefficients(kind, guided, cond_grad_weight))
+        eng.set_schedule(kind, self.step_coefficients(kind, guided, cond_grad_weight, eta))
         x_prev = th.empty_like(x, dtype=th.float32)
-        eng.sampler_update(i, x.float().contiguous(), out["pred_xstart"].float().contiguous(),
-                           noise.float().contiguous() if kind == self.DDPM else None, grad, x_prev)
-        return {"sample": x_prev, "pred_xstart": out["pred_xstart"], "other_outputs": out["other_outputs"]}
+        x0 = out["pred_xstart"].float().contiguous()
+        x0_out = th.empty_like(x0) if (kind == self.DDIM and grad is not None) else None
+        eng.sampler_update(i, x.float().contiguous(), x0,
+                           noise.float().contiguous() if (kind == self.DDPM or eta != 0.0) else None, grad, x_prev, x0_out)
+        return {"sample": x_prev, "pred_xstart": x0_out if x0_out is not None else out["pred_xstart"],
+                "other_outputs": out["other_outputs"]}
 
     def p_sample(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, cond_grad_weight=0.0):
         """gaussian_diffusion.py:298-337."""
@@ -169,14 +181,20 @@ class GaussianDiffusion:
         return self._generic_step(self.DDPM, model, batch, x, t, True, cond_grad_weight)
 
     def ddim_sample(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, eta=0.0):
-        """gaussian_diffusion.py:511-556 (eta = 0, the only value the reference passes, :770)."""
-        if eta != 0.0:
-            raise NotImplementedError("eta != 0 is never used by the reference (val_losses passes eta=0.0)")
-        return self._generic_step(self.DDIM, model, batch, x, t, False, 0.0)
+        """gaussian_diffusion.py:511-556."""
+        return self._generic_step(self.DDIM, model, batch, x, t, False, 0.0, eta)
+
+    def ddim_sample_with_grad(self, model, batch, x, t, clip_denoised=True, denoised_fn=None, eta=0.0):
+        """gaussian_diffusion.py:559-614: for respaced t <= 3 the collision gradient shifts eps, pred_xstart is
+        re-derived from it, then the DDIM update runs on the shifted prediction."""
+        return self._generic_step(self.DDIM, model, batch, x, t, True, 1.0, eta)
 
     # ------------------------------------------------------------------ loops
     def _loop(self, kind, model, batch, shape, noise, device, progress, skip_timesteps, init_data, cond_fn_with_grad,
-              cond_grad_weight):
+              cond_grad_weight, eta=0.0, noise_fn=None):
+        """`noise_fn(x) -> noise like x`: source of the per-step draws (default `th.randn_like`, the reference's :331 /
+        :373 / :547); `sample_many(noise=...)` and the graphed sampler pass a feed of pre-drawn noise here."""
+        noise_fn = noise_fn or th.randn_like
         if device is None:
             device = next(model.parameters()).device
         assert isinstance(shape, (tuple, list))
@@ -191,23 +209,23 @@ class GaussianDiffusion:
             from tqdm.auto import tqdm
             indices = tqdm(indices)
         guided = bool(cond_fn_with_grad)
-        if kind == self.DDIM and guided:
-            raise NotImplementedError("ddim_sample_with_grad: the reference documents DDIM as incompatible with the "
-                                      "collision guidance (README.md:145-148)")
+        guide_max_t = self.GUIDE_MAX_T[kind]
         if not self._is_fused(model):
             for i in indices:
                 t = th.tensor([i] * shape[0], device=device)
                 with th.no_grad():
-                    out = self._generic_step(kind, model, batch, data, t, guided, cond_grad_weight)
+                    out = self._generic_step(kind, model, batch, data, t, guided, cond_grad_weight, eta, noise_fn)
                     yield out
                     data = out["sample"]
             return
         # ---- fused path
         with th.no_grad():
             eng = model.engine
+            model.poll_overflow()      # a deferred operand-overflow report of an earlier call surfaces here
             cond = model.prepare(batch, num_samples=getattr(self, "_num_samples", 1))
             model.set_timesteps(self.timestep_map)
-            eng.set_schedule(kind, self.step_coefficients(kind, guided, cond_grad_weight))
+            eng.set_schedule(kind, self.step_coefficients(kind, guided, cond_grad_weight, eta))
+            use_noise = kind == self.DDPM or eta != 0.0
             x = data.float().contiguous()
             assert x.shape[0] == eng.n_bodies, (x.shape, eng.n_bodies)
             x_next, x0 = th.empty_like(x), th.empty_like(x)
@@ -215,22 +233,17 @@ class GaussianDiffusion:
             last = indices[-1] if not progress else 0
             for i in indices:
                 batch["x_t"] = x  # p_mean_variance mutates the caller's dict (:256)
-                step_noise = th.randn_like(x)  # drawn on every step, like the reference (:331, :547): same RNG stream
+                step_noise = noise_fn(x)  # drawn on every step, like the reference (:331, :547): same RNG stream
                 grad = None
-                if guided and i <= 10:
+                if guided and i <= guide_max_t:
                     t = th.full((x.shape[0],), i, device=device, dtype=th.long)
                     grad = model.guide_coll(batch, {"pred_smpl_params": {"betas": cond["betas_img"][cond["img_of_body"]]}},
                                             t, compute_grad="x_t").float().contiguous()
-                eng.denoise_step(i, x, step_noise if kind == self.DDPM else None, grad, x_next, x0)
+                eng.denoise_step(i, x, step_noise if use_noise else None, grad, x_next, x0)
                 is_last = i == last
                 other = model.assemble_outputs(batch, x0, cond) if is_last else {"pred_x_start": x0}
-                if is_last and getattr(model, "check_overflow_each_call", True) and not th.cuda.is_current_stream_capturing():
-                    # the fp16 hi/lo operands have a finite range (|activation| < 8188 in the GCN, < 1023 in the image
-                    # encoder); a checkpoint that exceeds it must fail loudly, not return Inf/NaN.  One flag read-back
-                    # per sampling call (the caller consumes the outputs on the host right after anyway).
-                    if eng.check_overflow():
-                        raise FloatingPointError("fp16 operand overflow inside the tensor-core kernels: an activation left "
-                                                 "the representable range of the hi/lo operand format (see DESIGN.md, K1 numerics)")
+                if is_last:
+                    model.note_sampling_call_done()    # operand-range check: sync read-back or deferred (EgoHMR.overflow_check)
                 yield {"sample": x_next, "pred_xstart": x0, "other_outputs": other}
                 if not is_last:
                     x, x_next = x_next, th.empty_like(x)
@@ -261,10 +274,8 @@ class GaussianDiffusion:
                                      device=None, progress=False, eta=0.0, skip_timesteps=0, init_data=None,
                                      cond_fn_with_grad=False):
         """gaussian_diffusion.py:670-718."""
-        if eta != 0.0:
-            raise NotImplementedError("eta != 0 is never used by the reference (val_losses passes eta=0.0)")
         yield from self._loop(self.DDIM, model, batch, shape, noise, device, progress, skip_timesteps, init_data,
-                              cond_fn_with_grad, 1.0)
+                              cond_fn_with_grad, 1.0, eta)
 
     def ddim_sample_loop(self, model, batch, shape, noise=None, clip_denoised=True, denoised_fn=None, device=None,
                          progress=False, eta=0.0, skip_timesteps=0, init_data=None, cond_fn_with_grad=False):
@@ -303,27 +314,18 @@ class GaussianDiffusion:
         the reference driver's sequential loop (test_egohmr.py:251-255).  Returns the final output dict with a leading
         [bs*num_samples] axis.  `noise`: optional [n_steps+1, bs*S, 144] pre-drawn noise (index 0 = initial x_T)."""
         model.validation_setup()
+        if hasattr(model, "invalidate"):
+            model.invalidate()   # a sample_many call is a batch boundary: never reuse cached conditioning across calls
         bs = batch["img"].shape[0]
         shape = [bs * num_samples, 144]
         kind = self.DDPM if timestep_respacing == "" else self.DDIM
+        feed = _NoiseFeed(noise) if noise is not None else None
         self._num_samples = num_samples
         try:
-            if noise is not None:
-                feed = _NoiseFeed(noise)
-                old = th.randn_like
-                th.randn_like = feed.randn_like
-                try:
-                    final = None
-                    for final in self._loop(kind, model, batch, shape, feed.initial(), None, False, 0, None,
-                                            cond_fn_with_grad, cond_grad_weight):
-                        pass
-                finally:
-                    th.randn_like = old
-            else:
-                final = None
-                for final in self._loop(kind, model, batch, shape, None, None, False, 0, None, cond_fn_with_grad,
-                                        cond_grad_weight):
-                    pass
+            final = None
+            for final in self._loop(kind, model, batch, shape, feed.initial() if feed else None, None, False, 0, None,
+                                    cond_fn_with_grad, cond_grad_weight, 0.0, feed.randn_like if feed else None):
+                pass
         finally:
             self._num_samples = 1
         out = final["other_outputs"]

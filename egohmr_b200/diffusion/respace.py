@@ -47,7 +47,15 @@ class SpacedDiffusion(GaussianDiffusion):
         kwargs["betas"] = np.array(new_betas)
         super().__init__(**kwargs)
 
+    def _scale_timesteps(self, t):
+        """respace.py:111-113: scaling is done by the wrapped model, after the index map."""
+        return t
+
     def _map_timesteps(self, t):
-        """_WrappedModel.__call__ (respace.py:124-129): respaced index -> original timestep."""
+        """_WrappedModel.__call__ (respace.py:124-129): respaced index -> original timestep, then (if rescale_timesteps)
+        scaled by 1000 / original_num_steps."""
         import torch
-        return torch.tensor(self.timestep_map, device=t.device, dtype=t.dtype)[t]
+        new_ts = torch.tensor(self.timestep_map, device=t.device, dtype=t.dtype)[t]
+        if self.rescale_timesteps:
+            new_ts = new_ts.float() * (1000.0 / self.original_num_steps)
+        return new_ts

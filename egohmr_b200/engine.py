@@ -272,10 +272,10 @@ class Engine:
                                                   _dev_ptr(out_cond, allow_none=True),
                                                   _dev_ptr(out_uncond, allow_none=True), _stream()))
 
-    def sampler_update(self, step, x_t, x0, noise, grad, x_prev):
-        check(self.lib.ehb_sampler_update(self._h, int(step), x_t.shape[0], _dev_ptr(x_t), _dev_ptr(x0),
-                                          _dev_ptr(noise, allow_none=True), _dev_ptr(grad, allow_none=True),
-                                          _dev_ptr(x_prev), _stream()))
+    def sampler_update(self, step, x_t, x0, noise, grad, x_prev, x0_out=None):
+        check(self.lib.ehb_sampler_update_ex(self._h, int(step), x_t.shape[0], _dev_ptr(x_t), _dev_ptr(x0),
+                                             _dev_ptr(noise, allow_none=True), _dev_ptr(grad, allow_none=True),
+                                             _dev_ptr(x_prev), _dev_ptr(x0_out, allow_none=True), _stream()))
 
     def decode(self, x0, betas, want_smpl=True):
         """x0 [B,144] (normalised) -> pose6d [B,144], R [B,24,3,3], verts [B,V,3] | None, joints [B,24+E,3] | None."""
@@ -371,8 +371,28 @@ class Engine:
     def set_resnet_mode(self, implicit_gemm):
         check(self.lib.ehb_debug_set_resnet_mode(self._h, 1 if implicit_gemm else 0))
 
+    def set_conv_kc(self, kc):
+        """k-blocks (x64 operand columns) per tensor-memory accumulation chunk of the ResNet convolution GEMMs (0 = whole K)."""
+        check(self.lib.ehb_debug_set_conv_kc(self._h, int(kc)))
+
+    def debug_gemm_hl(self, a, w, a_scale=1.0, w_scale=1.0, kc=0):
+        """out[m,n] = a[m,k] . w[n,k]^T through the convolution GEMM primitive (numpy in / out; unit tests of its numerics)."""
+        a, w = f32(a), f32(w)
+        m, k = a.shape
+        n = w.shape[0]
+        assert w.shape[1] == k
+        out = np.empty((m, n), np.float32)
+        check(self.lib.ehb_debug_gemm_hl(self._h, fptr(a), fptr(w), m, n, k, float(a_scale), float(w_scale), int(kc),
+                                         fptr(out)))
+        return out
+
     def check_overflow(self):
         return bool(self.lib.ehb_check_overflow(self._h, _stream()))
+
+    def overflow_flag_async(self, host_flag):
+        """Enqueue a copy of the fp16-overflow flag into `host_flag` (pinned int32 tensor) on the current stream."""
+        assert host_flag.is_pinned() and host_flag.dtype == torch.int32
+        check(self.lib.ehb_overflow_flag_async(self._h, C.c_void_p(host_flag.data_ptr()), _stream()))
 
     def time_stage(self, stage, step, x_t, iters):
         """Mean device ms of one stage of a reverse step (0 = K2 input layer, 1..8 = K1, 9 = K3 output + update)."""

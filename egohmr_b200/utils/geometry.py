@@ -12,10 +12,13 @@ def _engine_for(device):
     return _default_engine[idx]
 
 
-def rot6d_to_rotmat(x, rot6d_mode="diffusion", engine=None):
-    """utils/geometry.py:47-66 on the GPU (K4).  x: [..., 6k] CUDA tensor -> [N, 3, 3]."""
+def rot6d_to_rotmat(x, rot6d_mode="prohmr", engine=None):
+    """utils/geometry.py:47-66 on the GPU (K4).  x: [..., 6k] CUDA tensor -> [N, 3, 3].  Default mode 'prohmr' like the
+    reference; every EgoHMR call site passes 'diffusion' explicitly (egohmr.py:260,529)."""
     if rot6d_mode == "prohmr":
         x = x.reshape(-1, 2, 3).permute(0, 2, 1)
+    elif rot6d_mode != "diffusion":
+        raise ValueError(f"rot6d_mode must be 'prohmr' or 'diffusion', got {rot6d_mode!r}")
     x6 = x.reshape(-1, 6).float().contiguous()
     if not x6.is_cuda:
         raise RuntimeError("rot6d_to_rotmat: CUDA tensor required (no CPU fallback)")

@@ -111,7 +111,7 @@ int ehb_smpl_load(ehb_ctx* ctx, const ehb_smpl_model* m);
 int ehb_set_norm(ehb_ctx* ctx, const float* mean, const float* std);
 
 /* GaussianDiffusion.__init__ tables (diffusion/gaussian_diffusion.py:122-169) reduced to what one sampler update
- * needs.  kind 0 = ddim_sample (:511-556, eta = 0), 1 = p_sample / p_sample_with_grad (:298-388).
+ * needs.  kind 0 = ddim_sample / ddim_sample_with_grad (:511-614, any eta), 1 = p_sample / p_sample_with_grad (:298-388).
  * coef is HOST [n_steps][8] floats, row i = coefficients of respaced timestep i (see DESIGN.md "sampler update"). */
 int ehb_set_schedule(ehb_ctx* ctx, int kind, int n_steps, const float* coef);
 
@@ -147,6 +147,10 @@ int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float
  * denoiser.  All pointers [n][144]; noise / grad may be NULL. */
 int ehb_sampler_update(ehb_ctx* ctx, int step, int n, const float* x_t, const float* x0, const float* noise,
                        const float* grad, float* x_prev, void* stream);
+/* Same; x0_out [n][144] (may be NULL) receives the 'pred_xstart' the step returns: ddim_sample_with_grad (:559-614)
+ * re-derives it from the gradient-shifted eps on the guided steps, every other step returns x0 unchanged. */
+int ehb_sampler_update_ex(ehb_ctx* ctx, int step, int n, const float* x_t, const float* x0, const float* noise,
+                          const float* grad, float* x_prev, float* x0_out, void* stream);
 
 /* utils/geometry.py:47-66 rot6d_to_rotmat(x, 'diffusion'): x6 [n][6] -> R [n][3][3]. */
 int ehb_rot6d_to_rotmat(ehb_ctx* ctx, const float* x6, int n, float* R, void* stream);
@@ -253,8 +257,20 @@ int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);
 /* ResNet 3x3 convolutions: 1 = implicit GEMM through 4-D TMA boxes (product path), 0 = explicit im2col matrix + the
  * same GEMM (bring-up comparison; both must give identical bits). */
 int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm);
+/* ResNet convolution GEMMs: k-blocks (of 64 operand columns) chained into one tensor-memory accumulation before the
+ * epilogue takes the partial sum over in fp32 registers (0 = the whole contraction in one accumulator). */
+int ehb_debug_set_conv_kc(ehb_ctx* ctx, int kc);
+/* The convolution GEMM primitive alone, for unit tests of its numerics: out[m][n] = a[m][k] . w[n][k]^T in the library's
+ * error-compensated fp16 hi/lo scheme (operands scaled by a_scale / w_scale, powers of two).  All pointers HOST;
+ * synchronous.  n % 64 == 0, k % 64 == 0. */
+int ehb_debug_gemm_hl(ehb_ctx* ctx, const float* a, const float* w, int m, int n, int k, float a_scale, float w_scale,
+                      int kc, float* out);
 /* Returns 1 (and clears it) if any fp16 operand overflowed since the last call; synchronises `stream`. */
 int ehb_check_overflow(ehb_ctx* ctx, void* stream);
+/* Stream-ordered, non-blocking copy of the same flag into *host_flag (PINNED host memory): the caller reads it after
+ * any later synchronisation point, so a sequence of sampling calls needs no host sync of its own; graph-capturable.
+ * The device flag stays set until ehb_check_overflow clears it. */
+int ehb_overflow_flag_async(ehb_ctx* ctx, int32_t* host_flag, void* stream);
 /* Runs only hidden layer `layer` (1-based index into ehb_gcn_weights.layers) `iters` times on the current
  * activations and returns the average device time in ms through *ms (bench.py's roofline leg). */
 int ehb_time_hidden_layer(ehb_ctx* ctx, int layer, int iters, float* ms, void* stream);

@@ -74,7 +74,7 @@ def test_rot6d_golden(golden_dir):
 
 def test_rot6d_empty_input():
     from egohmr_b200.utils.geometry import rot6d_to_rotmat
-    assert rot6d_to_rotmat(torch.zeros(0, 144, device="cuda")).shape == (0, 3, 3)
+    assert rot6d_to_rotmat(torch.zeros(0, 144, device="cuda"), "diffusion").shape == (0, 3, 3)
 
 
 @pytest.mark.parametrize("n", [37, 64, 139])
@@ -461,8 +461,18 @@ def test_operand_overflow_fails_loudly(small):
     with torch.no_grad():
         model.diffusion_model.gconv_layers[0].gconv1.bn.weight.mul_(1e6)
     model.load_state_dict(model.state_dict(), strict=False)     # marks the kernels' weight copies dirty
+    batch = _tb(synth.make_batch(0, 2))
+    model.overflow_check = "sync"            # flag read back at the end of the call itself
     with pytest.raises(FloatingPointError):
-        diffusion.sample_many(model, _tb(synth.make_batch(0, 2)), 1, "ddim5")
+        diffusion.sample_many(model, batch, 1, "ddim5")
+    model.overflow_check = "deferred"        # default: no host sync per call, the report surfaces at the next touch point
+    diffusion.sample_many(model, batch, 1, "ddim5")
+    with pytest.raises(FloatingPointError):
+        model.poll_overflow(sync=True)
+    diffusion.sample_many(model, batch, 1, "ddim5")
+    torch.cuda.synchronize()
+    with pytest.raises(FloatingPointError):  # ... e.g. the next sampling call
+        diffusion.sample_many(model, batch, 1, "ddim5")
     model.engine.close()
 
 
