@@ -67,8 +67,13 @@ def parse():
     ap.add_argument("--n-img", type=int, default=N_IMG)
     ap.add_argument("--num-samples", type=int, default=N_SAMPLES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-img", type=int, default=8, help="images in the bounded CPU-baseline sample")
-    ap.add_argument("--cpu-sample-samples", type=int, default=4, help="samples per image in the CPU-baseline sample")
+    ap.add_argument("--cpu-sample-img", type=int, default=16, help="images per step of the bounded CPU sample (one val_losses call)")
+    ap.add_argument("--cpu-sample-samples", type=int, default=4, help="samples per image in the oracle-port CPU sample (fallback only)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 5],
+                    help="2 = configs[1] (headline; weak scaling over ranks + a configs[3] strong-scaling leg), "
+                         "5 = configs[4]: DDPM-1000, 512 images x 10 samples split over the ranks")
+    ap.add_argument("--no-strong", action="store_true", help="skip the configs[3] strong-scaling leg")
+    ap.add_argument("--strong-img", type=int, default=CFG4_IMG)
     return ap.parse_args()
 
 
@@ -499,19 +504,25 @@ def run_b200(args):
     e2e_s = time.perf_counter() - t0
 
     # ---- the literally unchanged driver loop (test_egohmr.py:251-255): num_samples sequential val_losses calls
-    def dropin_pass():
-        model.invalidate()
+    # (a new batch object per pass, as a dataloader delivers; from the second batch on val_losses runs the samples of a
+    # batch ahead as one pass — EgoHMR.samples_ahead — and the calls 2..S return the stored samples)
+    drop_batches = [batch_dev, torch_batch(synth.make_batch(200 + rank, n_img, N_PTS), dev)]
+
+    def dropin_pass(i):
+        outs = []
         for _ in range(S):
-            diffusion.val_losses(model=model, batch=batch_dev, shape=[n_img, 144], progress=False, clip_denoised=False,
-                                 cur_epoch=0, timestep_respacing=RESPACING, cond_fn_with_grad=False, cond_grad_weight=1.0,
-                                 compute_loss=False)
-    for _ in range(2):
-        dropin_pass()
-    n_drop = max(3, args.steps // 4)
+            o = diffusion.val_losses(model=model, batch=drop_batches[i % 2], shape=[n_img, 144], progress=False,
+                                     clip_denoised=False, cur_epoch=0, timestep_respacing=RESPACING, cond_fn_with_grad=False,
+                                     cond_grad_weight=1.0, compute_loss=False)
+            outs.append(o["pred_smpl_params"]["body_pose"].unsqueeze(1))
+        return torch.cat(outs, dim=1)
+    for i in range(3):
+        dropin_pass(i)
+    n_drop = max(4, args.steps // 2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(n_drop):
-        dropin_pass()
+    for i in range(n_drop):
+        dropin_pass(3 + i)
     barrier()
     dropin_s = (time.perf_counter() - t0) / n_drop
 

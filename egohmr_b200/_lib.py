@@ -77,6 +77,7 @@ SIGNATURES = {
     "ehb_set_temb": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "ehb_set_bodies": (C.c_int, [_vp, C.c_int, c_int32_p]),
     "ehb_denoise_step": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ehb_denoise_step_ex": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_denoise_step_debug": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_sampler_update": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ehb_sampler_update_ex": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -252,7 +252,7 @@ struct ehb_ctx {
   int rn_implicit = 1;   // 3x3 convolutions as implicit GEMMs through 4-D TMA boxes (0: explicit im2col matrix)
   // k-blocks (of 64) chained into one TMEM accumulation; longer contractions are summed chunk by chunk in fp32 registers
   // by the epilogue warps (0 = never split).  See DESIGN.md "K9 numerics".
-  int rn_kc = 4;
+  int rn_kc = 2;
   DevBuf rn_col, rn_x[2], rn_y1, rn_y2;
 
   DevBuf overflow, splitk;
@@ -629,7 +629,7 @@ static int run_input(ehb_ctx* ctx, int step, const float* x_t, cudaStream_t stre
 }
 
 static int run_output(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad, float* x_prev,
-                      float* x0, float* out_cond, float* out_uncond, cudaStream_t stream) {
+                      float* x0, float* out_cond, float* out_uncond, cudaStream_t stream, float* x0_model = nullptr) {
   ehb::OutputLayerParams p;
   p.adj = ctx->adj_out;
   p.act = ctx->res.as<float>();
@@ -646,6 +646,7 @@ static int run_output(ehb_ctx* ctx, int step, const float* x_t, const float* noi
   p.x0 = x0;
   p.out_cond = out_cond;
   p.out_uncond = out_uncond;
+  p.x0_model = x0_model;
   p.coef = ctx->coef[step];
   p.kind = ctx->kind;
   p.C = ctx->hid;
@@ -656,8 +657,8 @@ static int run_output(ehb_ctx* ctx, int step, const float* x_t, const float* noi
   return 0;
 }
 
-int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
-                           float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream_) {
+static int denoise_step_impl(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
+                             float* x_prev, float* x0, float* out_cond, float* out_uncond, float* x0_model, void* stream_) {
   if (!ctx || !x_t || !x_prev || !x0) return fail("ehb_denoise_step: null argument");
   if (!ctx->gcn_loaded || ctx->n_bodies <= 0 || ctx->n_img <= 0) return fail("ehb_denoise_step: context not set up");
   if (ctx->max_img_of_body >= ctx->n_img)
@@ -671,7 +672,17 @@ int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float
   for (int l = 0; l < static_cast<int>(ctx->hidden.size()); ++l)
     if (run_hidden(ctx, l, stream)) return 1;
   if (ctx->nl_loaded && run_nonlocal(ctx, stream)) return 1;
-  return run_output(ctx, step, x_t, noise, grad, x_prev, x0, out_cond, out_uncond, stream);
+  return run_output(ctx, step, x_t, noise, grad, x_prev, x0, out_cond, out_uncond, stream, x0_model);
+}
+
+int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
+                           float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream) {
+  return denoise_step_impl(ctx, step, x_t, noise, grad, x_prev, x0, out_cond, out_uncond, nullptr, stream);
+}
+
+int ehb_denoise_step_ex(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad, float* x_prev,
+                        float* x0, float* x0_model, void* stream) {
+  return denoise_step_impl(ctx, step, x_t, noise, grad, x_prev, x0, nullptr, nullptr, x0_model, stream);
 }
 
 namespace {

@@ -40,11 +40,12 @@ struct Cfg {
   static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
 };
 
+constexpr int MAX_ACC = 8;        // TMEM accumulator ring: 512 columns / tile_n stages (2 / 4 / 8)
 struct Barriers {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
-  uint64_t tfull[2];
-  uint64_t tempty[2];
+  uint64_t tfull[MAX_ACC];
+  uint64_t tempty[MAX_ACC];
   uint32_t tmem_base;
 };
 static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
@@ -72,6 +73,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // (models/resnet.py:90-94) is ONE launch, the projected identity never exists in memory
   const int KB1 = p.K / BK, KB = KB1 + p.K2 / BK;
   constexpr bool CHUNKED = BN <= 128;   // running sums live in registers: 64 / 32 per epilogue thread
+  constexpr int NACC = TMEM_COLS / BN;  // accumulator stages: the MMA warp may run NACC - 1 chunks ahead of the epilogue
   const int kc = (CHUNKED && p.kc > 0 && p.kc < KB) ? p.kc : KB;   // k-blocks per accumulation chunk
 
   if (warp == TMA_WARP && lane == 0) {
@@ -87,7 +89,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_init(&bars->full[s], 1);
       ptx::mbar_init(&bars->empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       ptx::mbar_init(&bars->tfull[s], 1);
       ptx::mbar_init(&bars->tempty[s], 2 * NUM_EPI_WARPS);
     }
@@ -169,6 +171,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::mbar_wait(&bars->full[stage], phase);
             ptx::tc_fence_after_sync();
             const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
+            // the small cross terms (hi*lo, lo*hi: 2^-11 of the main term) of the whole k-block go first: the tensor
+            // core truncates after every MMA by up to one ulp of the CURRENT accumulator, so terms added while the
+            // accumulator is still small cost (almost) nothing — only the 4 main MMAs see its full magnitude
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               const uint32_t koff = ks * UMMA_K * 2;
@@ -176,9 +181,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint64_t a_lo = ptx::make_kmajor_desc<128>(sa + A_BYTES + koff);
               const uint64_t b_hi = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + koff);
               const uint64_t b_lo = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + B_BYTES + koff);
-              ptx::umma_f16_2sm_elect(tacc, a_hi, b_hi, idesc, (kb > kb0 || ks != 0) ? 1u : 0u);
-              ptx::umma_f16_2sm_elect(tacc, a_hi, b_lo, idesc, 1u);
+              ptx::umma_f16_2sm_elect(tacc, a_hi, b_lo, idesc, (kb > kb0 || ks != 0) ? 1u : 0u);
               ptx::umma_f16_2sm_elect(tacc, a_lo, b_hi, idesc, 1u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint32_t koff = ks * UMMA_K * 2;
+              const uint64_t a_hi = ptx::make_kmajor_desc<128>(sa + koff);
+              const uint64_t b_hi = ptx::make_kmajor_desc<128>(sa + 2 * A_BYTES + koff);
+              ptx::umma_f16_2sm_elect(tacc, a_hi, b_hi, idesc, 1u);
             }
             ptx::umma_commit_2sm_mc_elect(&bars->empty[stage], 0b11);
             if (kb == kend - 1) ptx::umma_commit_2sm_mc_elect(&bars->tfull[as], 0b11);
@@ -188,7 +199,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               phase ^= 1;
             }
           }
-          if (++as == 2) {
+          if (++as == NACC) {
             as = 0;
             aphase ^= 1;
           }
@@ -258,7 +269,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (leader) ptx::mbar_arrive(&bars->tempty[as]);
               else ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->tempty[as]), 0));
             }
-            if (++as == 2) {
+            if (++as == NACC) {
               as = 0;
               aphase ^= 1;
             }
@@ -336,7 +347,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                               p.out_ld, rows_valid, lane);
         }
       }
-      if (++as == 2) {
+      if (++as == NACC) {
         as = 0;
         aphase ^= 1;
       }

@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(256, 2) gcn_output_fallback_kernel(const __gri
   const size_t idx = static_cast<size_t>(body) * XDIM + e;
   if (p.out_cond) p.out_cond[idx] = out[0];
   if (p.out_uncond) p.out_uncond[idx] = out[1];
+  if (p.x0_model) p.x0_model[idx] = x0;
   p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
   p.x0[idx] = x0;
 }
@@ -430,6 +431,7 @@ __global__ void __launch_bounds__((K3_CONSUMERS + 1) * 32, 1) gcn_output_kernel(
       const size_t idx = static_cast<size_t>(body) * XDIM + e;
       if (p.out_cond) p.out_cond[idx] = out[0];
       if (p.out_uncond) p.out_uncond[idx] = out[1];
+      if (p.x0_model) p.x0_model[idx] = x0;
       p.x_prev[idx] = sampler_update_one(p.coef, p.kind, p.x_t[idx], x0, p.noise, p.grad, idx);
       p.x0[idx] = x0;
     }

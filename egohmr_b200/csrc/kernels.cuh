@@ -129,6 +129,8 @@ struct OutputLayerParams {
   float* x0;              // [B][144]
   float* out_cond;        // optional [B][144] raw image-conditioned denoiser output (tests)
   float* out_uncond;      // optional [B][144]
+  float* x0_model;        // optional [B][144]: the fused model prediction BEFORE the sampler update touches it (the guided
+                          // DDIM step re-derives pred_xstart; EgoHMR.forward's own output, 'other_outputs', keeps this one)
   StepCoef coef;
   int kind;
   int C, n_bodies, diffuse_fuse;

@@ -94,7 +94,8 @@ class GraphedSampler:
 
     def check_overflow(self):
         """True if an fp16 operand overflowed in any replay since the last check (synchronises; replays themselves
-        cannot read the flag back)."""
+        cannot read the flag back — in the default `overflow_check='deferred'` mode every replay ends with a copy of the
+        flag to pinned memory, which `model.poll_overflow()` examines without blocking)."""
         return self.model.engine.check_overflow()
 
     def _version(self):
@@ -134,4 +135,6 @@ class GraphedSampler:
             if staged:
                 self._consumed_evt.record()
         self.graph.replay()
+        if self.model._ovf_event is not None:
+            self.model._ovf_event.record()    # the replay ended with a copy of the operand-overflow flag to pinned memory
         return self.static_out

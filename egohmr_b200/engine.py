@@ -262,8 +262,12 @@ class Engine:
         self.n_bodies = iob.shape[0]
 
     # ------------------------------------------------------------------ hot calls
-    def denoise_step(self, step, x_t, noise, grad, x_prev, x0, out_cond=None, out_uncond=None):
-        if out_cond is None and out_uncond is None:
+    def denoise_step(self, step, x_t, noise, grad, x_prev, x0, out_cond=None, out_uncond=None, x0_model=None):
+        if x0_model is not None:
+            check(self.lib.ehb_denoise_step_ex(self._h, int(step), _dev_ptr(x_t), _dev_ptr(noise, allow_none=True),
+                                               _dev_ptr(grad, allow_none=True), _dev_ptr(x_prev), _dev_ptr(x0),
+                                               _dev_ptr(x0_model), _stream()))
+        elif out_cond is None and out_uncond is None:
             check(self.lib.ehb_denoise_step(self._h, int(step), _dev_ptr(x_t), _dev_ptr(noise, allow_none=True),
                                             _dev_ptr(grad, allow_none=True), _dev_ptr(x_prev), _dev_ptr(x0), _stream()))
         else:

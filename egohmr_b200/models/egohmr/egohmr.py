@@ -198,6 +198,9 @@ class EgoHMR(nn.Module):
         # reference driver runs right after each val_losses call) and by poll_overflow() — the ten per-sample calls of the
         # driver's loop (test_egohmr.py:251-255) then need no host sync of their own.
         self.overflow_check = "deferred"
+        # val_losses draws the chains of several samples ahead and runs them as one batch (gaussian_diffusion.py::val_losses):
+        # "auto" = as many as the previous batch received calls, an int = that many, 0 = off (one chain per call)
+        self.samples_ahead = "auto"
         self._ovf_host = None
         self._ovf_event = None
         self.native_image_enc = True   # ResNet-50 on the tcgen05 convolution GEMMs (K9, fp32-class); False = cuDNN
@@ -249,17 +252,20 @@ class EgoHMR(nn.Module):
     # ------------------------------------------------------------------ operand-range check
     def note_sampling_call_done(self):
         """Called by the samplers after the last kernel of a sampling call."""
-        if torch.cuda.is_current_stream_capturing():
-            return
-        if self.overflow_check == "sync":
+        capturing = torch.cuda.is_current_stream_capturing()
+        if self.overflow_check == "sync" and not capturing:
             if self.engine.check_overflow():
                 raise FloatingPointError(self._OVF_MSG)
             return
         if self._ovf_host is None:
+            if capturing:
+                return
             self._ovf_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._ovf_event = torch.cuda.Event()
+        # the flag copy is part of a captured pass too; the graph's owner records the event after each replay
         self.engine.overflow_flag_async(self._ovf_host)
-        self._ovf_event.record()
+        if not capturing:
+            self._ovf_event.record()
 
     _OVF_MSG = ("fp16 operand overflow inside the tensor-core kernels: an activation left the representable range of the "
                 "hi/lo operand format (see DESIGN.md, K1 numerics)")
@@ -267,7 +273,7 @@ class EgoHMR(nn.Module):
     def poll_overflow(self, sync=False):
         """Raise FloatingPointError if an earlier sampling call overflowed the fp16 operand range.  Non-blocking unless
         `sync` (then it waits for the last enqueued flag copy)."""
-        if self._ovf_event is None:
+        if self._ovf_event is None or torch.cuda.is_current_stream_capturing():
             return
         if sync:
             self._ovf_event.synchronize()

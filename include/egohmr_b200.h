@@ -138,6 +138,11 @@ int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body);
  *   x_prev [n_bodies][144] out ('sample');  x0 [n_bodies][144] out ('pred_xstart' == 'pred_x_start'). */
 int ehb_denoise_step(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad, float* x_prev,
                      float* x0, void* stream);
+/* Same with one more output: x0_model [n_bodies][144] (may be NULL) = the model's own fused prediction, i.e.
+ * 'other_outputs'['pred_x_start'].  It differs from x0 only on the guided DDIM steps, where ddim_sample_with_grad
+ * (:579-592) re-derives 'pred_xstart' from the gradient-shifted eps. */
+int ehb_denoise_step_ex(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad, float* x_prev,
+                        float* x0, float* x0_model, void* stream);
 /* Same, but also returns the raw image-conditioned / image-masked denoiser outputs (egohmr.py:237,246). Tests only. */
 int ehb_denoise_step_debug(ehb_ctx* ctx, int step, const float* x_t, const float* noise, const float* grad,
                            float* x_prev, float* x0, float* out_cond, float* out_uncond, void* stream);

@@ -21,13 +21,7 @@ import ref_standins  # noqa: E402
 
 
 def to_torch(batch, dtype):
-    out = {}
-    for k, v in batch.items():
-        if isinstance(v, dict):
-            out[k] = to_torch(v, dtype)
-        else:
-            out[k] = torch.from_numpy(np.asarray(v)).to(dtype)
-    return out
+    return ref_standins.to_torch(batch, dtype)
 
 
 class NoiseFeed:
@@ -53,34 +47,13 @@ class NoiseFeed:
 
 
 def build_reference(hid, n_blocks, dtype, seed=0, only_mask_img_cond=True, diffuse_fuse=True, nonlocal_layer=False):
-    smpl_model = synth.make_smpl_model(seed)
-    ref_standins.install(smpl_model, smpl_model["init_betas"])
-    from models.egohmr.egohmr import EgoHMR
-    mean, std = synth.body_rep_stats(seed)
-    model = EgoHMR(cfg=ref_standins.make_cfg(), device="cpu",
-                   body_rep_mean=torch.from_numpy(mean).to(dtype), body_rep_std=torch.from_numpy(std).to(dtype),
-                   with_focal_length=True, with_bbox_info=True, with_cam_center=True, scene_feat_dim=512,
-                   scene_type="cube", scene_cano=True, cond_mask_prob=0.0, only_mask_img_cond=only_mask_img_cond,
-                   pelvis_vis_loosen=True, diffuse_fuse=diffuse_fuse, diffusion_blk=n_blocks, gcn_hid_dim=hid,
-                   gcn_nonlocal_layer=nonlocal_layer)
-    sd = synth.make_state_dict(seed, hid=hid, n_blocks=n_blocks, init_betas=smpl_model["init_betas"])
-    if nonlocal_layer:
-        synth.add_nonlocal(sd, seed, hid)
-    res = model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
-    assert not res.unexpected_keys and all(k.startswith("smpl") for k in res.missing_keys), res
-    # randomised adj2 must survive: the reference keeps `adj` as a plain attribute, adj2 as a parameter
-    model = model.to(dtype)
-    for m in model.modules():
-        if hasattr(m, "adj") and isinstance(getattr(m, "adj"), torch.Tensor):
-            m.adj = m.adj.to(dtype)
-    model.eval()
-    if dtype == torch.float64:
-        model.smpl.out_dtype = torch.float64
-    return model, mean, std
+    return ref_standins.build_reference(hid, n_blocks, dtype, seed, only_mask_img_cond, diffuse_fuse, nonlocal_layer)
 
 
 def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0, guided=False, only_mask_img_cond=True,
-             diffuse_fuse=True, nonlocal_layer=False):
+             diffuse_fuse=True, nonlocal_layer=False, trace_every=1, eta=None):
+    """`trace_every`: keep every n-th step of the per-step trace (long chains); `eta`: call ddim_sample_loop directly with
+    this eta (val_losses hard-codes eta=0.0, gaussian_diffusion.py:770)."""
     from diffusion.model_util import create_gaussian_diffusion
     import diffusion.gaussian_diffusion as gd
     model, mean, std = build_reference(hid, n_blocks, dtype, seed, only_mask_img_cond, diffuse_fuse, nonlocal_layer)
@@ -115,14 +88,22 @@ def run_case(name, T, respacing, hid, n_blocks, n_img, dtype, seed=0, guided=Fal
     torch.randn, torch.randn_like = feed.randn, feed.randn_like
     try:
         with torch.no_grad():   # the reference re-enables grad inside guide_coll (egohmr.py:518)
-            out = diffusion.val_losses(model=Wrapped(model), batch=batch, shape=[n_img, 144], progress=False,
-                                       clip_denoised=False, cur_epoch=0, timestep_respacing=respacing,
-                                       cond_fn_with_grad=guided, cond_grad_weight=2.0, compute_loss=False)
+            if eta is None:
+                out = diffusion.val_losses(model=Wrapped(model), batch=batch, shape=[n_img, 144], progress=False,
+                                           clip_denoised=False, cur_epoch=0, timestep_respacing=respacing,
+                                           cond_fn_with_grad=guided, cond_grad_weight=2.0, compute_loss=False)
+            else:
+                model.validation_setup()
+                out = diffusion.ddim_sample_loop(model=Wrapped(model), batch=batch, shape=[n_img, 144], progress=False,
+                                                 clip_denoised=False, eta=eta, cond_fn_with_grad=guided)["other_outputs"]
     finally:
         torch.randn, torch.randn_like = old_randn, old_randn_like
     g = lambda t: t.detach().numpy()
+    if trace_every > 1:
+        trace = trace[::trace_every] + ([trace[-1]] if (len(trace) - 1) % trace_every else [])
     rec = {
         "T": T, "respacing": respacing, "hid": hid, "n_blocks": n_blocks, "n_img": n_img, "seed": seed,
+        "trace_every": trace_every, "eta": -1.0 if eta is None else float(eta),
         "timestep_map": np.array(diffusion.timestep_map), "trace_t_orig": np.array([t for t, _, _ in trace]),
         "trace_x_t": np.stack([x for _, x, _ in trace]), "trace_x0": np.stack([x for _, _, x in trace]),
         "pred_x_start": g(out["pred_x_start"]), "pred_pose_6d": g(out["pred_pose_6d"]),
@@ -210,6 +191,88 @@ def procrustes_case():
     print("wrote procrustes", rec["re_avg"])
 
 
+def angle_axis_case():
+    """utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis straight from the reference: generic rotations,
+    theta -> 0 (identity and tiny angles), theta = pi about several axes, and every branch of the quaternion conversion."""
+    from utils.konia_transform import rotation_matrix_to_angle_axis
+
+    def rodrigues(v):
+        th_ = np.linalg.norm(v)
+        if th_ == 0:
+            return np.eye(3)
+        k = v / th_
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th_) * K + (1 - np.cos(th_)) * K @ K
+
+    rng = np.random.default_rng(5)
+    vs = [rng.normal(0, 1, 3) for _ in range(64)]
+    vs += [np.zeros(3), np.array([1e-7, 0, 0]), np.array([0, 1e-5, 1e-5]), np.array([1e-3, -1e-3, 1e-3])]
+    for ax in (np.array([1.0, 0, 0]), np.array([0, 1.0, 0]), np.array([0, 0, 1.0]), np.array([1.0, 1.0, 0]) / np.sqrt(2),
+               np.array([1.0, -2.0, 3.0]) / np.sqrt(14)):
+        vs += [np.pi * ax, (np.pi - 1e-4) * ax, (np.pi - 1e-2) * ax, 3.0 * ax, 0.5 * np.pi * ax]
+    R = np.stack([rodrigues(v) for v in vs]).astype(np.float32)
+    aa32 = rotation_matrix_to_angle_axis(torch.from_numpy(R)).numpy()
+    aa64 = rotation_matrix_to_angle_axis(torch.from_numpy(R).double()).numpy()
+    np.savez_compressed(os.path.join(HERE, "angle_axis.npz"), R=R, aa32=aa32, aa64=aa64)
+    print("wrote angle_axis", R.shape, "max|aa| =", float(np.abs(aa32).max()))
+
+
+def metrics_case():
+    """The evaluation-metric block of the reference driver (test_egohmr.py:373-494: G-MPJPE / MPJPE / PA-MPJPE / V2V with
+    visible / invisible splits, per-joint std and APD diversity) executed VERBATIM: the lines are read from the reference
+    file at generation time and exec'd on synthetic predictions / ground truth (they are inline script code, not a
+    function, and the file itself cannot be imported: pytorch3d / pyrender at its top)."""
+    import textwrap
+    import types as _t
+    from utils.geometry import perspective_projection
+    from utils.pose_utils import reconstruction_error, reconstruction_error_with_vis_mask
+    src = open(os.path.join(ref_standins.REFERENCE_ROOT, "test_egohmr.py")).read().splitlines()
+    first = next(i for i, l in enumerate(src) if "focal_length_proj = focal_length.unsqueeze(-1).repeat(1, 2)" in l)
+    last = next(i for i, l in enumerate(src) if "apd_joints_invis_all[step * args.batch_size" in l)
+    block = textwrap.dedent("\n".join(src[first:last + 1]))
+    rng = np.random.default_rng(11)
+    bs, S, V = 5, 4, 1000
+    f = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    gt_j = f(rng.normal(0, 0.35, (bs, 24, 3)) + np.array([0.0, 0.0, 3.0]))
+    gt_j[1, :6, 0] += 4.0      # some joints project outside the 1920 x 1080 image -> invisible
+    gt_j[3, 10:, 1] -= 3.0
+    gt_v = f(rng.normal(0, 0.35, (bs, V, 3)) + np.array([0.0, 0.0, 3.0]))
+    gt_v[1, :2000, 0] += 4.0
+    pred_j = gt_j.unsqueeze(1) - gt_j[:, None, [0]] + f(rng.normal(0, 0.05, (bs, S, 24, 3)))      # [bs,S,24,3] around the GT
+    pred_v = gt_v.unsqueeze(1) - gt_j[:, None, [0]] + f(rng.normal(0, 0.05, (bs, S, V, 3)))
+    transl = f(rng.normal(0, 0.1, (bs, 3)) + np.array([0.0, 0.0, 3.0]))
+    pred_pelvis = pred_j[:, :, [0]].clone()
+    ns = {"torch": torch, "np": np, "perspective_projection": perspective_projection,
+          "reconstruction_error": reconstruction_error, "reconstruction_error_with_vis_mask": reconstruction_error_with_vis_mask,
+          "device": "cpu", "step": 0, "curr_batch_size": bs,
+          "args": _t.SimpleNamespace(batch_size=bs, num_samples=S, eval_with_vis_mask_pa=False),
+          "focal_length": f(rng.uniform(1400, 1600, bs)), "cam_cx": f(np.full(bs, 960.0)), "cam_cy": f(np.full(bs, 540.0)),
+          "gt_keypoints_3d": gt_j, "gt_vertices": gt_v, "gt_keypoints_3d_align": gt_j - gt_j[:, [0]],
+          "gt_vertices_align": gt_v - gt_j[:, [0]], "pred_keypoints_3d_align": pred_j - pred_pelvis,
+          "pred_vertices_align": pred_v - pred_pelvis, "pred_keypoints_3d_full": pred_j + transl[:, None, None]}
+    for k in ("joint_vis_num_list", "joint_invis_num_list", "vertex_vis_num_list", "vertex_invis_num_list"):
+        ns[k] = []
+    names = ["g_mpjpe_all", "g_mpjpe_vis_all_list", "g_mpjpe_invis_all_list", "mpjpe_all", "mpjpe_vis_all_list",
+             "mpjpe_invis_all_list", "pa_mpjpe_all", "pa_mpjpe_vis_all_list", "pa_mpjpe_invis_all_list", "v2v_all",
+             "v2v_vis_all_list", "v2v_invis_all_list"]
+    for k in names:
+        ns[k] = np.zeros((bs, S))
+    names1 = ["std_joints_all", "std_joints_vis_all", "std_joints_invis_all", "apd_joints_all", "apd_joints_vis_all",
+              "apd_joints_invis_all"]
+    for k in names1:
+        ns[k] = np.zeros(bs)
+    exec(compile(block, "test_egohmr.py[metrics block]", "exec"), ns)
+    rec = {k: ns[k] for k in names + names1}
+    rec.update(pred_keypoints_3d=pred_j.numpy(), pred_vertices=pred_v.numpy(), transl=transl.numpy(), gt_keypoints_3d=gt_j.numpy(),
+               gt_vertices=gt_v.numpy(), focal_length=ns["focal_length"].numpy(), cam_cx=ns["cam_cx"].numpy(),
+               cam_cy=ns["cam_cy"].numpy(), joint_vis_mask=ns["joint_vis_mask"].numpy(),
+               vertex_vis_num=np.array(ns["vertex_vis_num_list"]), joint_vis_num=np.array(ns["joint_vis_num_list"]))
+    # store the inputs compactly: vertices as float16 offsets would change them, so keep float32 but only 5 x 4 bodies
+    np.savez_compressed(os.path.join(HERE, "eval_metrics.npz"), **rec)
+    print("wrote eval_metrics", {k: np.round(ns[k].mean(), 5) for k in ("mpjpe_all", "pa_mpjpe_all", "v2v_all", "apd_joints_all")},
+          "vis joints", ns["joint_vis_num_list"])
+
+
 def schedule_tables():
     from diffusion.model_util import create_gaussian_diffusion
     rec = {}
@@ -265,6 +328,25 @@ if __name__ == "__main__":
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "procrustes":
         procrustes_case()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "aa":
+        angle_axis_case()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "metrics":
+        metrics_case()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "ddim_guided":   # ddim_sample_with_grad (:559-614) and eta != 0
+        run_case("ddim5_guided_T50_hid256_f64", 50, "ddim5", 256, 2, 3, torch.float64, guided=True)
+        run_case("ddim5_guided_T50_hid256_f32", 50, "ddim5", 256, 2, 3, torch.float32, guided=True)
+        run_case("ddim5_eta05_T50_hid256_f64", 50, "ddim5", 256, 2, 3, torch.float64, eta=0.5)
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg3":          # configs[2] at its real denoiser size: hid 1024, 4 blocks
+        run_case("ddpm_guided_T100_hid1024_f64", 100, "", 1024, 4, 3, torch.float64, guided=True, trace_every=10)
+        run_case("ddpm_guided_T100_hid1024_f32", 100, "", 1024, 4, 3, torch.float32, guided=True, trace_every=10)
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg5":          # configs[4]'s chain length: T = 1000 DDPM steps
+        run_case("ddpm_T1000_hid256_f64", 1000, "", 256, 2, 2, torch.float64, trace_every=100)
+        run_case("ddpm_T1000_hid256_f32", 1000, "", 256, 2, 2, torch.float32, trace_every=100)
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "loss":
         loss_case("val_losses_compute_loss_f32", torch.float32)

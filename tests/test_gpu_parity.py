@@ -32,20 +32,41 @@ def _strict_fp32_encoders():
     yield
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
-X0_TOL = 2e-6          # max |pred_x_start - float64 reference| (normalised rot6d units, |x0| ~ 1); measured 3e-7
-VERT_TOL_M = 2e-5      # max per-vertex error in metres = 0.02 mm; measured 1.8e-3 mm vs float64 (reference fp32: 3.0e-3 mm)
+# Tolerances vs the float64 run of the UNMODIFIED reference (goldens).  north_star asks for < 1e-3 mm per vertex; the
+# reference's own fp32 run is 3.0e-3 mm / 4.4e-7 from its float64 run on these inputs (and its CPU and GPU fp32 runs differ
+# from each other by as much, profiles/r02_reference_noise_floor.json), so the enforced bar is "no worse than the
+# reference's own fp32 noise": measured here 2.6e-3 mm / 4.0e-7 with the default native encoders.
+X0_TOL = 1e-6          # max |pred_x_start - float64 reference| (normalised rot6d units, |x0| ~ 1)
+VERT_TOL_M = 5e-6      # max per-vertex error in metres = 5e-3 mm
 
 
 @pytest.fixture(scope="module")
-def full():
+def _full():
     from egohmr_b200.testing import build_model
     return build_model(1024, 4, T=50, respacing="ddim5")
 
 
 @pytest.fixture(scope="module")
-def small():
+def _small():
     from egohmr_b200.testing import build_model
     return build_model(256, 2, T=50, respacing="")
+
+
+def _fresh(bundle):
+    """The models are shared by the module's tests; what val_losses learned about the caller's loop must not leak."""
+    bundle[0].__dict__.pop("_ahead", None)
+    bundle[0].samples_ahead = "auto"
+    return bundle
+
+
+@pytest.fixture
+def full(_full):
+    return _fresh(_full)
+
+
+@pytest.fixture
+def small(_small):
+    return _fresh(_small)
 
 
 def _tb(batch_np):
@@ -230,8 +251,8 @@ def test_ddpm50_sampling_vs_reference_golden(small, golden_dir):
     d64 = np.abs(out["pred_x_start"].cpu().numpy() - g64["pred_x_start"]).max()
     floor = np.abs(g32["pred_x_start"] - g64["pred_x_start"]).max()
     print(f"DDPM-50 final max|x0 - ref_f64| = {d64:.3e}; reference fp32-vs-fp64 = {floor:.3e}")
-    assert d64 < 5e-6    # 50 chained steps; measured 2.8e-7
-    assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < 2e-5
+    assert d64 < X0_TOL  # 50 chained steps; measured 4e-7, the reference's own fp32 run 4.2e-7
+    assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < VERT_TOL_M
 
 
 @pytest.mark.parametrize("case,flags", [("ddim5_T50_hid256_maskall_f64", {"only_mask_img_cond": False}),
@@ -337,7 +358,7 @@ def test_native_resnet50_vs_module_and_float64(full):
         d_fp32 = (ref32.double() - ref64).abs().max().item()
         print(f"native ResNet-50 ({n_img} img): max|native - f64| = {d_native:.3e}, torch fp32 - f64 = {d_fp32:.3e} "
               f"(max|feat| = {scale:.3f})")
-        assert d_native < 2e-5 * max(1.0, scale)
+        assert d_native < 2e-6 * max(1.0, scale)   # measured 6.8e-7 (chunked accumulation, DESIGN.md K9 numerics); r01: 1.07e-5
         # the 3x3 convolutions as implicit GEMMs (4-D TMA boxes, zero padding = TMA out-of-bounds fill) and through an
         # explicit im2col matrix feed the tensor core the same operands in the same order: identical bits
         model.engine.set_resnet_mode(False)
@@ -474,6 +495,53 @@ def test_operand_overflow_fails_loudly(small):
     with pytest.raises(FloatingPointError):  # ... e.g. the next sampling call
         diffusion.sample_many(model, batch, 1, "ddim5")
     model.engine.close()
+
+
+@pytest.mark.parametrize("which,with_loss", [("full", False), ("small", True)])
+def test_val_losses_samples_ahead_equals_the_sequential_driver_loop(request, which, with_loss):
+    """The reference driver's loop unchanged (test_egohmr.py:251-255): `num_samples` val_losses calls per batch.  From the
+    second batch on, val_losses runs the chains of all samples of a batch at its first call (`samples_ahead="auto"`);
+    every returned tensor, the losses, and torch's generator state after the loop must equal the one-chain-per-call
+    execution bit for bit."""
+    model, diffusion, *_ = request.getfixturevalue(which)
+    respacing = "ddim5" if which == "full" else ""
+    S, n_img = 4, 3
+    mk = lambda i: (synth.merge_gt(synth.make_batch(20 + i, n_img), synth.make_gt(20 + i, n_img)) if with_loss
+                    else synth.make_batch(20 + i, n_img))
+    batches = [_tb(mk(i)) for i in range(3)]
+
+    def driver(ahead):
+        model.samples_ahead = ahead
+        model.__dict__.pop("_ahead", None)
+        torch.manual_seed(7)
+        recs = []
+        for b in batches:
+            for _n in range(S):
+                o = diffusion.val_losses(model=model, batch=b, shape=[n_img, 144], progress=False, clip_denoised=False,
+                                         cur_epoch=0, timestep_respacing=respacing, cond_fn_with_grad=False,
+                                         cond_grad_weight=1.0, compute_loss=with_loss)
+                r = {k: o[k].clone() for k in ("pred_x_start", "pred_pose_6d", "pred_vertices", "pred_keypoints_3d",
+                                               "pred_keypoints_3d_full", "pred_keypoints_2d_full")}
+                r.update({"p_" + k: v.clone() for k, v in o["pred_smpl_params"].items()})
+                if with_loss:
+                    r.update({"l_" + k: v.clone() for k, v in o["losses"].items()})
+                r["vis"] = b["vis_mask_smpl"].clone()
+                recs.append(r)
+        return recs, torch.randn(5, device="cuda")
+
+    seq, tail_seq = driver(0)
+    l0 = model.engine.launch_count()
+    ahead, tail_ahead = driver("auto")      # batch 0: one chain per call (nothing learned yet); batches 1, 2: 4 samples ahead
+    launches_ahead = model.engine.launch_count() - l0
+    assert len(seq) == len(ahead) == 3 * S
+    for i, (a, b) in enumerate(zip(seq, ahead)):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k].shape == b[k].shape and torch.equal(a[k], b[k]), (i, k)
+    assert torch.equal(tail_seq, tail_ahead)                      # the generator was consumed identically
+    assert model._ahead["learned"] == S and not model._ahead["pending"]
+    driver(0)
+    assert launches_ahead < (model.engine.launch_count() - l0 - launches_ahead)   # fewer, larger launches
 
 
 def test_image_sharding_reproduces_the_unsharded_chains(full):
@@ -769,8 +837,79 @@ def test_guided_ddpm100_vs_reference_golden(golden_dir):
     moved = (plain["pred_x_start"] - out["pred_x_start"]).abs().max().item()
     print(f"guided DDPM-100: max|x0 - ref_f64| = {d64:.3e}; reference fp32-vs-fp64 = {floor:.3e}; guidance moved x0 by {moved:.3e}")
     assert moved > 1e-6      # small (|grad| ~ 5e-3 times 0.02 .. 0.07) but far above the parity tolerance
-    assert d64 < 5e-6
-    assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < 2e-5
+    assert d64 < X0_TOL
+    assert np.abs(out["pred_vertices"].cpu().numpy() - g32["pred_vertices"]).max() < VERT_TOL_M
+
+
+def test_cfg3_guided_ddpm100_full_size_denoiser_vs_reference_golden(golden_dir):
+    """configs[2] with its real denoiser (hid 1024, 4 blocks): DDPM T=100, p_sample_with_grad on the last 11 steps
+    (gaussian_diffusion.py:340-388), golden from the unmodified reference (3 images); run here in the config's own layout —
+    images x 10 samples in one batch, every sample fed the golden's noise, so all 10 chains of an image must reproduce
+    the golden chain — and compared step by step on the stored trace (every 10th step)."""
+    from egohmr_b200.testing import build_model
+    model, diffusion, _, smpl_model, *_ = build_model(1024, 4, T=100, respacing="")
+    g64 = np.load(os.path.join(golden_dir, "ddpm_guided_T100_hid1024_f64.npz"))
+    g32 = np.load(os.path.join(golden_dir, "ddpm_guided_T100_hid1024_f32.npz"))
+    n_img, S = 3, 10
+    batch = _tb(synth.make_batch(0, n_img))
+    noise = synth.make_noise(0, 1, n_img, 100)[0]                       # [101, 3, 144]
+    noise_rep = torch.from_numpy(np.repeat(noise, S, axis=1)).cuda()     # body = img * S + n
+    out = diffusion.sample_many(model, batch, S, "", noise=noise_rep, cond_fn_with_grad=True, cond_grad_weight=2.0)
+    x0 = out["pred_x_start"].cpu().numpy().reshape(n_img, S, 144)
+    assert np.abs(x0 - x0[:, :1]).max() == 0                             # identical noise -> identical chains, bit for bit
+    d64 = np.abs(x0[:, 0] - g64["pred_x_start"]).max()
+    floor = np.abs(g32["pred_x_start"] - g64["pred_x_start"]).max()
+    R64 = np.concatenate([g64["global_orient"], g64["body_pose"]], axis=1)
+    v64 = o_smpl.smpl_forward(smpl_model, R64, g64["betas"])["vertices"]
+    dv = np.abs(out["pred_vertices"].cpu().numpy().reshape(n_img, S, -1, 3)[:, 0] - v64).max()
+    dv_ref = np.abs(g32["pred_vertices"] - v64).max()
+    print(f"cfg3 (hid 1024) guided DDPM-100: max|x0 - ref_f64| = {d64:.3e} (reference fp32: {floor:.3e}); "
+          f"vertices {dv * 1e3:.3e} mm (reference fp32: {dv_ref * 1e3:.3e} mm)")
+    assert d64 < X0_TOL and dv < VERT_TOL_M
+    assert not model.engine.check_overflow()
+
+
+@pytest.mark.parametrize("case,kw", [("ddim5_guided_T50_hid256", {"cond_fn_with_grad": True}),
+                                     ("ddim5_eta05_T50_hid256", {"eta": 0.5})])
+def test_ddim_with_grad_and_eta_vs_reference_golden(small, golden_dir, case, kw):
+    """ddim_sample_with_grad (gaussian_diffusion.py:559-614: the collision gradient shifts eps for respaced t <= 3 and
+    pred_xstart is re-derived) and eta != 0 (:541-555), both through ddim_sample_loop_progressive, per-step trace vs the
+    unmodified reference in float64."""
+    from egohmr_b200.testing import build_model
+    model, diffusion, *_ = build_model(256, 2, T=50, respacing="ddim5")
+    g = np.load(os.path.join(golden_dir, case + "_f64.npz"))
+    batch = _tb(synth.make_batch(0, 3))
+    noise = torch.from_numpy(synth.make_noise(0, 1, 3, 5)[0]).cuda()
+    feed = iter(noise[1:])
+    xs, x0s = [], []
+    old = torch.randn_like
+    torch.randn_like = lambda x, **k: next(feed)          # the per-step draws of the public loop come from torch.randn_like
+    try:
+        for out in diffusion.ddim_sample_loop_progressive(model, batch, [3, 144], noise=noise[0], **kw):
+            xs.append(batch["x_t"].cpu().numpy())
+            x0s.append(out["pred_xstart"].cpu().numpy())
+            final = out
+    finally:
+        torch.randn_like = old
+    d_xt = np.abs(np.stack(xs) - g["trace_x_t"]).max()
+    print(f"{case}: max|x_t - ref_f64| over the 5 steps = {d_xt:.3e}")
+    assert d_xt < X0_TOL
+    # the model's raw prediction at the last step is what val_losses returns (other_outputs)
+    assert np.abs(final["other_outputs"]["pred_x_start"].cpu().numpy() - g["pred_x_start"]).max() < X0_TOL
+    if "eta" in kw:   # stochastic DDIM: the chain must differ from eta = 0
+        plain = diffusion.ddim_sample_loop(model, batch, [3, 144], noise=noise[0])
+        assert (plain["sample"] - final["sample"]).abs().max().item() > 1e-3
+    else:             # guided: pred_xstart of the guided steps is the re-derived one, not the model's raw output
+        assert np.abs(x0s[-1] - g["trace_x0"][-1]).max() > 0
+
+
+def test_rotmat_to_angle_axis_vs_reference_golden(full, golden_dir):
+    """utils/konia_transform.py:316-339 straight from the reference (theta -> 0, theta = pi about several axes, every
+    quaternion branch): kernel vs the reference's float64 and float32 results."""
+    g = np.load(os.path.join(golden_dir, "angle_axis.npz"))
+    aa = full[0].engine.rotmat_to_angle_axis(torch.from_numpy(g["R"]).cuda()).cpu().numpy()
+    assert np.isfinite(aa).all()
+    assert np.abs(aa - g["aa64"]).max() < 2e-6 and np.abs(aa - g["aa32"]).max() < 2e-6
 
 
 def test_pointnet_tcgen05_vs_torch_and_oracle(full):

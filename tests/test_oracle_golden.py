@@ -214,3 +214,12 @@ def test_procrustes_golden(golden_dir):
     re_v, _ = pose_utils.reconstruction_error(g["S1"], g["S2"], mask=g["vis"], avg_joint=False)
     assert np.abs(re_v - g["re_vis"]).max() < 2e-5
     assert np.abs(pose_utils.reconstruction_error(g["S1"], g["S2"])[0] - g["re_avg"]).max() < 2e-5
+
+
+def test_angle_axis_oracle_vs_reference_golden(golden_dir):
+    """oracle/geometry.py::rotation_matrix_to_angle_axis pinned directly on the reference's own function
+    (utils/konia_transform.py:316-339), including theta -> 0 and theta = pi."""
+    from oracle import geometry
+    g = np.load(os.path.join(golden_dir, "angle_axis.npz"))
+    assert np.abs(geometry.rotation_matrix_to_angle_axis(g["R"].astype(np.float64)) - g["aa64"]).max() < 1e-14
+    assert np.abs(geometry.rotation_matrix_to_angle_axis(g["R"]) - g["aa32"]).max() < 5e-7
