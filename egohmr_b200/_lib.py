@@ -89,6 +89,7 @@ SIGNATURES = {
     "ehb_maxpool3x3s2_nhwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "ehb_scene_crop": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "ehb_procrustes_align": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "ehb_eval_metrics": (C.c_int, [_vp] + [_vp] * 8 + [C.c_int] * 4 + [_vp] * 5),
     "ehb_resnet_load": (C.c_int, [_vp, C.POINTER(ResnetWeights)]),
     "ehb_resnet_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "ehb_linear_f32": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

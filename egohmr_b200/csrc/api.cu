@@ -1322,6 +1322,26 @@ int ehb_procrustes_align(ehb_ctx* ctx, const float* s1, const float* s2, const f
   return 0;
 }
 
+int ehb_eval_metrics(ehb_ctx* ctx, const float* pred_joints, const float* pred_verts, const float* transl,
+                     const float* gt_joints, const float* gt_verts, const float* focal, const float* cam_cx,
+                     const float* cam_cy, int n_img, int n_samples, int n_joints, int n_verts, uint8_t* joint_vis,
+                     uint8_t* vert_vis, float* errors, float* diversity, void* stream_) {
+  if (!ctx || !pred_joints || !pred_verts || !transl || !gt_joints || !gt_verts || !focal || !cam_cx || !cam_cy ||
+      !joint_vis || !vert_vis || !errors || !diversity)
+    return fail("ehb_eval_metrics: null argument");
+  if (n_img <= 0 || n_samples <= 0 || n_joints <= 0 || n_joints > 256 || n_verts <= 0)
+    return fail("ehb_eval_metrics: need n_img, n_samples, n_verts > 0 and 0 < n_joints <= 256");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EHB_CUDA(ehb::launch_vis_mask(gt_joints, focal, cam_cx, cam_cy, joint_vis, n_img, n_joints, 1920.f, 1080.f, stream));
+  EHB_CUDA(ehb::launch_vis_mask(gt_verts, focal, cam_cx, cam_cy, vert_vis, n_img, n_verts, 1920.f, 1080.f, stream));
+  EHB_CUDA(ehb::launch_pose_errors(pred_joints, pred_verts, transl, gt_joints, gt_verts, joint_vis, vert_vis, errors, n_img,
+                                   n_samples, n_joints, n_verts, stream));
+  EHB_CUDA(ehb::launch_diversity(pred_joints, joint_vis, diversity, n_img, n_samples, n_joints, stream));
+  ctx->launches += 4;
+  return 0;
+}
+
 int ehb_resnet_load(ehb_ctx* ctx, const ehb_resnet_weights* w) {
   if (!ctx || !w || !w->convs) return fail("ehb_resnet_load: null argument");
   int expect = 1;

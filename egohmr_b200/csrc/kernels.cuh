@@ -262,6 +262,14 @@ cudaError_t launch_procrustes(const float* S1, const float* S2, const float* mas
 cudaError_t launch_nn_dist_sq(const float* q, const int32_t* q_index, int n_q, const float* r, const int32_t* r_index,
                               int n_r, int n_pairs, float* out, cudaStream_t stream);
 
+// evaluation reductions of the reference driver (test_egohmr.py:373-494), see metrics.cu
+cudaError_t launch_vis_mask(const float* pts, const float* focal, const float* cx, const float* cy, uint8_t* mask, int n_img,
+                            int n_pts, float W, float H, cudaStream_t stream);
+cudaError_t launch_pose_errors(const float* pj, const float* pv, const float* transl, const float* gj, const float* gv,
+                               const uint8_t* jmask, const uint8_t* vmask, float* out, int n_img, int S, int J, int V,
+                               cudaStream_t stream);
+cudaError_t launch_diversity(const float* pj, const uint8_t* jmask, float* out, int n_img, int S, int J, cudaStream_t stream);
+
 // ---- guidance backward (smpl_bwd.cu)
 cudaError_t launch_rotmat_to_aa(const float* R, float* aa, int n, cudaStream_t stream);
 // dL/dx [B][144] from dL/dverts [B][V][3], dL/djoints [B][24+E][3], dL/dfull_pose_aa [B][24][3] (each may be null).

@@ -245,4 +245,163 @@ cudaError_t launch_nn_dist_sq(const float* q, const int32_t* q_index, int n_q, c
   return cudaGetLastError();
 }
 
+
+// ------------------------------------------------------------------------------------------------ evaluation reductions
+// The metric block of the reference driver (test_egohmr.py:373-494) after the sampler: visibility masks of the ground
+// truth (:375-388), G-MPJPE / MPJPE / V2V per (image, sample) with their visible / invisible splits (:398-447), per-joint
+// standard deviation and average pairwise distance over the samples of an image (:449-494).  The reference evaluates them
+// with ~60 small torch launches, `.cpu().numpy()` copies and Python loops over the images of a batch.
+namespace {
+
+// mask[b][i] = 1 iff gt point i of image b projects into the 1920 x 1080 image (perspective_projection with identity
+// rotation and zero translation, utils/geometry.py:78-116; test_egohmr.py:375-388)
+__global__ void vis_mask_kernel(const float* __restrict__ pts, const float* __restrict__ focal, const float* __restrict__ cx,
+                                const float* __restrict__ cy, uint8_t* __restrict__ mask, int n_pts, float W, float H) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const float* p = pts + (static_cast<size_t>(b) * n_pts + i) * 3;
+  const float z = p[2];
+  const float px = __fdiv_rn(p[0], z), py = __fdiv_rn(p[1], z), pz = __fdiv_rn(z, z);
+  const float f = focal[b];
+  // K . [px, py, pz]: x = f*px + 0*py + cx*pz (einsum order), y = 0*px + f*py + cy*pz
+  const float x = __fadd_rn(__fadd_rn(__fmul_rn(f, px), __fmul_rn(0.f, py)), __fmul_rn(cx[b], pz));
+  const float y = __fadd_rn(__fadd_rn(__fmul_rn(0.f, px), __fmul_rn(f, py)), __fmul_rn(cy[b], pz));
+  mask[static_cast<size_t>(b) * n_pts + i] = (x >= 0.f && x < W && y >= 0.f && y < H) ? 1 : 0;
+}
+
+constexpr int EM_T = 256;
+
+__device__ inline float block_sum(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < EM_T / 32; ++i) t += red[i];
+  return t;
+}
+
+// block = (image, sample): out[b*S+s][0..8] = g_mpjpe (mean), g_vis (sum), g_invis (sum), mpjpe, mpjpe_vis, mpjpe_invis,
+// v2v (mean), v2v_vis (sum), v2v_invis (sum)
+__global__ void __launch_bounds__(EM_T) pose_error_kernel(const float* __restrict__ pj, const float* __restrict__ pv,
+                                                          const float* __restrict__ transl, const float* __restrict__ gj,
+                                                          const float* __restrict__ gv, const uint8_t* __restrict__ jmask,
+                                                          const uint8_t* __restrict__ vmask, float* __restrict__ out, int S,
+                                                          int J, int V) {
+  __shared__ float red[EM_T / 32];
+  const int bs = blockIdx.x, b = bs / S, t = threadIdx.x;
+  const float* pjb = pj + static_cast<size_t>(bs) * J * 3;
+  const float* gjb = gj + static_cast<size_t>(b) * J * 3;
+  const float pp[3] = {pjb[0], pjb[1], pjb[2]}, gp[3] = {gjb[0], gjb[1], gjb[2]};   // pelvis = joint 0
+  const float tr[3] = {transl[b * 3], transl[b * 3 + 1], transl[b * 3 + 2]};
+  float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int j = t; j < J; j += EM_T) {
+    float dg = 0.f, da = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const float p = pjb[j * 3 + c], g = gjb[j * 3 + c];
+      const float eg = (p + tr[c]) - g;                    // pred_keypoints_3d_full - gt_keypoints_3d
+      const float ea = (p - pp[c]) - (g - gp[c]);          // pelvis-aligned
+      dg += eg * eg;
+      da += ea * ea;
+    }
+    dg = sqrtf(dg);
+    da = sqrtf(da);
+    const bool vis = jmask[b * J + j] != 0;
+    acc[0] += dg; acc[1] += vis ? dg : 0.f; acc[2] += vis ? 0.f : dg;
+    acc[3] += da; acc[4] += vis ? da : 0.f; acc[5] += vis ? 0.f : da;
+  }
+  const float* pvb = pv + static_cast<size_t>(bs) * V * 3;
+  const float* gvb = gv + static_cast<size_t>(b) * V * 3;
+  for (int i = t; i < V; i += EM_T) {
+    float d = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      const float e = (pvb[i * 3 + c] - pp[c]) - (gvb[i * 3 + c] - gp[c]);
+      d += e * e;
+    }
+    d = sqrtf(d);
+    const bool vis = vmask[static_cast<size_t>(b) * V + i] != 0;
+    acc[6] += d; acc[7] += vis ? d : 0.f; acc[8] += vis ? 0.f : d;
+  }
+  for (int k = 0; k < 9; ++k) {
+    const float s = block_sum(acc[k], red);
+    if (t == 0) out[static_cast<size_t>(bs) * 9 + k] = (k == 0 || k == 3) ? s / J : (k == 6 ? s / V : s);
+  }
+}
+
+// block = image: out[b][0..5] = std_joints (all / visible / invisible joints), apd_joints (all / visible / invisible).
+// thread j < J handles joint j: unbiased std over the S samples of each coordinate of the pelvis-aligned joint, and the
+// sum over ordered sample pairs of the joint's distance.  Empty joint sets give NaN like the reference (mean of nothing).
+__global__ void __launch_bounds__(EM_T) diversity_kernel(const float* __restrict__ pj, const uint8_t* __restrict__ jmask,
+                                                         float* __restrict__ out, int S, int J) {
+  __shared__ float red[EM_T / 32];
+  const int b = blockIdx.x, t = threadIdx.x;
+  float sd = 0.f, pd = 0.f;
+  bool vis = false;
+  if (t < J) {
+    vis = jmask[b * J + t] != 0;
+    const float* base = pj + static_cast<size_t>(b) * S * J * 3;
+    for (int c = 0; c < 3; ++c) {
+      float mean = 0.f;
+      for (int s = 0; s < S; ++s) mean += base[(s * J + t) * 3 + c] - base[(s * J) * 3 + c];
+      mean /= S;
+      float var = 0.f;
+      for (int s = 0; s < S; ++s) {
+        const float d = (base[(s * J + t) * 3 + c] - base[(s * J) * 3 + c]) - mean;
+        var += d * d;
+      }
+      sd += sqrtf(var / (S - 1));
+    }
+    sd /= 3.f;
+    for (int s1 = 0; s1 < S; ++s1)
+      for (int s2 = 0; s2 < S; ++s2) {
+        float d = 0.f;
+        for (int c = 0; c < 3; ++c) {
+          const float e = (base[(s1 * J + t) * 3 + c] - base[(s1 * J) * 3 + c]) - (base[(s2 * J + t) * 3 + c] - base[(s2 * J) * 3 + c]);
+          d += e * e;
+        }
+        pd += sqrtf(d);
+      }
+  }
+  const float in = t < J ? 1.f : 0.f, v = (t < J && vis) ? 1.f : 0.f;
+  const float n_vis = block_sum(v, red), n_inv = block_sum(in - v, red);
+  const float s_all = block_sum(sd * in, red), s_vis = block_sum(sd * v, red), s_inv = block_sum(sd * (in - v), red);
+  const float p_all = block_sum(pd * in, red), p_vis = block_sum(pd * v, red), p_inv = block_sum(pd * (in - v), red);
+  if (t == 0) {
+    const float pairs = static_cast<float>(S) * (S - 1) * 2.f;      // the reference divides by n (n - 1) and by 2 (:472)
+    float* o = out + static_cast<size_t>(b) * 6;
+    o[0] = s_all / J;
+    o[1] = s_vis / n_vis;
+    o[2] = s_inv / n_inv;
+    o[3] = p_all / J / pairs;
+    o[4] = p_vis / n_vis / pairs;
+    o[5] = p_inv / n_inv / pairs;
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_vis_mask(const float* pts, const float* focal, const float* cx, const float* cy, uint8_t* mask, int n_img,
+                            int n_pts, float W, float H, cudaStream_t stream) {
+  if (n_img <= 0 || n_pts <= 0) return cudaSuccess;
+  vis_mask_kernel<<<dim3((n_pts + 255) / 256, n_img), 256, 0, stream>>>(pts, focal, cx, cy, mask, n_pts, W, H);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pose_errors(const float* pj, const float* pv, const float* transl, const float* gj, const float* gv,
+                               const uint8_t* jmask, const uint8_t* vmask, float* out, int n_img, int S, int J, int V,
+                               cudaStream_t stream) {
+  if (n_img <= 0 || S <= 0) return cudaSuccess;
+  pose_error_kernel<<<n_img * S, EM_T, 0, stream>>>(pj, pv, transl, gj, gv, jmask, vmask, out, S, J, V);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_diversity(const float* pj, const uint8_t* jmask, float* out, int n_img, int S, int J, cudaStream_t stream) {
+  if (n_img <= 0) return cudaSuccess;
+  if (J > EM_T) return cudaErrorInvalidValue;
+  diversity_kernel<<<n_img, EM_T, 0, stream>>>(pj, jmask, out, S, J);
+  return cudaGetLastError();
+}
+
 }  // namespace ehb

@@ -342,6 +342,22 @@ class Engine:
                                                 _dev_ptr(hat), _dev_ptr(err), _stream()))
         return hat, err
 
+    def eval_metrics(self, pred_joints, pred_verts, transl, gt_joints, gt_verts, focal, cam_cx, cam_cy):
+        """test_egohmr.py:373-494 for one batch (see include/egohmr_b200.h::ehb_eval_metrics).
+        -> joint_vis bool [bs,J], vert_vis bool [bs,V], errors [bs,S,9], diversity [bs,6]"""
+        bs, S, J = pred_joints.shape[:3]
+        V = pred_verts.shape[2]
+        dev = pred_joints.device
+        jv = torch.empty(bs, J, device=dev, dtype=torch.uint8)
+        vv = torch.empty(bs, V, device=dev, dtype=torch.uint8)
+        err = torch.empty(bs, S, 9, device=dev, dtype=torch.float32)
+        div = torch.empty(bs, 6, device=dev, dtype=torch.float32)
+        check(self.lib.ehb_eval_metrics(self._h, _dev_ptr(pred_joints), _dev_ptr(pred_verts), _dev_ptr(transl),
+                                        _dev_ptr(gt_joints), _dev_ptr(gt_verts), _dev_ptr(focal), _dev_ptr(cam_cx),
+                                        _dev_ptr(cam_cy), bs, S, J, V, _dev_ptr(jv, torch.uint8), _dev_ptr(vv, torch.uint8),
+                                        _dev_ptr(err), _dev_ptr(div), _stream()))
+        return jv.bool(), vv.bool(), err, div
+
     def nn_dist_sq(self, q, r, q_index=None, r_index=None, n_pairs=None):
         """Squared 1-NN distances: q [Nq_clouds,Pq,3] vs r [Nr_clouds,Pr,3], pair i = (q[q_index[i]], r[r_index[i]])
         (identity when the index is None) -> [n_pairs, Pq]."""

@@ -498,7 +498,11 @@ class EgoHMR(nn.Module):
                                                       ret_collision_mask=None)
             if int((losses == 0).sum()) >= B:
                 return torch.zeros(B, 144, device=x.device)
-            gv, gj, ga = torch.autograd.grad([-losses.mean()], [v, j, fp], allow_unused=True)
+            # The reference averages over the bodies of ONE val_losses call (:561), i.e. over the images of the batch.
+            # When the samples of an image are flattened into this batch (sample_many) the gradient of a body must not
+            # shrink with the number of samples: divide by the images, not by images x samples.
+            n_call = cond["bs"] if cond["bs"] * cond["num_samples"] == B else B
+            gv, gj, ga = torch.autograd.grad([-(losses.sum() / n_call)], [v, j, fp], allow_unused=True)
         c = lambda g: None if g is None else g.float().contiguous()
         grad = self.engine.smpl_backward(x, cond["betas_img"], c(gv), c(gj), c(ga)).reshape(-1, 24, 6)
         grad[:, 3:] = grad[:, 3:] * 2            # :564-565

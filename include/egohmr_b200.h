@@ -210,6 +210,22 @@ int ehb_scene_crop(ehb_ctx* ctx, const float* verts, int n_bodies, int n_verts, 
 int ehb_procrustes_align(ehb_ctx* ctx, const float* s1, const float* s2, const float* mask, int n_problems, int n_points,
                          float* s1_hat, float* err, void* stream);
 
+/* The metric block of the evaluation driver (test_egohmr.py:373-494) for one batch, four launches instead of ~60 torch
+ * launches, host copies and per-image Python loops:
+ *   pred_joints [n_img][n_samples][n_joints][3], pred_verts [n_img][n_samples][n_verts][3]  SMPL outputs, NOT pelvis-aligned
+ *   transl [n_img][3]; gt_joints [n_img][n_joints][3]; gt_verts [n_img][n_verts][3]; focal, cam_cx, cam_cy [n_img] (pixels)
+ * outputs:
+ *   joint_vis [n_img][n_joints], vert_vis [n_img][n_verts] uint8: the ground truth projects into the 1920 x 1080 frame (:375-388)
+ *   errors [n_img][n_samples][9] = G-MPJPE mean, visible sum, invisible sum (:398-406) | MPJPE (pelvis-aligned) mean, vis, invis
+ *          (:408-416) | V2V mean, vis, invis (:438-447)
+ *   diversity [n_img][6] = per-joint std over the samples: all / visible / invisible joints (:449-468) | APD: all / vis / invis
+ *          (:470-494); empty joint sets give NaN, as the reference's mean over nothing does.
+ * PA-MPJPE (:418-436) is ehb_procrustes_align on the pelvis-aligned joints. */
+int ehb_eval_metrics(ehb_ctx* ctx, const float* pred_joints, const float* pred_verts, const float* transl,
+                     const float* gt_joints, const float* gt_verts, const float* focal, const float* cam_cx,
+                     const float* cam_cy, int n_img, int n_samples, int n_joints, int n_verts, uint8_t* joint_vis,
+                     uint8_t* vert_vis, float* errors, float* diversity, void* stream);
+
 /* ResNet-50 image encoder (models/resnet.py:100-150: torchvision-style v1.5 bottlenecks, global average pool, no fc),
  * one entry per convolution with the BatchNorm2d that follows it, in network order: the stem, then for every
  * bottleneck conv1, conv2, conv3 and — in the first block of a stage — downsample.  HOST. */

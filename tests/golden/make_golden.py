@@ -191,6 +191,34 @@ def procrustes_case():
     print("wrote procrustes", rec["re_avg"])
 
 
+def cfg2_case(name, dtype, n_img=8, S=10, seed=3):
+    """configs[1] at its own denoiser size and sample count, through the reference DRIVER's loop (test_egohmr.py:247-266 via
+    baseline/ref_harness.driver_loop): 8 distinct images x 10 sequential samples, DDIM-5 of T=50, hid 1024 / 4 blocks.
+    The GPU test replicates the 8 images 8 times -> the full 64 x 10 = 640-body batch of the benchmark."""
+    model, mean, std = build_reference(1024, 4, dtype, 0)
+    diffusion = ref_standins.build_sampler(50, "ddim5", mean, std, dtype)
+    batch = to_torch(synth.make_batch(seed, n_img), dtype)
+    noise = synth.make_noise(seed, S, n_img, 5)                       # [S, 6, n_img, 144]
+    feed = NoiseFeed([noise[n][k] for n in range(S) for k in range(6)], dtype)
+    old_randn, old_randn_like = torch.randn, torch.randn_like
+    torch.randn, torch.randn_like = feed.randn, feed.randn_like
+    xs = []
+    try:
+        with torch.no_grad():
+            for n in range(S):
+                out = diffusion.val_losses(model=model, batch=batch, shape=[n_img, 144], progress=False, clip_denoised=False,
+                                           cur_epoch=0, timestep_respacing="ddim5", cond_fn_with_grad=False,
+                                           cond_grad_weight=1.0, compute_loss=False)
+                xs.append({k: out[k].detach().clone().numpy() for k in ("pred_x_start", "pred_keypoints_3d")} |
+                          {k: v.detach().clone().numpy() for k, v in out["pred_smpl_params"].items()})
+    finally:
+        torch.randn, torch.randn_like = old_randn, old_randn_like
+    rec = {k: np.stack([x[k] for x in xs], axis=1) for k in xs[0]}    # [n_img, S, ...]
+    rec.update(seed=seed, n_img=n_img, S=S)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **rec)
+    print("wrote", name, {k: getattr(v, "shape", v) for k, v in rec.items()})
+
+
 def angle_axis_case():
     """utils/konia_transform.py:316-339 rotation_matrix_to_angle_axis straight from the reference: generic rotations,
     theta -> 0 (identity and tiny angles), theta = pi about several axes, and every branch of the quaternion conversion."""
@@ -328,6 +356,10 @@ if __name__ == "__main__":
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "procrustes":
         procrustes_case()
+        raise SystemExit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg2":
+        cfg2_case("cfg2_ddim5_8img_x10_hid1024_f64", torch.float64)
+        cfg2_case("cfg2_ddim5_8img_x10_hid1024_f32", torch.float32)
         raise SystemExit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "aa":
         angle_axis_case()

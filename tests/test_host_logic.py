@@ -6,6 +6,7 @@ import re
 
 import numpy as np
 import pytest
+import torch
 
 from egohmr_b200 import _lib
 from egohmr_b200.diffusion.model_util import create_gaussian_diffusion
@@ -94,3 +95,34 @@ def test_preprocess_stats_loader(tmp_path):
     np.savez(d / "preprocess_stats.npz", Xmean=mean)
     with pytest.raises(KeyError):
         checkpoint.load_preprocess_stats(str(tmp_path / "run" / "x.pt"))
+
+
+def test_stage1_handoff_and_scene_cloud_readers(tmp_path):
+    """`results.pkl['pred_cam_full_list']` (egobody_dataset.py:94-98) and the per-frame scene cloud `.npy`
+    (:213-225, :270-273) in the formats the reference's dataloader reads."""
+    import pickle
+    from egohmr_b200 import data
+    rng = np.random.default_rng(0)
+    cams = rng.normal(0, 1, (10, 3))
+    with open(tmp_path / "results.pkl", "wb") as fp:
+        pickle.dump({"pred_cam_full_list": cams, "other": 1}, fp)
+    t = data.load_stage1_translations(tmp_path / "results.pkl", spacing=3)
+    assert t.dtype == np.float32 and t.shape == (4, 3) and np.array_equal(t, cams.astype(np.float64)[::3].astype(np.float32))
+    with open(tmp_path / "bad.pkl", "wb") as fp:
+        pickle.dump({"pred_cam": cams}, fp)
+    with pytest.raises(KeyError):
+        data.load_stage1_translations(tmp_path / "bad.pkl")
+    pts = rng.normal(0, 1, (20000, 3))
+    np.save(tmp_path / "frame_01234.npy", pts)
+    T = np.eye(4)
+    T[:3, :3] = np.linalg.qr(rng.normal(0, 1, (3, 3)))[0]
+    T[:3, 3] = [0.1, -0.2, 3.0]
+    got = data.load_scene_cloud(tmp_path / "frame_01234.npy", T, downsample_rate=2, n_points=10000)
+    want = (pts @ T[:3, :3].T + T[:3, 3]).astype(np.float32)[::2]           # utils/geometry.py:137-141
+    assert got.dtype == np.float32 and np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        data.load_scene_cloud(tmp_path / "frame_01234.npy", T, n_points=5000)
+    b = data.make_batch(np.zeros((2, 3, 224, 224), np.float32), np.ones((2, 25, 3)), [1500.0, 3000.0], [960, 960], [540, 540],
+                        np.zeros((2, 2)), [300, 400], t[:2], [got, got], device="cpu")
+    assert b["fx"].tolist() == [1.0, 2.0] and b["scene_pcd_verts_full"].shape == (2, 10000, 3)
+    assert b["smpl_params"]["transl"] is b["stage1_transl_full"] and b["img"].dtype == torch.float32
