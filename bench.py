@@ -259,6 +259,8 @@ def run_reference_cuda(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
+    """nvidia-smi polled every 20 ms in the background; rows are time-stamped on receipt so that `stop(t0, t1)` keeps the
+    samples taken DURING the timed region (nvidia-smi needs ~1 s to start: start it well before)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -269,7 +271,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -277,15 +279,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 is None or (t0 <= ts <= t1 + 0.03)]
+        window = "timed region"
+        if not rows:     # region shorter than the polling period: fall back to everything seen (warm-up replays included)
+            rows, window = [r for _, r in self.rows], "warm-up + timed region"
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -296,7 +307,7 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -427,6 +438,8 @@ def run_b200(args):
     l0 = model.engine.launch_count()
     eager_step(batch_dev)
     launches_per_pass = model.engine.launch_count() - l0
+    clocks = ClockSampler(local)
+    clocks.start()
     sampler = None
     if not args.no_graph:
         sampler = diffusion.capture_sample_many(model, batch_dev, S, RESPACING)
@@ -450,10 +463,11 @@ def run_b200(args):
         return e0.elapsed_time(e1)
 
     # ---- device-resident leg (value)
-    clocks = ClockSampler(local)
-    clocks.start()
+    clocks.wait_first()
+    timed_steps(one_step, 2)
+    w0 = time.time()
     ms = timed_steps(one_step, args.steps)
-    clk = clocks.stop()
+    clk = clocks.stop(w0, time.time())
     launches = launches_per_pass * args.steps
     eager_ms = timed_steps(eager_step, args.steps) if sampler is not None else ms
     # the same pass with the image encoder on cuDNN instead of the native tcgen05 convolution GEMMs, at torch's default

@@ -99,17 +99,26 @@ int make_tmap_f16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t col
 // 4-D fp16 NHWC activation [N][H][W][C2] (C2 = hi(C) | lo(C) halves per pixel): box = nb images x th*stride rows x
 // tw*stride columns x 64 halves, traversed with element stride `stride` in H and W (so th x tw pixels are loaded);
 // 128-byte swizzle like the 2-D maps.
+// `window` > 0: an overlapping-window view for the space-to-depth stem — a "pixel" of the map is the 64 halves starting
+// at physical pixel x (physical pixels hold `window` = 16 halves, so consecutive map pixels overlap by 48 halves); W is
+// then the number of valid window positions.
 int make_tmap_f16_nhwc(CUtensorMap* tm, const void* base, uint64_t N, uint64_t H, uint64_t W, uint64_t C2, uint32_t nb,
-                       uint32_t th, uint32_t tw, uint32_t stride) {
+                       uint32_t th, uint32_t tw, uint32_t stride, uint32_t window = 0, uint64_t W_phys = 0) {
   auto fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[4] = {C2, W, H, N};
   cuuint64_t gstride[3] = {C2 * sizeof(__half), W * C2 * sizeof(__half), H * W * C2 * sizeof(__half)};
+  if (window) {
+    gdim[0] = 64;
+    gstride[0] = window * sizeof(__half);
+    gstride[1] = W_phys * window * sizeof(__half);
+    gstride[2] = H * W_phys * window * sizeof(__half);
+  }
   cuuint32_t box[4] = {64, tw * stride, th * stride, nb};
   cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (4-D) failed with CUresult " + std::to_string(int(r)));
   return 0;
 }
@@ -179,6 +188,7 @@ struct ehb_ctx {
   int num_sms = 0;
   int64_t launches = 0;
   int gemm_mode = 0;   // 0 = tcgen05 CTA-pair kernel, 1 = fp32 FFMA check path, 2 = tcgen05 one-CTA kernel
+  int pdl = 1;         // hidden-layer launches use programmatic dependent launch (set-up overlaps the previous layer's tail)
   float act_scale = 8.f;
 
   // ---- denoiser
@@ -236,6 +246,7 @@ struct ehb_ctx {
   // ---- ResNet-50 image encoder (conv_umma.cu)
   struct ConvPlan {
     int cout = 0, cin = 0, kh = 0, kw = 0, stride = 1, pad = 0, Kp = 0;
+    bool stem = false;   // the space-to-depth stem: windowed tensor map, hi / lo planes
     float w_scale = 1.f;
     DevBuf w_hl, bias;
     std::vector<float> wf, bias_h;   // folded fp32 weights / bias (kept on the host until the scales are final)
@@ -253,7 +264,7 @@ struct ehb_ctx {
   // k-blocks (of 64) chained into one TMEM accumulation; longer contractions are summed chunk by chunk in fp32 registers
   // by the epilogue warps (0 = never split).  See DESIGN.md "K9 numerics".
   int rn_kc = 2;
-  DevBuf rn_col, rn_x[2], rn_y1, rn_y2;
+  DevBuf rn_col, rn_x[2], rn_y1, rn_y2, rn_s2d;
 
   DevBuf overflow, splitk;
 
@@ -579,10 +590,10 @@ static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
   p.write_f32 = second ? 1 : 0;
   p.write_hl = (l != L - 1 || ctx->nl_loaded) ? 1 : 0;   // the non-local block consumes the last layer's operand
   if (ctx->gemm_mode == 0) {
-    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB2, p, ctx->num_sms, 2, stream));
+    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB2, p, ctx->num_sms, 2, ctx->pdl != 0, stream));
     ctx->launches += 1;
   } else if (ctx->gemm_mode == 2) {
-    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB, p, ctx->num_sms, 1, stream));
+    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB, p, ctx->num_sms, 1, ctx->pdl != 0, stream));
     ctx->launches += 1;
   } else {
     const size_t rows = static_cast<size_t>(ctx->n_mtiles) * ehb::TILE_ROWS;
@@ -1362,6 +1373,40 @@ int ehb_resnet_load(ehb_ctx* ctx, const ehb_resnet_weights* w) {
     auto* pl = new ehb_ctx::ConvPlan();
     ctx->rn_convs.push_back(pl);
     pl->cout = c.cout; pl->cin = c.cin; pl->kh = c.kh; pl->kw = c.kw; pl->stride = c.stride; pl->pad = c.pad;
+    if (i == 0) {
+      // The 7x7 / stride 2 / pad 3 stem on 3 channels (models/resnet.py:109) == a 4x4 / stride 1 / pad 2 convolution on the
+      // space-to-depth image (16 channels: (dy*2 + dx)*3 + c, 12 used): input row 2*oy - 3 + ky = 2*(oy - 2 + ty) + dy with
+      // ky = 2*ty + dy - 1 (taps with ky or kx outside 0..6 get zero weights).  The implicit-GEMM kernel then reads the image
+      // through TMA boxes; no im2col matrix (617 MB written and re-read for 64 images) exists.
+      if (c.kh != 7 || c.kw != 7 || c.cin != 3 || c.stride != 2 || c.pad != 3) return fail("ehb_resnet_load: unexpected stem");
+      pl->Kp = 256;
+      std::vector<float> wf(static_cast<size_t>(c.cout) * 256, 0.f), bias(c.cout);
+      float maxabs = 0.f;
+      for (int co = 0; co < c.cout; ++co) {
+        const double s = double(c.bn_weight[co]) / std::sqrt(double(c.bn_var[co]) + double(c.bn_eps));
+        bias[co] = float(double(c.bn_bias[co]) - double(c.bn_mean[co]) * s);
+        for (int ty = 0; ty < 4; ++ty)
+          for (int tx = 0; tx < 4; ++tx)
+            for (int dy = 0; dy < 2; ++dy)
+              for (int dx = 0; dx < 2; ++dx) {
+                const int ky = 2 * ty + dy - 1, kx = 2 * tx + dx - 1;
+                if (ky < 0 || ky > 6 || kx < 0 || kx > 6) continue;
+                for (int ci = 0; ci < 3; ++ci) {
+                  const float v = float(double(c.weight[((static_cast<size_t>(co) * 3 + ci) * 7 + ky) * 7 + kx]) * s);
+                  wf[static_cast<size_t>(co) * 256 + (ty * 4 + tx) * 16 + (dy * 2 + dx) * 3 + ci] = v;
+                  maxabs = std::max(maxabs, std::fabs(v));
+                }
+              }
+      }
+      if (!std::isfinite(maxabs)) return fail("ehb_resnet_load: non-finite weight");
+      // what the kernel executes: 4 vertical taps over 64-half windows (4 horizontal taps x 16 channels), see stem_s2d_kernel
+      pl->cin = 64; pl->kh = 4; pl->kw = 1; pl->stride = 1; pl->pad = 2;
+      pl->stem = true;
+      pl->w_scale = pow2_scale(maxabs);
+      pl->wf.swap(wf);
+      pl->bias_h.swap(bias);
+      continue;
+    }
     const int K = c.kh * c.kw * c.cin;
     pl->Kp = (K + 63) / 64 * 64;
     // fold BatchNorm (eval): y = conv(x; W) * s + (beta - mean * s),  s = gamma / sqrt(var + eps)
@@ -1468,7 +1513,9 @@ static int rn_gemm_implicit(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __ha
   const bool chunked = ctx->rn_kc > 0 && c.Kp / 64 > ctx->rn_kc;
   const int bn = ehb::conv_gemm_tile_n(c.cout, static_cast<long long>(n_tiles) * 128, ctx->num_sms, chunked ? 128 : 256);
   CUtensorMap tA, tB;
-  if (make_tmap_f16_nhwc(&tA, x, n, H, W, 2 * static_cast<uint64_t>(c.cin), nb, th, Wo, c.stride)) return 1;
+  if (c.stem) {   // x = planes [2][n][H][W + 4][16]: both planes are "images" of one windowed map (lo = image n_img + i)
+    if (make_tmap_f16_nhwc(&tA, x, 2 * static_cast<uint64_t>(n), H, Wo, 64, nb, th, Wo, 1, 16, W + 4)) return 1;
+  } else if (make_tmap_f16_nhwc(&tA, x, n, H, W, 2 * static_cast<uint64_t>(c.cin), nb, th, Wo, c.stride)) return 1;
   if (make_tmap_f16(&tB, c.w_hl.p, c.cout, 2 * static_cast<uint64_t>(c.Kp), bn / 2)) return 1;
   ehb::ConvGemmParams p{};
   p.bias = c.bias.as<float>();
@@ -1485,6 +1532,8 @@ static int rn_gemm_implicit(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __ha
   p.relu = relu;
   p.kc = ctx->rn_kc;
   p.implicit = 1;
+  p.pad_w = c.stem ? 0 : c.pad;
+  p.lo_plane = c.stem ? n : 0;
   p.Cin = c.cin; p.kw = c.kw; p.pad = c.pad; p.stride = c.stride;
   p.Ho = Ho; p.Wo = Wo; p.th = th; p.nb = nb; p.tiles_per_img = tpi; p.n_img = n;
   EHB_CUDA(ehb::launch_conv_gemm(tA, tB, tA, tB, p, ctx->num_sms, stream));
@@ -1495,6 +1544,12 @@ static int rn_gemm_implicit(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __ha
 int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm) {
   if (!ctx) return fail("null ctx");
   ctx->rn_implicit = implicit_gemm ? 1 : 0;
+  return 0;
+}
+
+int ehb_debug_set_pdl(ehb_ctx* ctx, int on) {
+  if (!ctx) return fail("null ctx");
+  ctx->pdl = on ? 1 : 0;
   return 0;
 }
 
@@ -1557,7 +1612,9 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
   const auto& cv = ctx->rn_convs;
   // ---- buffer sizes for this batch
   const int H1 = out_dim(h, 7, 2, 3), W1 = out_dim(w, 7, 2, 3), H2 = out_dim(H1, 3, 2, 1), W2 = out_dim(W1, 3, 2, 1);
-  size_t col_bytes = pad_rows(static_cast<long long>(n) * H1 * W1) * 2 * cv[0]->Kp * sizeof(__half);
+  // space-to-depth image: planes [hi | lo][n][H2][W2 + 4][16] (stem_s2d_kernel writes every element, pad columns included)
+  const size_t s2d_bytes = 2 * static_cast<size_t>(n) * ((h + 1) / 2) * ((w + 1) / 2 + 4) * 16 * sizeof(__half) + 256;
+  size_t col_bytes = 256;
   size_t x_bytes = pad_rows(static_cast<long long>(n) * H1 * W1) * 2 * cv[0]->cout * sizeof(__half);
   size_t y_bytes = 0;
   {
@@ -1581,6 +1638,7 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
         W = Wo;
       }
   }
+  EHB_CUDA(ctx->rn_s2d.ensure(s2d_bytes, true));
   EHB_CUDA(ctx->rn_col.ensure(col_bytes, true));
   EHB_CUDA(ctx->rn_x[0].ensure(x_bytes, true));
   EHB_CUDA(ctx->rn_x[1].ensure(x_bytes, true));
@@ -1590,9 +1648,11 @@ int ehb_resnet_forward(ehb_ctx* ctx, const float* img, int n, int h, int w, floa
   // ---- stem: conv 7x7 / 2 + BN + ReLU, max-pool 3x3 / 2  (models/resnet.py:109-113, 140-143)
   {
     const auto& c0 = *cv[0];
-    if (c0.kh != 7 || c0.kw != 7 || c0.cin != 3 || c0.stride != 2 || c0.pad != 3) return fail("ehb_resnet_forward: unexpected stem");
-    EHB_CUDA(ehb::launch_im2col_stem(img, col, n, h, w, H1, W1, c0.Kp, ctx->rn_act_scale, stream));
-    if (rn_gemm(ctx, c0, col, static_cast<long long>(n) * H1 * W1, nullptr, ctx->rn_x[1].as<__half>(), 1, stream)) return 1;
+    if (W1 > 128) return fail("ehb_resnet_forward: images wider than 256 pixels are not supported by the implicit-GEMM stem");
+    // image -> space-to-depth hi/lo operand (51 MB for 64 images), then the stem as an implicit GEMM over it
+    EHB_CUDA(ehb::launch_stem_s2d(img, ctx->rn_s2d.as<__half>(), n, h, w, ctx->rn_act_scale, stream));
+    if (rn_gemm_implicit(ctx, c0, ctx->rn_s2d.as<__half>(), n, (h + 1) / 2, (w + 1) / 2, H1, W1, ctx->rn_x[1].as<__half>(), 1, stream))
+      return 1;
     EHB_CUDA(ehb::launch_maxpool_hl(ctx->rn_x[1].as<__half>(), ctx->rn_x[0].as<__half>(), n, H1, W1, c0.cout, stream));
     ctx->launches += 2;
   }

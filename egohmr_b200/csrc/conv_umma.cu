@@ -61,7 +61,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
-  float* addv_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + BAR_BYTES);
   uint8_t* scratch_s = smem + STAGES * STAGE_BYTES + BAR_BYTES + ADDV_BYTES;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -124,10 +123,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
           if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * (2 * a_box_bytes + 2 * B_BYTES));
           if (p.implicit) {
-            const int tap = kb / cpk, c = (kb % cpk) * BK;
-            const int wi = tap % p.kw - p.pad, hi = hi0 + tap / p.kw;
-            ptx::tma_load_4d_2sm(s, &tmA, lfull, c, wi, hi, n0);
-            ptx::tma_load_4d_2sm(s + A_BYTES, &tmA, lfull, p.Cin + c, wi, hi, n0);
+            {
+              const int tap = kb / cpk, c = (kb % cpk) * BK;
+              const int wi = tap % p.kw - p.pad_w, hi = hi0 + tap / p.kw;
+              ptx::tma_load_4d_2sm(s, &tmA, lfull, c, wi, hi, n0);
+              // the lo half: the upper channels of the same pixel, or (lo_plane) a second plane of images behind the first
+              if (p.lo_plane) ptx::tma_load_4d_2sm(s + A_BYTES, &tmA, lfull, c, wi, hi, n0 + p.lo_plane);
+              else ptx::tma_load_4d_2sm(s + A_BYTES, &tmA, lfull, p.Cin + c, wi, hi, n0);
+            }
             ptx::tma_load_2d_2sm(s + 2 * A_BYTES, &tmB, lfull, kb * BK, b_row);
             ptx::tma_load_2d_2sm(s + 2 * A_BYTES + B_BYTES, &tmB, lfull, p.K + kb * BK, b_row);
             if (++stage == STAGES) {
@@ -212,11 +215,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int CHUNKS = HALF / 32;
     const int q = warp & 3;               // TMEM lane quadrant
     const int col_half = warp >> 2;
-    const int et = threadIdx.x;           // 0..255
     const float inv_act = 1.f / p.act_scale;
     uint8_t* scratch = scratch_s + warp * EPI_SCRATCH_BYTES;
     int as = 0;
-    uint32_t aphase = 0, tpar = 0;
+    uint32_t aphase = 0;
     float amax = 0.f;
     const int n_chunks = (KB + kc - 1) / kc;
     float acc[CHUNKED ? HALF : 1];        // fp32 running sum of the first n_chunks - 1 accumulation chunks
@@ -234,10 +236,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const long long row = tile_first + q * 32 + lane;
       const bool valid = q * 32 + lane < tile_rows;
       const long long row0w = row - lane;                  // first row of this warp's 32
-      float* addv = addv_s + tpar * 256;
-      tpar ^= 1;
-      if (et < BN) addv[et] = __ldg(p.bias + n_tile * BN + et);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // bias of this warp's columns: broadcast loads (every lane reads the same 16 bytes), no block-wide staging barrier
+      const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n_tile * BN + col_half * HALF);
       // the identity block of the first chunk is requested before the accumulator is awaited, every further chunk's
       // while the previous one is processed: its global latency never sits on the epilogue's critical path
       const long long rows_valid = tile_rows - q * 32;     // rows of this warp's 32 that exist
@@ -298,10 +298,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int c = 0; c < 32; ++c) v[c] += acc[ch * 32 + c];
           }
         }
-        const int ct = col_half * HALF + ch * 32;          // column within the tile
-        const int cg = n_tile * BN + ct;                   // output channel
+        const int cg = n_tile * BN + col_half * HALF + ch * 32;   // output channel
 #pragma unroll
-        for (int c = 0; c < 32; ++c) v[c] = v[c] * p.acc_scale_inv + addv[ct + c];
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 b = __ldg(bias4 + ch * 8 + c4);
+          v[4 * c4 + 0] = v[4 * c4 + 0] * p.acc_scale_inv + b.x;
+          v[4 * c4 + 1] = v[4 * c4 + 1] * p.acc_scale_inv + b.y;
+          v[4 * c4 + 2] = v[4 * c4 + 2] * p.acc_scale_inv + b.z;
+          v[4 * c4 + 3] = v[4 * c4 + 3] * p.acc_scale_inv + b.w;
+        }
         // global accesses go through the warp transposes of epilogue.cuh: 8 rows x 64 B per instruction
         if (p.res_hl) {   // identity branch of the bottleneck (models/resnet.py:93-94), stored as its own hi/lo operand
           uint4 rh[4], rl[4];

@@ -129,6 +129,12 @@ gcn_hidden_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if (CTAS == 2) ptx::cluster_sync();   // the peer's barriers must be initialised before anything remote touches them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  // Programmatic dependent launch: the 8 hidden layers of a pass are launched back to back; the next layer's CTAs may
+  // take over SMs as this layer's CTAs retire and run the set-up above (barriers, TMEM allocation, tensor-map prefetch)
+  // while the tail of this layer still computes.  Everything below reads the previous layer's activations or overwrites
+  // buffers it may still be reading, so it waits for the prerequisite grid here.
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
@@ -383,7 +389,7 @@ int gcn_hidden_umma_bk() { return BK; }
 
 template <int CTAS>
 static cudaError_t launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p, int num_sms,
-                               cudaStream_t stream) {
+                               bool pdl, cudaStream_t stream) {
   static bool attr_set = false;
   auto kern = gcn_hidden_umma_kernel<CTAS>;
   if (!attr_set) {
@@ -399,24 +405,26 @@ static cudaError_t launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, c
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg<CTAS>::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CTAS;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl ? 2 : 1;
   return cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p);
 }
 
 cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
-                                   int num_sms, int ctas, cudaStream_t stream) {
+                                   int num_sms, int ctas, bool pdl, cudaStream_t stream) {
   if (p.C % 128 != 0 || p.n_ntiles != p.C / 128) return cudaErrorInvalidValue;
   if (ctas == 2) {
     if (p.n_mtiles % 2 != 0) return cudaErrorInvalidValue;  // the activation buffers are padded to whole pair-tiles
-    return launch_impl<2>(tmA, tmB, p, num_sms, stream);
+    return launch_impl<2>(tmA, tmB, p, num_sms, pdl, stream);
   }
-  return launch_impl<1>(tmA, tmB, p, num_sms, stream);
+  return launch_impl<1>(tmA, tmB, p, num_sms, pdl, stream);
 }
 
 }  // namespace ehb

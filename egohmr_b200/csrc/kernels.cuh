@@ -38,8 +38,10 @@ struct HiddenLayerParams {
 // launchers (gcn_umma.cu / gcn_simt.cu / smpl_lbs.cu)
 // ctas = 1: one CTA per 128x256 tile (tmB box = 256 rows); ctas = 2: CTA pairs, tcgen05 cta_group::2 (tmB box = 128
 // rows, n_mtiles even).
+// pdl: launch with programmatic stream serialization (the kernel overlaps its set-up with the tail of the previous
+// kernel in the stream and waits for it with griddepcontrol.wait before touching global memory)
 cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
-                                   int num_sms, int ctas, cudaStream_t stream);
+                                   int num_sms, int ctas, bool pdl, cudaStream_t stream);
 size_t gcn_hidden_umma_smem_bytes();
 int gcn_hidden_umma_bk();   // fp16 elements per TMA box row (32: SWIZZLE_64B, 64: SWIZZLE_128B)
 #ifndef EHB_UMMA_BK
@@ -226,7 +228,9 @@ struct ConvGemmParams {
   // zero padding is TMA's out-of-bounds fill, no im2col matrix exists.  An M tile is `nb` images x `th` full output
   // rows (th * Wo * nb <= 128); its output rows are contiguous, first row = (n0 * Ho + ho0) * Wo.
   int implicit;
-  int Cin, kw, pad, stride;   // K = kh * kw * Cin, k = (ky * kw + kx) * Cin + c
+  int Cin, kw, pad, stride;   // K = kh * kw * Cin, k = (ky * kw + kx) * Cin + c; `pad` rows above, `pad_w` columns left
+  int pad_w;
+  int lo_plane;               // 0: a pixel holds [hi(Cin) | lo(Cin)]; > 0: the lo halves are images n + lo_plane of the tensor
   int Ho, Wo, th, nb, tiles_per_img, n_img;
 };
 int conv_gemm_tile_n(int cout, long long rows, int num_sms, int max_bn = 256);   // 256, 128 or 64 output channels per tile
@@ -236,9 +240,10 @@ cudaError_t launch_conv_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, con
 // dst [N*Ho*Wo][hi(KH*KW*C) | lo(KH*KW*C)], k = (ky*KW + kx)*C + c, zero outside the image.  C % 8 == 0.
 cudaError_t launch_im2col_hl(const __half* src, __half* dst, int N, int H, int W, int C, int KH, int KW, int stride,
                              int pad, int Ho, int Wo, cudaStream_t stream);
-// the stem's im2col straight from the fp32 NCHW image: dst [N*Ho*Wo][hi(Kp) | lo(Kp)], k = (ky*7 + kx)*3 + c < 147
-cudaError_t launch_im2col_stem(const float* img, __half* dst, int N, int H, int W, int Ho, int Wo, int Kp, float act_scale,
-                               cudaStream_t stream);
+// space-to-depth of the fp32 NCHW image for the stem as a stride-1 4x4 convolution on 16 channels: two planes (hi, lo) of
+// dst [2][N][H2][W2 + 4][16], channel (dy*2 + dx)*3 + c = act_scale * img[n][c][2*y2 + dy][2*(x - 2) + dx] (12 used, 4 zero);
+// two zero columns on each side; H2 = (H+1)/2, W2 = (W+1)/2
+cudaError_t launch_stem_s2d(const float* img, __half* dst, int N, int H, int W, float act_scale, cudaStream_t stream);
 // MaxPool2d(3, 2, 1) on an NHWC hi/lo activation (the pair with the largest hi + lo wins; exact in fp32)
 cudaError_t launch_maxpool_hl(const __half* src, __half* dst, int N, int H, int W, int C, cudaStream_t stream);
 // global average pool: [N][HW][hi(C) | lo(C)] -> fp32 [N][C]

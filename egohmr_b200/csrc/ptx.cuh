@@ -144,8 +144,12 @@ __device__ __forceinline__ uint32_t mapa(uint32_t cta_addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
   return r;
 }
+// Arrive on a barrier in another CTA of the cluster.  Default semantics (.release at .cta scope), as CUTLASS's
+// ClusterBarrier::arrive does: the barrier only orders tensor-memory traffic here (tcgen05.wait::ld + tcgen05.fence before
+// it).  An explicit .release.cluster makes the arriving warp drain all its outstanding GLOBAL stores first (ncu: `membar`
+// was the second-largest stall of the convolution kernel's epilogue warps).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -259,6 +263,13 @@ __device__ __forceinline__ void umma_commit_2sm_mc_elect(uint64_t* bar, uint16_t
       "h"(cta_mask)
       : "memory");
 }
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel in the stream (launched with cudaLaunchAttributeProgrammaticStreamSerialization) may
+// start occupying SMs as this grid's CTAs retire, instead of after the whole grid has drained; wait: block until the
+// prerequisite grid has completed and its memory operations are visible.  Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major operand tile whose rows are exactly one swizzle span wide

@@ -1,5 +1,5 @@
-// Data movers around the ResNet-50 convolution GEMMs (conv_umma.cu): im2col of hi/lo activations, the stem's im2col
-// from the fp32 image, max-pool and global average pool on hi/lo activations.  All HBM-bound, 128-bit accesses.
+// Data movers around the ResNet-50 convolution GEMMs (conv_umma.cu): im2col of hi/lo activations, the stem's
+// space-to-depth transform of the fp32 image, max-pool and global average pool on hi/lo activations.  All HBM-bound, 128-bit accesses.
 #include "kernels.cuh"
 
 namespace ehb {
@@ -33,46 +33,39 @@ __global__ void __launch_bounds__(256) im2col_hl_kernel(const uint4* __restrict_
   dst[dp + K8] = lo;
 }
 
-// The 7x7 / stride 2 / pad 3 stem (models/resnet.py:109-110).  Block = 32 consecutive output pixels of one output row:
-// the 7 x 69 x 3 input patch they share is staged in shared memory with coalesced reads (each input value is used by
-// up to 4 x 7 outputs), then every thread emits 8 consecutive k of one pixel, so the 384-byte hi / lo row segments of a
-// pixel are written by 24 consecutive threads.
-constexpr int STEM_TW = 32;
-constexpr int STEM_PW = 2 * STEM_TW + 5;   // 69 input columns
-__global__ void __launch_bounds__(256) im2col_stem_kernel(const float* __restrict__ img, uint4* __restrict__ dst, int N, int H,
-                                                          int W, int Ho, int Wo, int Kp8, float act_scale) {
-  __shared__ float patch[3][7][STEM_PW + 1];
-  __shared__ int16_t koff[192];   // k -> offset of (c, ky, kx) inside `patch` (-1: K padding), instead of div/mod per element
-  for (int k = threadIdx.x; k < 192; k += blockDim.x) {
-    const int tap = k / 3, c = k % 3;
-    koff[k] = k < 147 ? static_cast<int16_t>((c * 7 + tap / 7) * (STEM_PW + 1) + tap % 7) : static_cast<int16_t>(-1);
-  }
-  const int wo0 = blockIdx.x * STEM_TW, ho = blockIdx.y, n = blockIdx.z;
-  const int y0 = ho * 2 - 3, x0 = wo0 * 2 - 3;
-  for (int e = threadIdx.x; e < 3 * 7 * STEM_PW; e += blockDim.x) {
-    const int px = e % STEM_PW, py = (e / STEM_PW) % 7, c = e / (STEM_PW * 7);
-    const int y = y0 + py, x = x0 + px;
-    patch[c][py][px] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + ((static_cast<size_t>(n) * 3 + c) * H + y) * W + x) : 0.f;
-  }
-  __syncthreads();
-  for (int item = threadIdx.x; item < STEM_TW * Kp8; item += blockDim.x) {
-    const int kg = item % Kp8, pw = item / Kp8;
-    const int wo = wo0 + pw;
-    if (wo >= Wo) continue;
-    __align__(16) __half hi[8], lo[8];
+// Space-to-depth of the image (thread = one 2 x 2 input block of one image): the 7x7 / stride-2 stem becomes a 4x4 /
+// stride-1 convolution on 16 channels (12 used).  The four horizontal taps of an output pixel are 4 consecutive pixels =
+// 64 contiguous halves of a plane, so the implicit-GEMM kernel reads one ordinary [rows][64] TMA box per vertical tap
+// through an overlapping-window tensor map (pixel stride 32 B, box row 128 B); the 2 zero pad columns on either side
+// replace the horizontal out-of-bounds fill, which a windowed map cannot express.
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ img, uint4* __restrict__ dst, int N, int H,
+                                                       int W, int H2, int W2, float act_scale) {
+  const int W2p = W2 + 4;     // two zero pad columns on either side, written here too (no dependence on a memset)
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<size_t>(N) * H2 * W2p) return;
+  const int xp = static_cast<int>(i % W2p), y2 = static_cast<int>((i / W2p) % H2), n = static_cast<int>(i / (static_cast<size_t>(W2p) * H2));
+  const int x2 = xp - 2;
+  __align__(16) __half hi[16], lo[16];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int off = koff[kg * 8 + e];
-      const float v = off >= 0 ? (&patch[0][0][0])[off + pw * 2] : 0.f;
-      const float sv = v * act_scale;
-      hi[e] = __float2half_rn(sv);
-      lo[e] = __float2half_rn(sv - __half2float(hi[e]));
+  for (int q = 0; q < 16; ++q) {
+    float v = 0.f;
+    if (q < 12 && x2 >= 0 && x2 < W2) {
+      const int c = q % 3, dx = (q / 3) & 1, dy = q / 6;
+      const int y = 2 * y2 + dy, x = 2 * x2 + dx;
+      if (y < H && x < W) v = __ldg(img + ((static_cast<size_t>(n) * 3 + c) * H + y) * W + x);
     }
-    const size_t r = (static_cast<size_t>(n) * Ho + ho) * Wo + wo;
-    const size_t dp = r * (2 * static_cast<size_t>(Kp8)) + kg;
-    dst[dp] = *reinterpret_cast<const uint4*>(hi);
-    dst[dp + Kp8] = *reinterpret_cast<const uint4*>(lo);
+    const float sv = v * act_scale;
+    hi[q] = __float2half_rn(sv);
+    lo[q] = __float2half_rn(sv - __half2float(hi[q]));
   }
+  // planes [hi | lo][N][H2][W2 + 4][16 halves]: 32 bytes per pixel and plane
+  const size_t plane = static_cast<size_t>(N) * H2 * W2p;
+  uint4* dh = dst + i * 2;
+  uint4* dl = dst + (plane + i) * 2;
+  dh[0] = reinterpret_cast<const uint4*>(hi)[0];
+  dh[1] = reinterpret_cast<const uint4*>(hi)[1];
+  dl[0] = reinterpret_cast<const uint4*>(lo)[0];
+  dl[1] = reinterpret_cast<const uint4*>(lo)[1];
 }
 
 // thread = 8 channels of one output pixel; the (hi, lo) pair with the largest value hi + lo wins (the sum of an fp16
@@ -149,11 +142,12 @@ cudaError_t launch_im2col_hl(const __half* src, __half* dst, int N, int H, int W
   return cudaGetLastError();
 }
 
-cudaError_t launch_im2col_stem(const float* img, __half* dst, int N, int H, int W, int Ho, int Wo, int Kp, float act_scale,
-                               cudaStream_t stream) {
-  if (N <= 0 || Ho <= 0 || Wo <= 0) return cudaSuccess;
-  const dim3 grid((Wo + STEM_TW - 1) / STEM_TW, Ho, N);
-  im2col_stem_kernel<<<grid, 256, 0, stream>>>(img, reinterpret_cast<uint4*>(dst), N, H, W, Ho, Wo, Kp / 8, act_scale);
+cudaError_t launch_stem_s2d(const float* img, __half* dst, int N, int H, int W, float act_scale, cudaStream_t stream) {
+  const int H2 = (H + 1) / 2, W2 = (W + 1) / 2;
+  const size_t total = static_cast<size_t>(N) * H2 * (W2 + 4);
+  if (total == 0) return cudaSuccess;
+  stem_s2d_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(img, reinterpret_cast<uint4*>(dst), N, H, W,
+                                                                                  H2, W2, act_scale);
   return cudaGetLastError();
 }
 

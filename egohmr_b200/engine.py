@@ -391,6 +391,9 @@ class Engine:
     def set_resnet_mode(self, implicit_gemm):
         check(self.lib.ehb_debug_set_resnet_mode(self._h, 1 if implicit_gemm else 0))
 
+    def set_pdl(self, on):
+        check(self.lib.ehb_debug_set_pdl(self._h, 1 if on else 0))
+
     def set_conv_kc(self, kc):
         """k-blocks (x64 operand columns) per tensor-memory accumulation chunk of the ResNet convolution GEMMs (0 = whole K)."""
         check(self.lib.ehb_debug_set_conv_kc(self._h, int(kc)))

@@ -278,6 +278,8 @@ int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);
 /* ResNet 3x3 convolutions: 1 = implicit GEMM through 4-D TMA boxes (product path), 0 = explicit im2col matrix + the
  * same GEMM (bring-up comparison; both must give identical bits). */
 int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm);
+/* Hidden-layer launches with (1, default) or without (0) programmatic dependent launch (bring-up comparison). */
+int ehb_debug_set_pdl(ehb_ctx* ctx, int on);
 /* ResNet convolution GEMMs: k-blocks (of 64 operand columns) chained into one tensor-memory accumulation before the
  * epilogue takes the partial sum over in fp32 registers (0 = the whole contraction in one accumulator). */
 int ehb_debug_set_conv_kc(ehb_ctx* ctx, int kc);
