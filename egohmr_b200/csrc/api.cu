@@ -264,6 +264,7 @@ struct ehb_ctx {
   // k-blocks (of 64) chained into one TMEM accumulation; longer contractions are summed chunk by chunk in fp32 registers
   // by the epilogue warps (0 = never split).  See DESIGN.md "K9 numerics".
   int rn_kc = 2;
+  int rn_kc_1x1 = 2;
   DevBuf rn_col, rn_x[2], rn_y1, rn_y2, rn_s2d;
 
   DevBuf overflow, splitk;
@@ -1463,7 +1464,9 @@ static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, lo
   const int n_mtiles = static_cast<int>((rows + 255) / 256) * 2;
   const size_t rows_pad = static_cast<size_t>(n_mtiles) * 128;
   const int kb_total = (c.Kp + (c2 ? c2->Kp : 0)) / 64;
-  const bool chunked = ctx->rn_kc > 0 && kb_total > ctx->rn_kc;
+  // 1x1 convolutions with up to `rn_kc_1x1` k-blocks stay in one accumulation (and may use the 256-wide tile): they are
+  // epilogue-bound, and their chains are short (<= 16 main MMAs)
+  const bool chunked = ctx->rn_kc > 0 && kb_total > std::max(ctx->rn_kc, c.kh == 1 ? ctx->rn_kc_1x1 : 0);
   const int bn = ehb::conv_gemm_tile_n(c.cout, rows, ctx->num_sms, chunked ? 128 : 256);
   CUtensorMap tA, tB;
   if (make_tmap_f16(&tA, A, rows_pad, 2 * static_cast<uint64_t>(c.Kp), 128)) return 1;
@@ -1489,7 +1492,7 @@ static int rn_gemm(ehb_ctx* ctx, const ehb_ctx::ConvPlan& c, const __half* A, lo
   p.n_mtiles = n_mtiles;
   p.n_ntiles = c.cout / bn;
   p.relu = relu;
-  p.kc = ctx->rn_kc;
+  p.kc = chunked ? ctx->rn_kc : 0;
   EHB_CUDA(ehb::launch_conv_gemm(tA, tB, tA2, tB2, p, ctx->num_sms, stream));
   ctx->launches += 1;
   return 0;
@@ -1556,7 +1559,8 @@ int ehb_debug_set_pdl(ehb_ctx* ctx, int on) {
 int ehb_debug_set_conv_kc(ehb_ctx* ctx, int kc) {
   if (!ctx) return fail("null ctx");
   if (kc < 0) return fail("ehb_debug_set_conv_kc: kc must be >= 0");
-  ctx->rn_kc = kc;
+  ctx->rn_kc = kc % 100;
+  ctx->rn_kc_1x1 = kc >= 100 ? kc / 100 : ctx->rn_kc;   // bring-up: kc = 100 * (1x1 threshold) + chunk length
   return 0;
 }
 

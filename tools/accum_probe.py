@@ -45,7 +45,8 @@ def resnet_probe():
     model, diffusion, sd, smpl_model, mean, std = build_model(1024, 4, T=50, respacing="ddim5")
     model._sync_engine()
     eng = model.engine
-    gemm_probe(eng)
+    if len(sys.argv) == 1:
+        gemm_probe(eng)
     img3 = torch_batch(synth.make_batch(4, 3), "cuda:0")["img"]
     img64 = torch_batch(synth.make_batch(100, 64), "cuda:0")["img"]
     torch.backends.cudnn.allow_tf32 = False
@@ -55,7 +56,7 @@ def resnet_probe():
         ref32 = model.backbone(img3)
     print(json.dumps({"probe": "resnet", "impl": "torch fp32 (cuDNN strict)", "max_err_vs_f64": float((ref32.double() - ref64).abs().max()),
                       "max_feat": float(ref64.abs().max())}), flush=True)
-    for kc in (0, 1, 2, 3, 4, 6, 9, 18):
+    for kc in (int(a) for a in sys.argv[1:]) if len(sys.argv) > 1 else (0, 1, 2, 3, 4, 6, 9, 18):
         eng.set_conv_kc(kc)
         got = eng.resnet_forward(img3.contiguous())
         err = float((got.double() - ref64).abs().max())
