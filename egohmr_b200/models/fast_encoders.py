@@ -1,6 +1,7 @@
-"""Inference forms of the two step-invariant feature providers.  Still PyTorch/cuDNN/cuBLAS — the
-encoders are outside the accelerated hot path — but arranged so that they stop dominating a sampling pass once the
-denoiser loop runs on tensor cores:
+"""Library (PyTorch / cuDNN / cuBLAS) inference forms of the two step-invariant feature providers.  NOT the
+default: a sampling pass runs both encoders natively (K9 / K7 in the CUDA library); these forms are what
+`EgoHMR.native_image_enc = False` / `native_scene_enc = False` select, kept as comparison points (bench.py times the pass with
+the cuDNN TF32 image encoder as `eager_cudnn_tf32_enc`).  Arranged so that they do not dominate a pass either:
 
 * ResNet-50: BatchNorm(eval) folded into the convolution weights/bias (exact in real arithmetic), channels_last so cuDNN
   does not transpose around every convolution;

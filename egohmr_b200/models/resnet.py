@@ -1,7 +1,9 @@
 """ResNet-50 image encoder: a step-invariant *feature provider* for the sampling hot path.
 
-It is evaluated once per image, outside the diffusion loop (the reference re-runs it on every step, egohmr.py:183),
-and stays on PyTorch/cuDNN.  Parameter names match the reference's `backbone.*` state_dict keys
+It is evaluated once per image, outside the diffusion loop (the reference re-runs it on every step, egohmr.py:183).
+This nn.Module only HOLDS the parameters (and is the fp32 / fp64 comparison form in the tests): on a sampling pass the
+encoder runs as tcgen05 convolution GEMMs in the CUDA library (`ehb_resnet_forward`, csrc/conv_umma.cu), unless
+`EgoHMR.native_image_enc = False` selects the cuDNN inference form of models/fast_encoders.py.  Parameter names match the reference's `backbone.*` state_dict keys
 (models/resnet.py:100-150: torchvision-style v1.5 bottlenecks, global average pool, no fc)."""
 import torch.nn as nn
 
