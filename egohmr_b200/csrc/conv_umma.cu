@@ -246,6 +246,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int cg0 = n_tile * BN + col_half * HALF;
         warp_issue_rows_64B(raw_h, p.res_hl + row0w * p.out_ld + cg0, p.out_ld, rows_valid, lane);
         warp_issue_rows_64B(raw_l, p.res_hl + row0w * p.out_ld + p.Cout + cg0, p.out_ld, rows_valid, lane);
+        // The identity tile of this CTA's NEXT unit is pulled into L2 now, one unit (~10 us) ahead: the epilogue is bound by
+        // the latency of its global loads (~32 KB in flight per SM), and an L2 hit costs less than half of an HBM miss.
+        // Lane = row; HALF halves of hi and of lo = HALF / 64 128-byte lines each (non-implicit tiles: rows are tile * 128 + r).
+        const int un = u + unit_step;
+        if (un < n_units && !p.implicit) {
+          const long long rn = (static_cast<long long>(un / p.n_ntiles) * 2 + static_cast<int>(rank)) * BM + q * 32 + lane;
+          if (rn < p.M) {
+            const __half* pn = p.res_hl + rn * p.out_ld + (un % p.n_ntiles) * BN + col_half * HALF;
+#pragma unroll
+            for (int l = 0; l < (HALF + 63) / 64; ++l) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + l * 64));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + p.Cout + l * 64));
+            }
+          }
+        }
       }
       if constexpr (CHUNKED) {
         if (n_chunks > 1) {
