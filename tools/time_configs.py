@@ -19,7 +19,7 @@ from egohmr_b200 import synth  # noqa: E402
 from egohmr_b200.diffusion.model_util import create_gaussian_diffusion  # noqa: E402
 from egohmr_b200.testing import BatchedSyntheticCollision, SyntheticCollision, build_model, torch_batch  # noqa: E402
 
-which = sys.argv[1:] or ["dropin", "guided", "ddpm1000", "strong", "realpts", "metrics"]
+which = sys.argv[1:] or ["dropin", "guided", "guided_reference", "ddpm1000", "strong", "realpts", "metrics", "evalmetrics"]
 dev = "cuda:0"
 model, diffusion, sd, smpl_model, mean, std = build_model(1024, 4, T=50, respacing="ddim5")
 mk = lambda T, r: create_gaussian_diffusion(num_diffusion_timesteps=T, timestep_respacing=r,
@@ -46,15 +46,25 @@ def emit(name, bodies, ms, wall, **kw):
 
 
 if "dropin" in which:
-    batch = torch_batch(synth.make_batch(100, 64), dev)
+    # a new batch object per pass, as a dataloader delivers (from the second batch on val_losses runs the samples ahead)
+    batches = [torch_batch(synth.make_batch(100 + i, 64), dev) for i in range(2)]
+    state = {"i": 0}
 
     def run():
-        model._cond_key = None
+        b = batches[state["i"] % 2]
+        state["i"] += 1
+        outs = []
         for _ in range(10):
-            diffusion.val_losses(model=model, batch=batch, shape=[64, 144], progress=False, clip_denoised=False,
-                                 cur_epoch=0, timestep_respacing="ddim5", compute_loss=False)
-    ms, wall = timed(run, 5)
-    emit("cfg2 drop-in loop: 10 sequential val_losses calls of 64 bodies (test_egohmr.py:251-255), DDIM-5", 640, ms, wall)
+            o = diffusion.val_losses(model=model, batch=b, shape=[64, 144], progress=False, clip_denoised=False,
+                                     cur_epoch=0, timestep_respacing="ddim5", compute_loss=False)
+            outs.append(o["pred_smpl_params"]["body_pose"].unsqueeze(1))
+        return torch.cat(outs, dim=1)
+    ms, wall = timed(run, 6, warm=3)
+    emit("cfg2 drop-in loop: 10 sequential val_losses calls of 64 bodies (test_egohmr.py:251-255), DDIM-5, samples_ahead='auto'", 640, ms, wall)
+    model.samples_ahead = 0
+    ms, wall = timed(run, 6, warm=2)
+    emit("cfg2 drop-in loop with samples_ahead=0 (one chain per call)", 640, ms, wall)
+    model.samples_ahead = "auto"
 
 if "guided" in which:
     d100 = mk(100, "")
@@ -68,6 +78,24 @@ if "guided" in which:
             d100.sample_many(model, batch, 10, "", cond_fn_with_grad=True, cond_grad_weight=2.0)
         ms, wall = timed(run, 2)
         emit("cfg3 DDPM-100 + collision guidance (t <= 10), 32 images x 10 samples", 320, ms, wall, collision=label)
+
+if "guided_reference" in which:
+    # configs[2] on the UNMODIFIED reference (baseline/_ref through baseline/ref_harness.py), same GPU: the driver's loop, 10
+    # sequential guided DDPM-100 chains of 32 images, per-body collision calls as the reference does them (one pass only)
+    from baseline import ref_harness as rh
+    if rh.reference_root()[0]:
+        rmodel, rmean, rstd = rh.build_reference(1024, 4, device=dev)
+        rsamp = rh.build_sampler(100, "", rmean, rstd, device=dev)
+        rbatch = rh.make_driver_batch(101, 32, device=dev)
+        rh.driver_loop(rmodel, rsamp, rh.make_driver_batch(101, 2, device=dev), 1, "", with_coap_grad=True, cond_grad_weight=2.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        rh.driver_loop(rmodel, rsamp, rbatch, 10, "", with_coap_grad=True, cond_grad_weight=2.0)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        emit("cfg3 on the UNMODIFIED reference (CUDA, torch defaults): DDPM-100 + collision guidance, 32 images x 10 sequential samples",
+             320, dt * 1e3, dt * 1e3)
+        del rmodel
 
 if "ddpm1000" in which:
     d1000 = mk(1000, "")
@@ -124,3 +152,17 @@ if "metrics" in which:
     a, b = torch.randn(640, 24, 3, device=dev), torch.randn(640, 24, 3, device=dev)
     ms, wall = timed(lambda: pose_utils.reconstruction_error(a, b, avg_joint=False), 20, warm=2)
     emit("PA-MPJPE: Procrustes alignment of 640 x 24 joints", 640, ms, wall)
+
+if "evalmetrics" in which:
+    from egohmr_b200.utils.eval_metrics import evaluate_batch
+    g = torch.Generator(device="cpu").manual_seed(0)
+    bs, S = 64, 10
+    pj = (torch.randn(bs, S, 24, 3, generator=g) * 0.3).to(dev)
+    pv = (torch.randn(bs, S, 6890, 3, generator=g) * 0.3).to(dev)
+    gj = (torch.randn(bs, 24, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 3.0])).to(dev)
+    gv = (torch.randn(bs, 6890, 3, generator=g) * 0.3 + torch.tensor([0.0, 0.0, 3.0])).to(dev)
+    tr = torch.tensor([[0.0, 0.0, 3.0]]).repeat(bs, 1).to(dev)
+    f, cx, cy = torch.full((bs,), 1500.0, device=dev), torch.full((bs,), 960.0, device=dev), torch.full((bs,), 540.0, device=dev)
+    ms, wall = timed(lambda: evaluate_batch(pj, pv, tr, gj, gv, f, cx, cy, engine=model.engine), 20, warm=2)
+    emit("evaluation metrics of one batch (test_egohmr.py:373-494): 64 images x 10 samples, G-MPJPE / MPJPE / PA-MPJPE / V2V / std / APD",
+         640, ms, wall)
