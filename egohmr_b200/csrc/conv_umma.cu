@@ -103,6 +103,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::cluster_sync();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  // programmatic dependent launch (see gcn_umma.cu): the set-up above overlaps the tail of the previous kernel in the
+  // stream; everything below reads its output or overwrites buffers it may still read
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   if (warp == TMA_WARP) {
     if (lane == 0) {
@@ -401,13 +405,15 @@ cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, conv_gemm_kernel<BN>, tmA, tmB, tmA2, tmB2, p);
 }
 

@@ -87,6 +87,10 @@ linear_umma_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_consta
   ptx::cluster_sync();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = bars->tmem_base;
+  // programmatic dependent launch (see gcn_umma.cu): the set-up above overlaps the tail of the previous kernel in the
+  // stream; everything below reads its output or overwrites buffers it may still read
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
 
   if (warp == TMA_WARP) {
     if (lane == 0) {
@@ -387,13 +391,15 @@ cudaError_t launch_linear_umma(const CUtensorMap& tmA1, const CUtensorMap& tmB1,
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, linear_umma_kernel, tmA1, tmB1, tmA2, tmB2, p);
 }
 
