@@ -998,6 +998,36 @@ def test_rotmat_to_angle_axis_vs_reference_golden(full, golden_dir):
     assert np.abs(aa - g["aa64"]).max() < 2e-6 and np.abs(aa - g["aa32"]).max() < 2e-6
 
 
+def test_gemm_primitive_numerics_and_accumulation_chunks(full):
+    """The convolution GEMM primitive alone (`ehb_debug_gemm_hl`) against exact float64 sums.  (a) fp32-valued, signed
+    operands through the hi/lo split: fp32-class.  (b) What the chunked accumulation is for (DESIGN.md, K9 numerics): with
+    all-positive operands that are exact in fp16 the tensor core's fp32 accumulator loses ~0.5 ulp per chained MMA, always
+    towards zero — -5.8e-6 over K = 1024 in one accumulator, 40x less when every k-block is summed in fp32 registers."""
+    eng = full[0].engine
+    rng = np.random.default_rng(0)
+    M, N, K = 256, 128, 1024
+    a = rng.normal(0, 1, (M, K)).astype(np.float32)
+    w = rng.normal(0, 1, (N, K)).astype(np.float32)
+    exact = a.astype(np.float64) @ w.astype(np.float64).T
+    scale = np.abs(a).astype(np.float64) @ np.abs(w).astype(np.float64).T
+    errs = {}
+    for kc in (0, 2, 1):
+        got = eng.debug_gemm_hl(a, w, 64.0, 1024.0, kc).astype(np.float64)
+        errs[kc] = np.abs((got - exact) / scale).max()      # relative to the sum of |terms|
+    f32 = np.abs(((a @ w.T).astype(np.float64) - exact) / scale).max()
+    print(f"hi/lo GEMM, signed fp32 operands, K = 1024: max error / sum|terms| = {errs[0]:.2e} in one accumulator, {errs[2]:.2e} "
+          f"with 2-k-block chunks, {errs[1]:.2e} with 1-k-block chunks (numpy fp32 matmul: {f32:.2e})")
+    assert errs[0] < 2e-6 and errs[2] < 4e-7 and errs[1] < 1e-7
+    ap = rng.uniform(0.5, 1.0, (M, K)).astype(np.float16).astype(np.float32)
+    wp = rng.uniform(0.5, 1.0, (N, K)).astype(np.float16).astype(np.float32)
+    ex = ap.astype(np.float64) @ wp.astype(np.float64).T
+    bias = {kc: float(((eng.debug_gemm_hl(ap, wp, 1.0, 1.0, kc).astype(np.float64) - ex) / ex).mean()) for kc in (0, 4, 1)}
+    print(f"tcgen05 fp32 accumulation, positive operands, K = 1024: mean relative error {bias[0]:.2e} in one accumulator, "
+          f"{bias[4]:.2e} with 4-k-block chunks, {bias[1]:.2e} with 1-k-block chunks")
+    assert bias[0] < -3e-6 and -3e-7 < bias[1] <= 0 and bias[0] < bias[4] < bias[1]
+    assert not eng.check_overflow()
+
+
 def test_pointnet_tcgen05_vs_torch_and_oracle(full):
     """K7: ResPointNet (models/respointnet.py:33-59) on the tcgen05 linear kernel vs the float64 oracle and vs the
     PyTorch fp32 module, including a ragged cloud size (pooling across tile boundaries) and a single cloud."""

@@ -126,3 +126,22 @@ def test_stage1_handoff_and_scene_cloud_readers(tmp_path):
                         np.zeros((2, 2)), [300, 400], t[:2], [got, got], device="cpu")
     assert b["fx"].tolist() == [1.0, 2.0] and b["scene_pcd_verts_full"].shape == (2, 10000, 3)
     assert b["smpl_params"]["transl"] is b["stage1_transl_full"] and b["img"].dtype == torch.float32
+
+
+def test_rescale_timesteps_follows_the_wrapped_model_order():
+    """respace.py:111-129: SpacedDiffusion never scales the sampler index itself; the wrapped model maps the respaced index to
+    the original timestep FIRST and then scales by 1000 / original_num_steps (the factory passes rescale_timesteps=False, so
+    this only matters to callers that build SpacedDiffusion themselves)."""
+    from egohmr_b200.diffusion.gaussian_diffusion import get_named_beta_schedule
+    from egohmr_b200.diffusion.respace import SpacedDiffusion, space_timesteps
+    betas = get_named_beta_schedule("cosine", 50)
+    for rescale in (False, True):
+        d = SpacedDiffusion(use_timesteps=space_timesteps(50, "ddim5"), betas=betas, rescale_timesteps=rescale)
+        t = torch.tensor([0, 1, 4, 3])
+        assert torch.equal(d._scale_timesteps(t), t)
+        got = d._map_timesteps(t)
+        want = torch.tensor(d.timestep_map)[t]
+        if rescale:
+            assert got.dtype == torch.float32 and torch.allclose(got, want.float() * (1000.0 / 50))
+        else:
+            assert torch.equal(got, want)
