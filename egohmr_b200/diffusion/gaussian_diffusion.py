@@ -330,9 +330,9 @@ class GaussianDiffusion:
         if not want:
             return None
         st = model.__dict__.setdefault("_ahead", {"key": None, "pending": [], "calls": 0, "learned": 1})
-        key = (model._cond_cache_key(batch, batch["smpl_params"]["transl"], 0, None), tuple(shape), bool(guided),
-               float(cond_grad_weight), respacing, id(self))
-        if key == st["key"]:
+        key = model.batch_token(batch, batch["smpl_params"]["transl"],
+                                (tuple(shape), bool(guided), float(cond_grad_weight), respacing, id(self)))
+        if model.token_matches(st["key"], key):
             st["calls"] += 1
             if st["pending"]:
                 out = st["pending"].pop(0)

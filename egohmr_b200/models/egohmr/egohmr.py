@@ -186,6 +186,7 @@ class EgoHMR(nn.Module):
         self._weights_dirty = True
         self._cond_key = None
         self._cond = None
+        self._cond_features = None
         self._temb_key = None
         self._bodies_key = None
         self._bodies_idx = None
@@ -291,7 +292,7 @@ class EgoHMR(nn.Module):
     # ------------------------------------------------------------------ step-invariant conditioning
     @staticmethod
     def _tkey(t):
-        return (t.data_ptr(), tuple(t.shape), t._version)
+        return (id(t), t.data_ptr(), tuple(t.shape), t._version)
 
     def _cam_feats(self, batch):  # egohmr.py:195-205
         feats = []
@@ -309,14 +310,17 @@ class EgoHMR(nn.Module):
     def invalidate(self):
         """Forget the cached step-invariant conditioning: the next `prepare` / sampling call re-runs the encoders.
         `sample_many` calls this itself (one call = one batch).  The per-sample `val_losses` calls of the reference
-        driver's loop (test_egohmr.py:251-255) deliberately share the cache; it is keyed on (data_ptr, shape, _version)
-        of EVERY batch tensor the conditioning reads, so a new batch or any torch in-place write re-runs the encoders —
-        but a writer that bypasses torch's version counter (`.data` writes, DLPack / raw-pointer writers, c10d
-        collectives into a preallocated buffer) must call `invalidate()` (or pass `batch['batch_id']`, any hashable that
-        changes per batch and joins the key)."""
+        driver's loop (test_egohmr.py:251-255) deliberately share the cache.  It is keyed on the IDENTITY of every batch
+        tensor the conditioning reads (held through weak references: a new tensor that the caching allocator happens to
+        place at a freed batch's address is a different object and misses) plus its data_ptr / shape / `_version`, so a new
+        batch or any torch in-place write re-runs the encoders — but a writer that bypasses torch's version counter
+        (`.data` writes, DLPack / raw-pointer writers, c10d collectives into a preallocated buffer) must call
+        `invalidate()` (or pass `batch['batch_id']`, any hashable that changes per batch and joins the key)."""
         self._cond_key = None
 
-    def _cond_cache_key(self, batch, transl, num_samples, features):
+    def batch_token(self, batch, transl, extra=()):
+        """-> (key, weakrefs) identifying the content the step-invariant conditioning is computed from."""
+        import weakref
         keys = ["img", "scene_pcd_verts_full", "orig_keypoints_2d"]
         if self.with_focal_length or self.with_bbox_info or self.with_cam_center:
             keys.append("fx")
@@ -324,8 +328,15 @@ class EgoHMR(nn.Module):
             keys += ["box_center", "box_size"]
         if self.with_cam_center:
             keys += ["cam_cx", "cam_cy"]
-        return tuple(self._tkey(batch[k]) for k in keys) + (self._tkey(transl), num_samples, id(features),
-                                                            batch.get("batch_id"))
+        tensors = [batch[k] for k in keys] + [transl]
+        key = tuple(self._tkey(t) for t in tensors) + tuple(extra) + (batch.get("batch_id"),)
+        return key, [weakref.ref(t) for t in tensors]
+
+    @staticmethod
+    def token_matches(old, new):
+        """The cached token still describes the batch at hand: equal keys AND every tensor it was taken from is still alive
+        (ids and addresses are recycled once a tensor is freed)."""
+        return old is not None and old[0] == new[0] and all(r() is not None and r() is n() for r, n in zip(old[1], new[1]))
 
     @torch.no_grad()
     def prepare(self, batch, num_samples=1, features=None, force=False):
@@ -334,9 +345,10 @@ class EgoHMR(nn.Module):
         `force=True` ignores the cache (see `invalidate`)."""
         self._sync_engine()
         transl = batch["smpl_params"]["transl"]
-        key = self._cond_cache_key(batch, transl, num_samples, features)
-        if key == self._cond_key and not force:
+        key = self.batch_token(batch, transl, (num_samples,))
+        if not force and self.token_matches(self._cond_key, key) and self._cond_features is features:
             return self._cond
+        self._cond_features = features
         was_training = self.training
         self.eval()
         bs = batch["img"].shape[0]

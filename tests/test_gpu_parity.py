@@ -547,6 +547,34 @@ def test_val_losses_samples_ahead_equals_the_sequential_driver_loop(request, whi
     assert launches_ahead < (model.engine.launch_count() - l0 - launches_ahead)   # fewer, larger launches
 
 
+def test_conditioning_cache_survives_address_reuse(full):
+    """A new batch that the caching allocator places at a freed batch's addresses (same shapes, `_version` 0) must not be
+    mistaken for the old one: the cache tokens hold weak references to the tensors they were taken from.  The betas depend
+    on the batch only (not on the noise), so they tell which conditioning a call used."""
+    import gc
+    model, diffusion, *_ = full
+    model.samples_ahead = 2
+    kw = dict(shape=[3, 144], progress=False, clip_denoised=False, cur_epoch=0, timestep_respacing="ddim5", compute_loss=False)
+    a = _tb(synth.make_batch(60, 3))
+    betas_a = diffusion.val_losses(model=model, batch=a, **kw)["pred_smpl_params"]["betas"].clone()   # sample 1 of `a` is pending
+    ptrs = (a["img"].data_ptr(), a["scene_pcd_verts_full"].data_ptr())
+    del a
+    gc.collect()
+    b = _tb(synth.make_batch(61, 3))
+    reused = (b["img"].data_ptr(), b["scene_pcd_verts_full"].data_ptr()) == ptrs
+    got = diffusion.val_losses(model=model, batch=b, **kw)["pred_smpl_params"]["betas"].clone()
+    want = model.prepare(b, 1, force=True)["betas_img"]
+    print(f"address reuse by the allocator: {reused}")
+    assert torch.equal(got, want) and not torch.equal(got, betas_a)
+    # in-place refill through torch bumps _version: also a miss
+    c = _tb(synth.make_batch(62, 3))
+    for k in ("img", "scene_pcd_verts_full", "orig_keypoints_2d", "fx", "box_center", "box_size", "cam_cx", "cam_cy"):
+        b[k].copy_(c[k])
+    b["smpl_params"]["transl"].copy_(c["smpl_params"]["transl"])
+    got = diffusion.val_losses(model=model, batch=b, **kw)["pred_smpl_params"]["betas"].clone()
+    assert torch.equal(got, model.prepare(c, 1, force=True)["betas_img"])
+
+
 def test_image_sharding_reproduces_the_unsharded_chains(full):
     """images split contiguously over ranks, noise pre-drawn globally and sliced per rank — every shard's
     chains equal the unsharded run bit for bit (bodies never interact), for even and ragged splits."""
