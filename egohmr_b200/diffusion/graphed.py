@@ -99,7 +99,7 @@ class GraphedSampler:
         return self.model.engine.check_overflow()
 
     def _version(self):
-        return sum(p._version for p in self.model.parameters())
+        return self.model._weights_version()
 
     def __call__(self, batch=None, noise=None, staged=False):
         """Replay the pass on `batch` (same shapes as at capture; None = reuse the static inputs as they are;

@@ -184,6 +184,7 @@ class EgoHMR(nn.Module):
                              "pose_6d_ortho": weight_loss_pose_6d_ortho}
         self.to(self.device)
         self._weights_dirty = True
+        self._synced_version = None
         self._cond_key = None
         self._cond = None
         self._cond_features = None
@@ -220,8 +221,15 @@ class EgoHMR(nn.Module):
                 raise RuntimeError(f"missing keys in state_dict: {missing[:5]}...")
         return res
 
+    def _weights_version(self):
+        """Sum of the autograd version counters of every parameter and buffer: any torch in-place update (load_state_dict on
+        a sub-module, an optimizer step, .copy_) changes it."""
+        return sum(t._version for t in self.parameters()) + sum(t._version for t in self.buffers())
+
     def _sync_engine(self):
-        if not self._weights_dirty:
+        """(Re)pack the module's weights for the kernels when they changed since the last sampling call."""
+        version = self._weights_version()
+        if not self._weights_dirty and version == self._synced_version:
             return
         sd = {k: v for k, v in self.state_dict().items()
               if k.startswith("diffusion_model.") or k.startswith("input_process.")}
@@ -246,6 +254,7 @@ class EgoHMR(nn.Module):
         self.engine.load_resnet({k: v for k, v in self.state_dict().items() if k.startswith("backbone.")},
                                 bn_eps=self.backbone.bn1.eps)
         self._weights_dirty = False
+        self._synced_version = version
         self._cond_key = None
         self._temb_key = None
         self._bodies_key = None

@@ -547,6 +547,27 @@ def test_val_losses_samples_ahead_equals_the_sequential_driver_loop(request, whi
     assert launches_ahead < (model.engine.launch_count() - l0 - launches_ahead)   # fewer, larger launches
 
 
+def test_in_place_weight_updates_reach_the_kernels(small):
+    """Weights are repacked for the kernels on first use; an in-place update that does not go through
+    EgoHMR.load_state_dict (a sub-module's load_state_dict, an optimizer step) must be picked up by the next call."""
+    model, diffusion, *_ = small
+    batch = _tb(synth.make_batch(70, 2))
+    noise = torch.from_numpy(synth.make_noise(70, 1, 2, 50)[0]).cuda()
+    a = diffusion.sample_many(model, batch, 1, "", noise=noise)["pred_x_start"].clone()
+    w = model.diffusion_model.gconv_output.W
+    old = w.detach().clone()
+    try:
+        with torch.no_grad():
+            w.mul_(1.5)
+        b = diffusion.sample_many(model, batch, 1, "", noise=noise)["pred_x_start"].clone()
+        assert (a - b).abs().max().item() > 1e-3
+    finally:
+        with torch.no_grad():
+            w.copy_(old)
+    c = diffusion.sample_many(model, batch, 1, "", noise=noise)["pred_x_start"]
+    assert torch.equal(a, c)
+
+
 def test_conditioning_cache_survives_address_reuse(full):
     """A new batch that the caching allocator places at a freed batch's addresses (same shapes, `_version` 0) must not be
     mistaken for the old one: the cache tokens hold weak references to the tensors they were taken from.  The betas depend
