@@ -102,6 +102,7 @@ __device__ __forceinline__ size_t slot_row0(int slot) {
 // HBM-bound: 2 x 98.3 KB written per slot.  Compute is thread = channel (coalesced parameter reads); the 24 x 128
 // output tile is staged in shared memory and written out as 128-bit fp32 / 64-bit fp16 row segments.
 __global__ void __launch_bounds__(128) gcn_input_kernel(const __grid_constant__ InputLayerParams p) {
+  ptx::pdl_launch_dependents();   // the first hidden layer (launched with programmatic serialization) sets up meanwhile
   __shared__ float xs[NJ][6];
   __shared__ float visf[NJ];
   __shared__ __align__(16) float tile[NJ][128];

@@ -1,6 +1,7 @@
 // Data movers around the ResNet-50 convolution GEMMs (conv_umma.cu): im2col of hi/lo activations, the stem's
 // space-to-depth transform of the fp32 image, max-pool and global average pool on hi/lo activations.  All HBM-bound, 128-bit accesses.
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 namespace ehb {
 namespace {
@@ -9,6 +10,7 @@ namespace {
 __global__ void __launch_bounds__(256) im2col_hl_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int H,
                                                         int W, int C8, int KH, int KW, int stride, int pad, int Ho,
                                                         int Wo) {
+  ptx::pdl_launch_dependents();   // the convolution GEMM that follows may run its set-up while this kernel drains
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int taps = KH * KW;
   const size_t total = static_cast<size_t>(N) * Ho * Wo * taps * C8;
@@ -40,6 +42,7 @@ __global__ void __launch_bounds__(256) im2col_hl_kernel(const uint4* __restrict_
 // replace the horizontal out-of-bounds fill, which a windowed map cannot express.
 __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__ img, uint4* __restrict__ dst, int N, int H,
                                                        int W, int H2, int W2, float act_scale) {
+  ptx::pdl_launch_dependents();   // the convolution GEMM that follows may run its set-up while this kernel drains
   const int W2p = W2 + 4;     // two zero pad columns on either side, written here too (no dependence on a memset)
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(N) * H2 * W2p) return;
@@ -72,6 +75,7 @@ __global__ void __launch_bounds__(256) stem_s2d_kernel(const float* __restrict__
 // hi/lo split is exact in fp32, so this is exactly max over the represented values)
 __global__ void __launch_bounds__(256) maxpool_hl_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int N, int H,
                                                          int W, int C8, int Ho, int Wo) {
+  ptx::pdl_launch_dependents();   // the convolution GEMM that follows may run its set-up while this kernel drains
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t total = static_cast<size_t>(N) * Ho * Wo * C8;
   if (i >= total) return;
@@ -117,6 +121,7 @@ __global__ void __launch_bounds__(256) maxpool_hl_kernel(const uint4* __restrict
 // x.mean(dim=(2, 3)) (models/resnet.py:148-149 avgpool + flatten): thread = one (image, channel), coalesced over channels
 __global__ void __launch_bounds__(256) avgpool_hl_kernel(const __half* __restrict__ src, float* __restrict__ dst, int N, int HW,
                                                          int C, float inv_scale_hw) {
+  ptx::pdl_launch_dependents();   // the convolution GEMM that follows may run its set-up while this kernel drains
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<size_t>(N) * C) return;
   const int c = static_cast<int>(i % C);
