@@ -87,6 +87,8 @@ SIGNATURES = {
     "ehb_pointnet_load": (C.c_int, [_vp, C.POINTER(PointnetWeights)]),
     "ehb_pointnet_forward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
     "ehb_maxpool3x3s2_nhwc": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "ehb_cond_inputs": (C.c_int, [_vp] + [_vp] * 9 + [C.c_int] * 7 + [c_int32_p, C.c_float, _vp, _vp, _vp, _vp]),
+    "ehb_project_joints": (C.c_int, [_vp] + [_vp] * 6 + [C.c_int, C.c_int, C.c_float, C.c_float] + [_vp] * 5),
     "ehb_scene_crop": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "ehb_procrustes_align": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "ehb_eval_metrics": (C.c_int, [_vp] + [_vp] * 8 + [C.c_int] * 4 + [_vp] * 5),

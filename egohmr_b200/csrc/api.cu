@@ -1312,6 +1312,40 @@ int ehb_maxpool3x3s2_nhwc(ehb_ctx* ctx, const float* in, int n, int h, int w, in
   return 0;
 }
 
+int ehb_cond_inputs(ehb_ctx* ctx, const float* kp2d, const float* scene_feat, const float* transl_feat, const float* img_feat,
+                    const float* fx, const float* box_center, const float* box_size, const float* cam_cx, const float* cam_cy,
+                    int n_img, int scene_dim, int transl_dim, int img_dim, int with_focal_length, int with_bbox_info,
+                    int with_cam_center, const int32_t* openpose_to_smpl, float fx_norm_coeff, uint8_t* vis, float* rest,
+                    float* ctx_full, void* stream_) {
+  if (!ctx || !kp2d || !scene_feat || !transl_feat || !img_feat || !openpose_to_smpl || !vis || !rest || !ctx_full)
+    return fail("ehb_cond_inputs: null argument");
+  if (n_img <= 0 || scene_dim <= 0 || transl_dim <= 0 || img_dim <= 0) return fail("ehb_cond_inputs: sizes must be positive");
+  if ((with_focal_length || with_bbox_info || with_cam_center) && !fx) return fail("ehb_cond_inputs: fx is required by the camera flags");
+  if (with_bbox_info && (!box_center || !box_size)) return fail("ehb_cond_inputs: box_center / box_size required (with_bbox_info)");
+  if (with_cam_center && (!cam_cx || !cam_cy)) return fail("ehb_cond_inputs: cam_cx / cam_cy required (with_cam_center)");
+  for (int j = 0; j < ehb::NJ; ++j)
+    if (openpose_to_smpl[j] < 0 || openpose_to_smpl[j] >= 25) return fail("ehb_cond_inputs: openpose_to_smpl entries must be in [0, 25)");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_cond_inputs(kp2d, scene_feat, transl_feat, img_feat, fx, box_center, box_size, cam_cx, cam_cy, n_img,
+                                   scene_dim, transl_dim, img_dim, with_focal_length, with_bbox_info, with_cam_center,
+                                   openpose_to_smpl, fx_norm_coeff, vis, rest, ctx_full, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += 1;
+  return 0;
+}
+
+int ehb_project_joints(ehb_ctx* ctx, const float* joints, const float* transl, const float* fx, const float* cam_cx,
+                       const float* cam_cy, const int32_t* img_of_body, int n_bodies, int n_joints, float fx_norm_coeff,
+                       float default_focal, float* kp3d_full, float* kp2d, float* focal_out, float* center_out, void* stream_) {
+  if (!ctx || !joints || !transl || !kp3d_full || !kp2d || !focal_out || !center_out) return fail("ehb_project_joints: null argument");
+  if (fx && (!cam_cx || !cam_cy)) return fail("ehb_project_joints: cam_cx / cam_cy required together with fx");
+  if (n_bodies <= 0 || n_joints <= 0) return fail("ehb_project_joints: sizes must be positive");
+  EHB_CUDA(cudaSetDevice(ctx->device));
+  EHB_CUDA(ehb::launch_project_joints(joints, transl, fx, cam_cx, cam_cy, img_of_body, n_bodies, n_joints, fx_norm_coeff,
+                                      default_focal, kp3d_full, kp2d, focal_out, center_out, static_cast<cudaStream_t>(stream_)));
+  ctx->launches += 1;
+  return 0;
+}
+
 int ehb_scene_crop(ehb_ctx* ctx, const float* verts, int n_bodies, int n_verts, const float* scene, int n_pts,
                    const int32_t* img_of_body, uint8_t* mask, int32_t* count, float* bbox, void* stream_) {
   if (!ctx || !verts || !scene || !mask || !count) return fail("ehb_scene_crop: null argument");

@@ -252,6 +252,18 @@ cudaError_t launch_avgpool_hl(const __half* src, float* dst, int N, int HW, int 
 // ---- image ops (image_ops.cu): MaxPool2d(3, 2, 1) on NHWC fp32, C % 4 == 0; out is [N][(H+1)/2][(W+1)/2][C]
 cudaError_t launch_maxpool3x3s2_nhwc(const float* in, float* out, int N, int H, int W, int C, cudaStream_t stream);
 
+// step-invariant glue of EgoHMR.forward (visibility mask, [scene | transl | camera] condition vector, beta-head input) and
+// the final joints' translation + perspective projection; see image_ops.cu
+cudaError_t launch_cond_inputs(const float* kp2d, const float* scene_feat, const float* transl_feat, const float* img_feat,
+                               const float* fx, const float* box_center, const float* box_size, const float* cam_cx,
+                               const float* cam_cy, int n, int sf, int tf, int img_dim, int with_focal, int with_bbox,
+                               int with_center, const int32_t* o2s, float coeff, uint8_t* vis, float* rest, float* ctxfull,
+                               cudaStream_t stream);
+cudaError_t launch_project_joints(const float* joints, const float* transl, const float* fx, const float* cam_cx,
+                                  const float* cam_cy, const int32_t* img_of_body, int n_bodies, int J, float coeff,
+                                  float default_focal, float* kp3d_full, float* kp2d, float* focal_out, float* center_out,
+                                  cudaStream_t stream);
+
 // per-body bounding-box crop of the scene cloud (egohmr.py:550-554): mask [B][n_pts], count [B], bbox [B][6] (optional)
 cudaError_t launch_scene_crop(const float* verts, int n_bodies, int V, const float* scene, int n_pts,
                               const int32_t* img_of_body, uint8_t* mask, int32_t* count, float* bbox,

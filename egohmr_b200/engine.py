@@ -319,6 +319,41 @@ class Engine:
             check(self.lib.ehb_rotmat_to_angle_axis(self._h, _dev_ptr(R), n, _dev_ptr(aa), _stream()))
         return aa
 
+    def cond_inputs(self, kp2d, scene_feat, transl_feat, img_feat, fx, box_center, box_size, cam_cx, cam_cy, flags,
+                    openpose_to_smpl, fx_norm_coeff):
+        """EgoHMR.forward's step-invariant glue in one launch (include/egohmr_b200.h::ehb_cond_inputs).
+        flags = (with_focal_length, with_bbox_info, with_cam_center) -> vis uint8 [n,24], rest [n,R], ctx_full [n,img+R]."""
+        n, sf, tf, img_dim = kp2d.shape[0], scene_feat.shape[1], transl_feat.shape[1], img_feat.shape[1]
+        rdim = sf + tf + (1 if flags[0] else 0) + (3 if flags[1] else 0) + (2 if flags[2] else 0)
+        dev = kp2d.device
+        vis = torch.empty(n, 24, device=dev, dtype=torch.uint8)
+        rest = torch.empty(n, rdim, device=dev, dtype=torch.float32)
+        full = torch.empty(n, img_dim + rdim, device=dev, dtype=torch.float32)
+        o2s = np.ascontiguousarray(openpose_to_smpl, dtype=np.int32)
+        opt = lambda t: _dev_ptr(t, allow_none=True)
+        check(self.lib.ehb_cond_inputs(self._h, _dev_ptr(kp2d), _dev_ptr(scene_feat), _dev_ptr(transl_feat), _dev_ptr(img_feat),
+                                       opt(fx), opt(box_center), opt(box_size), opt(cam_cx), opt(cam_cy), n, sf, tf, img_dim,
+                                       int(bool(flags[0])), int(bool(flags[1])), int(bool(flags[2])),
+                                       o2s.ctypes.data_as(_lib.c_int32_p), float(fx_norm_coeff), _dev_ptr(vis, torch.uint8),
+                                       _dev_ptr(rest), _dev_ptr(full), _stream()))
+        return vis, rest, full
+
+    def project_joints(self, joints, transl, fx, cam_cx, cam_cy, img_of_body, fx_norm_coeff, default_focal):
+        """joints [B,J,3] + per-image translation / camera -> (kp3d_full [B,J,3], kp2d [B,J,2] normalised to the full frame,
+        focal [B,2], centre [B,2]) in one launch (ehb_project_joints)."""
+        B, J = joints.shape[0], joints.shape[1]
+        dev = joints.device
+        full = torch.empty(B, J, 3, device=dev, dtype=torch.float32)
+        kp2d = torch.empty(B, J, 2, device=dev, dtype=torch.float32)
+        focal = torch.empty(B, 2, device=dev, dtype=torch.float32)
+        center = torch.empty(B, 2, device=dev, dtype=torch.float32)
+        opt = lambda t: _dev_ptr(t, allow_none=True)
+        check(self.lib.ehb_project_joints(self._h, _dev_ptr(joints), _dev_ptr(transl), opt(fx), opt(cam_cx), opt(cam_cy),
+                                          _dev_ptr(img_of_body, torch.int32, allow_none=True), B, J, float(fx_norm_coeff),
+                                          float(default_focal), _dev_ptr(full), _dev_ptr(kp2d), _dev_ptr(focal),
+                                          _dev_ptr(center), _stream()))
+        return full, kp2d, focal, center
+
     def scene_crop(self, verts, scene, img_of_body=None):
         """Bounding-box crop of guide_coll / eval_coll (egohmr.py:550-554) for all bodies at once.
         verts [B,V,3], scene [n_clouds,N,3], img_of_body int32 [B] (device) or None -> mask bool [B,N], count int32 [B]."""

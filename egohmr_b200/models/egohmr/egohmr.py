@@ -191,8 +191,6 @@ class EgoHMR(nn.Module):
         self._temb_key = None
         self._bodies_key = None
         self._bodies_idx = None
-        self._op2smpl_idx = None
-        self._default_center = None
         # The fp16 hi/lo operands have a finite range; a checkpoint that exceeds it must fail loudly (FloatingPointError),
         # not return Inf/NaN.  "sync": the flag is read back at the end of every eager sampling call (one host sync per
         # call).  "deferred" (default): every call enqueues a stream-ordered copy of the flag into pinned host memory and
@@ -303,19 +301,6 @@ class EgoHMR(nn.Module):
     def _tkey(t):
         return (id(t), t.data_ptr(), tuple(t.shape), t._version)
 
-    def _cam_feats(self, batch):  # egohmr.py:195-205
-        feats = []
-        if self.with_focal_length:
-            feats = [batch["fx"].unsqueeze(1)] + feats
-        if self.with_bbox_info:
-            orig_fx = batch["fx"] * self.cfg.CAM.FX_NORM_COEFF
-            feats = [torch.stack([batch["box_center"][:, 0] / orig_fx, batch["box_center"][:, 1] / orig_fx,
-                                  batch["box_size"] / orig_fx], dim=-1)] + feats
-        if self.with_cam_center:
-            orig_fx = batch["fx"] * self.cfg.CAM.FX_NORM_COEFF
-            feats = [torch.stack([batch["cam_cx"] / orig_fx, batch["cam_cy"] / orig_fx], dim=-1)] + feats
-        return feats
-
     def invalidate(self):
         """Forget the cached step-invariant conditioning: the next `prepare` / sampling call re-runs the encoders.
         `sample_many` calls this itself (one call = one batch).  The per-sample `val_losses` calls of the reference
@@ -361,11 +346,6 @@ class EgoHMR(nn.Module):
         was_training = self.training
         self.eval()
         bs = batch["img"].shape[0]
-        vis_op = batch["orig_keypoints_2d"][:, :, -1] > 0  # egohmr.py:186-189
-        vis_op[:, 8] = True
-        if self._op2smpl_idx is None or self._op2smpl_idx.device != vis_op.device:
-            self._op2smpl_idx = torch.tensor(self.openpose_to_smpl, device=vis_op.device, dtype=torch.long)
-        vis = vis_op.index_select(1, self._op2smpl_idx)   # device-resident index: no per-call upload, graph-capturable
         pts = batch["scene_pcd_verts_full"] - transl.unsqueeze(1) if self.scene_cano else batch["scene_pcd_verts_full"]
         if features is None:
             img_feats = (self.engine.resnet_forward(batch["img"].float().contiguous()) if self.native_image_enc
@@ -376,11 +356,20 @@ class EgoHMR(nn.Module):
             transl_feat = self.engine.linear(h, *self._heads["transl2"])
         else:
             img_feats, scene_feats, transl_feat = features["img_feats"], features["scene_feats"], features["transl_feat"]
-        rest = torch.cat([scene_feats, transl_feat] + self._cam_feats(batch), dim=1).float().contiguous()
+        # visibility mask (:186-189), [scene | transl | camera] condition vector (:195-223) and the beta head's input (:263):
+        # one kernel instead of ~18 small torch launches
+        c = lambda k: batch[k].float().contiguous() if k in batch else None
+        flags = (self.with_focal_length, self.with_bbox_info, self.with_cam_center)
         img_feats = img_feats.float().contiguous()
-        hb = self.engine.linear(torch.cat([img_feats, rest], dim=1).contiguous(), *self._heads["beta0"], relu=True)
+        vis_u8, rest, ctx_full = self.engine.cond_inputs(
+            c("orig_keypoints_2d"), scene_feats.float().contiguous(), transl_feat.float().contiguous(), img_feats,
+            c("fx") if any(flags) else None, c("box_center") if flags[1] else None, c("box_size") if flags[1] else None,
+            c("cam_cx") if flags[2] else None, c("cam_cy") if flags[2] else None, flags, self.openpose_to_smpl,
+            self.cfg.CAM.FX_NORM_COEFF)
+        vis = vis_u8.bool()
+        hb = self.engine.linear(ctx_full, *self._heads["beta0"], relu=True)
         betas = self.engine.linear(hb, *self._heads["beta2"]) + self.beta_layer.init_betas  # :263-265, :673-679
-        self.engine.set_cond(img_feats, rest, vis.to(torch.uint8).contiguous())
+        self.engine.set_cond(img_feats, rest, vis_u8)
         iob = np.repeat(np.arange(bs, dtype=np.int32), num_samples)
         if self._bodies_key != (bs, num_samples) or self.engine.n_bodies != iob.shape[0]:
             self.engine.set_bodies(iob)      # uploads the slot tables (synchronising): only when the layout changes
@@ -420,18 +409,16 @@ class EgoHMR(nn.Module):
         out = {"pred_x_start": x0, "pred_pose_6d": pose6d,
                "pred_smpl_params": {"global_orient": R[:, 0:1].clone(), "body_pose": R[:, 1:].clone(), "betas": betas.clone()},
                "pred_keypoints_3d": joints, "pred_vertices": verts}
+        # full-frame joints and their projection (:277-301) in one kernel; focal / centre rows are what compute_loss reads
         if self.with_focal_length:
-            focal = (batch["fx"].unsqueeze(-1).repeat(1, 2) * self.cfg.CAM.FX_NORM_COEFF)[idx]
-            center = torch.stack([batch["cam_cx"], batch["cam_cy"]], dim=-1)[idx]
+            cam = (batch["fx"].float().contiguous(), batch["cam_cx"].float().contiguous(), batch["cam_cy"].float().contiguous())
         else:
-            focal = self.cfg.EXTRA.FOCAL_LENGTH * torch.ones(x0.shape[0], 2, device=x0.device)
-            if self._default_center is None or self._default_center.device != x0.device:
-                self._default_center = torch.tensor([[960.0, 540.0]], device=x0.device)
-            center = self._default_center.repeat(x0.shape[0], 1)
+            cam = (None, None, None)
+        full, kp2d, focal, center = self.engine.project_joints(joints, cond["transl"].float().contiguous(), *cam,
+                                                               cond["img_of_body_i32"], self.cfg.CAM.FX_NORM_COEFF,
+                                                               self.cfg.EXTRA.FOCAL_LENGTH)
         self.camera_center_full, self.focal_length = center, focal
-        out["pred_keypoints_3d_full"] = joints + transl.unsqueeze(1)
-        kp2d = perspective_projection(joints, transl, focal, center)
-        kp2d = torch.stack([kp2d[:, :, 0] / 1920 - 0.5, kp2d[:, :, 1] / 1080 - 0.5], dim=-1)
+        out["pred_keypoints_3d_full"] = full
         out["pred_keypoints_2d_full"] = kp2d
         return out
 

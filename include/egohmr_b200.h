@@ -194,6 +194,28 @@ int ehb_pointnet_forward(ehb_ctx* ctx, const float* pts, int n_clouds, int n_pts
  * tensor: in [n][h][w][c] -> out [n][(h+1)/2][(w+1)/2][c]; c % 4 == 0, 16-byte aligned pointers. */
 int ehb_maxpool3x3s2_nhwc(ehb_ctx* ctx, const float* in, int n, int h, int w, int c, float* out, void* stream);
 
+/* The step-invariant glue of EgoHMR.forward for n_img images in one launch (the reference: ~18 small torch kernels):
+ *   vis  [n_img][24] uint8: vis_mask_smpl (egohmr.py:186-189) from orig_keypoints_2d kp2d [n_img][25][3] through the
+ *        OpenPose -> SMPL table (HOST int32 [24], :110-114), OpenPose joint 8 forced visible;
+ *   rest [n_img][scene_dim + transl_dim + cams] = [scene_feats | transl_feat | cam_cx/f, cam_cy/f | box_cx/f, box_cy/f,
+ *        box_size/f | fx] with f = fx * fx_norm_coeff (:195-205, 220-223; camera parts per flag, in this order);
+ *   ctx_full [n_img][img_dim + rest] = [img_feats | rest], the beta head's input (:262-263).
+ * fx is the NORMALISED focal length of the batch dict; pointers a flag does not need may be NULL. */
+int ehb_cond_inputs(ehb_ctx* ctx, const float* kp2d, const float* scene_feat, const float* transl_feat, const float* img_feat,
+                    const float* fx, const float* box_center, const float* box_size, const float* cam_cx, const float* cam_cy,
+                    int n_img, int scene_dim, int transl_dim, int img_dim, int with_focal_length, int with_bbox_info,
+                    int with_cam_center, const int32_t* openpose_to_smpl, float fx_norm_coeff, uint8_t* vis, float* rest,
+                    float* ctx_full, void* stream);
+
+/* egohmr.py:277-301 for the final joints [n_bodies][n_joints][3]: kp3d_full = joints + transl[img], kp2d [n_bodies][n_joints][2]
+ * = perspective_projection(joints, transl, focal, centre) (utils/geometry.py:78-116, identity rotation) mapped to
+ * (u / 1920 - 0.5, v / 1080 - 0.5); focal_out / center_out [n_bodies][2] are the rows compute_loss reads (:361-366).
+ * fx != NULL: focal = fx[img] * fx_norm_coeff, centre = (cam_cx, cam_cy)[img]; fx == NULL: default_focal and (960, 540).
+ * img_of_body device int32 [n_bodies] or NULL (identity). */
+int ehb_project_joints(ehb_ctx* ctx, const float* joints, const float* transl, const float* fx, const float* cam_cx,
+                       const float* cam_cy, const int32_t* img_of_body, int n_bodies, int n_joints, float fx_norm_coeff,
+                       float default_focal, float* kp3d_full, float* kp2d, float* focal_out, float* center_out, void* stream);
+
 /* The scene crop of guide_coll / eval_coll (egohmr.py:550-554, 504-508) for every body in one launch: body b's
  * axis-aligned bounding box over verts [n_bodies][n_verts][3], then mask[b][i] = 1 iff point i of cloud
  * img_of_body[b] (device int32 [n_bodies], NULL = identity) lies inside it (inclusive on both sides, like the
