@@ -504,7 +504,9 @@ class EgoHMR(nn.Module):
                         so = smpl_mod.SMPLOutput(vertices=v[[i]], joints=j[[i]], full_pose=fp[[i]])
                         losses[i] = cm.collision_loss(self.scene_pcd_verts[idx_l[i]][mask[i]].unsqueeze(0), so,
                                                       ret_collision_mask=None)
-            if int((losses == 0).sum()) >= B:
+            # No body collides -> zero gradient (:561-570).  The per-body path knows that on the host already; the batched
+            # path needs no read-back: bodies with an empty crop have a masked, constant-zero loss whose gradient is zero.
+            if not losses.requires_grad or (not hasattr(cm, "collision_loss_batched") and not any(counts)):
                 return torch.zeros(B, 144, device=x.device)
             # The reference averages over the bodies of ONE val_losses call (:561), i.e. over the images of the batch.
             # When the samples of an image are flattened into this batch (sample_many) the gradient of a body must not
