@@ -1077,6 +1077,69 @@ def test_gemm_primitive_numerics_and_accumulation_chunks(full):
     assert not eng.check_overflow()
 
 
+def test_glue_kernels_bit_exact_vs_the_reference_expressions(full):
+    """`ehb_cond_inputs` (egohmr.py:186-205, 220-223) and `ehb_project_joints` (egohmr.py:277-301 +
+    utils/geometry.py:78-116) replay the reference's fp32 torch expressions: identical bits, every camera-flag combination."""
+    eng = full[0].engine
+    g = torch.Generator(device="cpu").manual_seed(3)
+    n = 7
+    r = lambda *s: torch.rand(*s, generator=g).cuda()
+    kp = torch.cat([r(n, 25, 2) * 1000, (r(n, 25, 1) - 0.4)], dim=2).contiguous()
+    kp[0, 8, 2] = -1.0                                           # OpenPose joint 8 is forced visible
+    scene, tr, img = r(n, 512), r(n, 128), r(n, 2048)
+    fx, bc, bs_, cx, cy = r(n) * 0.2 + 0.9, r(n, 2) * 1000, r(n) * 500 + 100, r(n) * 100 + 900, r(n) * 100 + 500
+    table = [8, 13, 10, 8, 13, 10, 8, 14, 11, 8, 14, 11, 1, 5, 2, 0, 5, 2, 6, 3, 7, 4, 7, 4]
+    for flags in ((1, 1, 1), (1, 0, 0), (0, 1, 1), (0, 0, 0), (1, 0, 1)):
+        vis, rest, full_ctx = eng.cond_inputs(kp, scene, tr, img, fx if any(flags) else None, bc if flags[1] else None,
+                                              bs_ if flags[1] else None, cx if flags[2] else None, cy if flags[2] else None,
+                                              flags, table, 1500.0)
+        vis_op = kp[:, :, -1] > 0
+        vis_op[:, 8] = True
+        feats = []
+        if flags[0]:
+            feats = [fx.unsqueeze(1)] + feats
+        if flags[1]:
+            f = fx * 1500.0
+            feats = [torch.stack([bc[:, 0] / f, bc[:, 1] / f, bs_ / f], dim=-1)] + feats
+        if flags[2]:
+            f = fx * 1500.0
+            feats = [torch.stack([cx / f, cy / f], dim=-1)] + feats
+        want_rest = torch.cat([scene, tr] + feats, dim=1)
+        assert torch.equal(vis.bool(), vis_op[:, table]) and torch.equal(rest, want_rest)
+        assert torch.equal(full_ctx, torch.cat([img, want_rest], dim=1))
+    from egohmr_b200.utils.geometry import perspective_projection
+    B, S = n * 3, 3
+    joints = r(B, 45, 3) - 0.5
+    transl = r(n, 3) * 0.2 + torch.tensor([0.0, 0.0, 3.0], device="cuda")
+    iob = torch.arange(n, device="cuda").repeat_interleave(S)
+    full3d, kp2d, focal, center = eng.project_joints(joints, transl.contiguous(), fx, cx, cy, iob.to(torch.int32), 1500.0, 5000.0)
+    f2 = (fx.unsqueeze(-1).repeat(1, 2) * 1500.0)[iob]
+    c2 = torch.stack([cx, cy], dim=-1)[iob]
+    # expected values with torch's CPU kernels, as the goldens were produced (`x / 1920` is a true division there; torch's
+    # CUDA kernel multiplies by the rounded reciprocal, up to 1 ulp away)
+    want = perspective_projection(joints.cpu(), transl[iob].cpu(), f2.cpu(), c2.cpu())
+    want = torch.stack([want[:, :, 0] / 1920 - 0.5, want[:, :, 1] / 1080 - 0.5], dim=-1)
+    assert torch.equal(full3d, joints + transl[iob].unsqueeze(1)) and torch.equal(kp2d.cpu(), want)
+    assert torch.equal(focal, f2) and torch.equal(center, c2)
+    _, _, focal_d, center_d = eng.project_joints(joints, transl.contiguous(), None, None, None, iob.to(torch.int32), 1500.0, 5000.0)
+    assert bool((focal_d == 5000.0).all()) and torch.equal(center_d, torch.tensor([[960.0, 540.0]], device="cuda").repeat(B, 1))
+
+
+def test_pointnet_at_the_dataset_cloud_size(full):
+    """K7 at the real dataset's cloud size (20 000 points, dataloaders/egobody_dataset.py:213-225; 157 tiles per cloud, clouds
+    not aligned to tiles) against the fp32 PyTorch module."""
+    model = full[0]
+    model._sync_engine()
+    rng = np.random.default_rng(5)
+    pts = torch.from_numpy(rng.uniform(-1, 1, (3, 20000, 3)).astype(np.float32)).cuda()
+    with torch.no_grad():
+        ref = model.scene_enc(pts)
+    got = model.engine.pointnet_forward(pts)
+    err = (got - ref).abs().max().item()
+    print(f"pointnet 3 x 20000: tcgen05 vs torch fp32 {err:.3e} (max|ref| {ref.abs().max().item():.3f})")
+    assert err < 2e-6 and not model.engine.check_overflow()
+
+
 def test_pointnet_tcgen05_vs_torch_and_oracle(full):
     """K7: ResPointNet (models/respointnet.py:33-59) on the tcgen05 linear kernel vs the float64 oracle and vs the
     PyTorch fp32 module, including a ragged cloud size (pooling across tile boundaries) and a single cloud."""
