@@ -188,6 +188,7 @@ struct ehb_ctx {
   int num_sms = 0;
   int64_t launches = 0;
   int gemm_mode = 0;   // 0 = tcgen05 CTA-pair kernel, 1 = fp32 FFMA check path, 2 = tcgen05 one-CTA kernel
+  int input_umma = 0;  // 1 = K2's joint mix on tcgen05 (gcn_input_umma.cu): measured equal to the FFMA kernel, opt-in
   int pdl = 1;         // hidden-layer launches use programmatic dependent launch (set-up overlaps the previous layer's tail)
   float act_scale = 8.f;
 
@@ -635,7 +636,9 @@ static int run_input(ehb_ctx* ctx, int step, const float* x_t, cudaStream_t stre
   p.n_slots = ctx->n_slots;
   p.step = step;
   p.mask_all = ctx->mask_all;
-  EHB_CUDA(ehb::launch_gcn_input(p, stream));
+  // the tensor-pipe joint mix is opt-in (ehb_debug_set_input_mode): both kernels take 0.083-0.087 ms at 640 x 2 slots
+  if (ctx->gemm_mode == 1 || !ctx->input_umma) EHB_CUDA(ehb::launch_gcn_input(p, stream));
+  else EHB_CUDA(ehb::launch_gcn_input_umma(p, ctx->num_sms, stream));
   ctx->launches += 1;
   return 0;
 }
@@ -1587,6 +1590,12 @@ int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm) {
 int ehb_debug_set_pdl(ehb_ctx* ctx, int on) {
   if (!ctx) return fail("null ctx");
   ctx->pdl = on ? 1 : 0;
+  return 0;
+}
+
+int ehb_debug_set_input_mode(ehb_ctx* ctx, int umma) {
+  if (!ctx) return fail("null ctx");
+  ctx->input_umma = umma ? 1 : 0;
   return 0;
 }
 

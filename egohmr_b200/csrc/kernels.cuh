@@ -86,7 +86,8 @@ struct InputLayerParams {
   int C, n_slots, step;
   int mask_all;          // image-masked pass drops every condition (only_mask_img_cond=False, egohmr.py:157-158)
 };
-cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream);
+cudaError_t launch_gcn_input(const InputLayerParams& p, cudaStream_t stream);            // fp32 FFMA (check path)
+cudaError_t launch_gcn_input_umma(const InputLayerParams& p, int num_sms, cudaStream_t stream);   // joint mix on tcgen05
 
 // Non-local block between the residual blocks and the output layer (ModulatedGCN(nonlocal_layer=True)).
 struct NonLocalParams {

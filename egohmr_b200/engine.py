@@ -429,6 +429,10 @@ class Engine:
     def set_pdl(self, on):
         check(self.lib.ehb_debug_set_pdl(self._h, 1 if on else 0))
 
+    def set_input_mode(self, umma):
+        """K2's joint mix on tcgen05 (True) or the fp32 FFMA kernel (False, default; measured equal)."""
+        check(self.lib.ehb_debug_set_input_mode(self._h, 1 if umma else 0))
+
     def set_conv_kc(self, kc):
         """k-blocks (x64 operand columns) per tensor-memory accumulation chunk of the ResNet convolution GEMMs (0 = whole K)."""
         check(self.lib.ehb_debug_set_conv_kc(self._h, int(kc)))

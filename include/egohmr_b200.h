@@ -302,6 +302,9 @@ int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);
 int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm);
 /* Hidden-layer launches with (1, default) or without (0) programmatic dependent launch (bring-up comparison). */
 int ehb_debug_set_pdl(ehb_ctx* ctx, int on);
+/* Input graph-convolution layer (K2): the fp32 FFMA kernel (0, default) or the variant with the 24x24 joint mix on the
+ * tensor pipe (1; same result to fp32 rounding, same time: the kernel is bound by assembling the per-joint features). */
+int ehb_debug_set_input_mode(ehb_ctx* ctx, int umma);
 /* ResNet convolution GEMMs: k-blocks (of 64 operand columns) chained into one tensor-memory accumulation before the
  * epilogue takes the partial sum over in fp32 registers (0 = the whole contraction in one accumulator). */
 int ehb_debug_set_conv_kc(ehb_ctx* ctx, int kc);

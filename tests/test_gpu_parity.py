@@ -154,11 +154,20 @@ def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
         torch.cuda.synchronize()
         outs[mode] = (x0.cpu().numpy(), oc.cpu().numpy(), ou.cpu().numpy())
     model.engine.set_gemm_mode(0)
+    # the opt-in input layer with its 24x24 joint mix on the tensor pipe (gcn_input_umma.cu): same bar
+    model.engine.set_input_mode(True)
+    x0, xp, oc, ou = (torch.empty_like(xt) for _ in range(4))
+    model.engine.denoise_step(0, xt, None, None, xp, x0, oc, ou)
+    torch.cuda.synchronize()
+    model.engine.set_input_mode(False)
+    k2t = (x0.cpu().numpy(), oc.cpu().numpy(), ou.cpu().numpy())
     model._temb_key = None
     model._cond_key = None
     assert not model.engine.check_overflow()
     print(f"fp32-FFMA path vs f64: {np.abs(outs[1][0] - ref_x0).max():.3e}; tcgen05 path vs f64: "
-          f"{np.abs(outs[0][0] - ref_x0).max():.3e}")
+          f"{np.abs(outs[0][0] - ref_x0).max():.3e}; with the tensor-pipe input layer: {np.abs(k2t[0] - ref_x0).max():.3e}")
+    assert np.abs(k2t[1] - ref_c).max() < X0_TOL and np.abs(k2t[2] - ref_u).max() < X0_TOL
+    assert np.abs(k2t[0] - ref_x0).max() < X0_TOL
     assert np.abs(outs[1][0] - ref_x0).max() < 3e-6        # fp32 FFMA path vs float64
     assert np.abs(outs[0][1] - ref_c).max() < X0_TOL       # image-conditioned pass
     assert np.abs(outs[0][2] - ref_u).max() < X0_TOL       # image-masked pass
@@ -274,7 +283,16 @@ def test_model_flag_variants_vs_reference_golden(golden_dir, case, flags):
     d = np.abs(np.stack(x0s) - g64["trace_x0"]).max()
     print(f"{case}: max|x0 - ref_f64| = {d:.3e}")
     # the optional non-local block (off in both reference drivers) adds a softmax and two more GEMMs per pass: 1.2e-6
-    assert d < (2e-6 if flags.get("nonlocal_layer") else X0_TOL)
+    tol = 2e-6 if flags.get("nonlocal_layer") else X0_TOL
+    assert d < tol
+    # the same chain through the opt-in input layer with its joint mix on the tensor pipe (2 channel chunks at hid 256;
+    # the drop-every-condition and single-pass slot tables)
+    model.engine.set_input_mode(True)
+    x0t = [o["pred_xstart"].cpu().numpy() for o in
+           diffusion.ddim_sample_loop_progressive(model, batch, [3, 144], noise=torch.from_numpy(noise[0]).cuda())]
+    dt = np.abs(np.stack(x0t) - g64["trace_x0"]).max()
+    print(f"{case}: tensor-pipe input layer max|x0 - ref_f64| = {dt:.3e}")
+    assert dt < tol
     assert not model.engine.check_overflow()
     model.engine.close()
 
