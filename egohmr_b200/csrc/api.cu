@@ -187,7 +187,8 @@ struct ehb_ctx {
   int device = 0;
   int num_sms = 0;
   int64_t launches = 0;
-  int gemm_mode = 0;   // 0 = tcgen05 CTA-pair kernel, 1 = fp32 FFMA check path, 2 = tcgen05 one-CTA kernel
+  int gemm_mode = 0;   // 0 = tcgen05 CTA pairs, transposed product (product path), 1 = fp32 FFMA check path,
+                       // 2 = tcgen05 one-CTA row-major kernel, 3 = tcgen05 CTA pairs, row-major product
   int input_umma = 0;  // 1 = K2's joint mix on tcgen05 (gcn_input_umma.cu): measured equal to the FFMA kernel, opt-in
   int pdl = 1;         // hidden-layer launches use programmatic dependent launch (set-up overlaps the previous layer's tail)
   float act_scale = 8.f;
@@ -201,6 +202,7 @@ struct ehb_ctx {
     float w_scale = 1.f;
     CUtensorMap tmB;    // box 256 rows (one-CTA kernel)
     CUtensorMap tmB2;   // box 128 rows (CTA-pair kernel: each CTA stages half of the B tile)
+    CUtensorMap tmW;    // box 64 rows (transposed kernel: 64 channels of h0 / h1 per CTA)
   };
   std::vector<Hidden*> hidden;
   ehb::AdjMix adj_in, adj_out;
@@ -222,6 +224,7 @@ struct ehb_ctx {
   DevBuf img_of_body, slot_body, slot_cond, body_slot;
   DevBuf act_hl[2], res, mid, h_tmp;
   CUtensorMap tmA[2];
+  CUtensorMap tmX[2];  // the same buffers with 120-row boxes (transposed kernel: the real rows of a 128-row tile)
 
   // ---- sampler
   int kind = 0;
@@ -331,8 +334,8 @@ void ehb_ctx_destroy(ehb_ctx* ctx) {
 
 int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode) {
   if (!ctx) return fail("null ctx");
-  if (gemm_mode < 0 || gemm_mode > 2)
-    return fail("gemm_mode must be 0 (tcgen05 CTA pairs), 1 (fp32 check) or 2 (tcgen05 single CTA)");
+  if (gemm_mode < 0 || gemm_mode > 3)
+    return fail("gemm_mode must be 0 (tcgen05 CTA pairs, transposed product), 1 (fp32 check), 2 (tcgen05 single CTA) or 3 (tcgen05 CTA pairs, row-major product)");
   ctx->gemm_mode = gemm_mode;
   return 0;
 }
@@ -440,6 +443,7 @@ int ehb_gcn_load(ehb_ctx* ctx, const ehb_gcn_weights* w) {
     EHB_CUDA(h->bn_shift.upload(sh));
     if (make_tmap_f16(&h->tmB, h->w_hl.p, C2, C2, 256)) return 1;
     if (make_tmap_f16(&h->tmB2, h->w_hl.p, C2, C2, 128)) return 1;
+    if (make_tmap_f16(&h->tmW, h->w_hl.p, C2, C2, 64)) return 1;
   }
 
   // ---- output layer
@@ -560,6 +564,7 @@ int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body) {
       EHB_CUDA(ctx->act_hl[i].ensure(rows * 2 * C * sizeof(__half), true));
       EHB_CUDA(cudaMemset(ctx->act_hl[i].p, 0, rows * 2 * C * sizeof(__half)));
       if (make_tmap_f16(&ctx->tmA[i], ctx->act_hl[i].p, rows, 2 * C, 128)) return 1;
+      if (make_tmap_f16(&ctx->tmX[i], ctx->act_hl[i].p, rows, 2 * C, ehb::SLOTS_PER_TILE * ehb::NJ)) return 1;
     }
     EHB_CUDA(ctx->res.ensure(rows * C * sizeof(float), true));
     EHB_CUDA(cudaMemset(ctx->res.p, 0, rows * C * sizeof(float)));
@@ -592,10 +597,15 @@ static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
   p.write_f32 = second ? 1 : 0;
   p.write_hl = (l != L - 1 || ctx->nl_loaded) ? 1 : 0;   // the non-local block consumes the last layer's operand
   if (ctx->gemm_mode == 0) {
-    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB2, p, ctx->num_sms, 2, ctx->pdl != 0, stream));
+    // product path: transposed product, N = 240 activation rows = 10 slots per CTA pair, no pad rows (gcn_umma_t.cu)
+    EHB_CUDA(ehb::launch_gcn_hidden_umma_t(ctx->tmX[l & 1], h.tmW, p, ctx->num_sms, ctx->pdl != 0, stream));
     ctx->launches += 1;
   } else if (ctx->gemm_mode == 2) {
     EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB, p, ctx->num_sms, 1, ctx->pdl != 0, stream));
+    ctx->launches += 1;
+  } else if (ctx->gemm_mode == 3) {
+    // the round-1 kernel: activations on the M side, 5 slots + 8 pad rows per 128-row tile (same bits, 6 % more MMA time)
+    EHB_CUDA(ehb::launch_gcn_hidden_umma(ctx->tmA[l & 1], h.tmB2, p, ctx->num_sms, 2, ctx->pdl != 0, stream));
     ctx->launches += 1;
   } else {
     const size_t rows = static_cast<size_t>(ctx->n_mtiles) * ehb::TILE_ROWS;

@@ -42,6 +42,10 @@ struct HiddenLayerParams {
 // kernel in the stream and waits for it with griddepcontrol.wait before touching global memory)
 cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const HiddenLayerParams& p,
                                    int num_sms, int ctas, bool pdl, cudaStream_t stream);
+// transposed product (gcn_umma_t.cu): weights on the M side, N = 240 activation rows = 10 slots without pad rows.
+// tmX: activation map with 120-row boxes; tmW: weight map with 64-row boxes.  n_mtiles even.
+cudaError_t launch_gcn_hidden_umma_t(const CUtensorMap& tmX, const CUtensorMap& tmW, const HiddenLayerParams& p,
+                                     int num_sms, bool pdl, cudaStream_t stream);
 size_t gcn_hidden_umma_smem_bytes();
 int gcn_hidden_umma_bk();   // fp16 elements per TMA box row (32: SWIZZLE_64B, 64: SWIZZLE_128B)
 #ifndef EHB_UMMA_BK

@@ -294,8 +294,10 @@ int ehb_rotmat_to_angle_axis(ehb_ctx* ctx, const float* R, int n, float* aa, voi
 int ehb_smpl_backward(ehb_ctx* ctx, const float* x_t, const float* betas, const float* g_verts, const float* g_joints,
                       const float* g_aa, float* grad_x, void* stream);
 
-/* Diagnostics.  gemm_mode 0 = tcgen05 fp16x3 kernel on CTA pairs (cta_group::2, product path), 1 = fp32 FFMA check
- * path (tests only), 2 = tcgen05 fp16x3 kernel on single CTAs (cta_group::1, bring-up comparison). */
+/* Diagnostics.  gemm_mode 0 = tcgen05 fp16x3 kernel on CTA pairs (cta_group::2), transposed product: weights on the M
+ * side, N = 240 activation rows = 10 (body, pass) slots, no pad rows (product path); 1 = fp32 FFMA check path (tests only);
+ * 2 = tcgen05 fp16x3 row-major kernel on single CTAs (cta_group::1, bring-up comparison); 3 = the row-major CTA-pair
+ * kernel (activations on the M side, 5 slots + 8 pad rows per 128-row tile: same bits as mode 0, 6 % more MMA time). */
 int ehb_debug_set_gemm_mode(ehb_ctx* ctx, int gemm_mode);
 /* ResNet 3x3 convolutions: 1 = implicit GEMM through 4-D TMA boxes (product path), 0 = explicit im2col matrix + the
  * same GEMM (bring-up comparison; both must give identical bits). */

@@ -134,7 +134,8 @@ def _oracle_denoise(sd, n_blocks, x_t, t_orig, g, dtype=np.float64):
 
 def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
     """One EgoHMR.forward at t=30 on the reference's own encoder features: tcgen05 path vs float64 oracle, and the
-    tcgen05 path vs the fp32 FFMA check path (isolates the tensor-core numerics)."""
+    tcgen05 path vs the fp32 FFMA check path (isolates the tensor-core numerics).  The product kernel (transposed
+    product, no pad rows) and the row-major CTA-pair kernel accumulate the same terms in the same order: equal bits."""
     model, diffusion, sd, _, _, _ = full
     g = np.load(os.path.join(golden_dir, "ddim5_T50_hid1024_f64.npz"))
     batch = _tb(synth.make_batch(0, 2))
@@ -147,7 +148,7 @@ def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
     model.engine.set_schedule(0, np.array([[1, 1, 1, 0, 0, 0, 0, 0]], np.float32))
     xt = torch.from_numpy(x_t.astype(np.float32)).cuda()
     outs = {}
-    for mode in (1, 0):
+    for mode in (1, 3, 0):
         model.engine.set_gemm_mode(mode)
         x0, xp, oc, ou = (torch.empty_like(xt) for _ in range(4))
         model.engine.denoise_step(0, xt, None, None, xp, x0, oc, ou)
@@ -173,6 +174,8 @@ def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
     assert np.abs(outs[0][2] - ref_u).max() < X0_TOL       # image-masked pass
     assert np.abs(outs[0][0] - ref_x0).max() < X0_TOL      # fused select
     assert np.abs(outs[0][0] - outs[1][0]).max() < X0_TOL
+    for a, b in zip(outs[0], outs[3]):
+        assert np.array_equal(a, b)
 
 
 def test_forward_signature_and_outputs(full):
