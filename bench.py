@@ -584,7 +584,7 @@ def run_b200(args):
     except (OSError, ValueError, KeyError):
         pass
     roofline = {
-        "kernel": "gcn_hidden_umma_kernel (8 launches per reverse step, 40 per sampling pass)",
+        "kernel": "gcn_hidden_umma_t_kernel (8 launches per reverse step, 40 per sampling pass)",
         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590",
         "issued_tflops": 3 * achieved, "issued_frac": 3 * achieved / peak,
