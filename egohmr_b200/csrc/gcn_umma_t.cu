@@ -16,6 +16,7 @@
 // and the mix warps are the ones of gcn_umma.cu unchanged (slot x joint-half each, lane = channel).  A hand-off chunk is
 // (one of the pair's two tiles) x (32 channels): filled by the two tcgen05.ld warps that own those channels' h0 / h1 lanes
 // while the other two already fetch the next chunk from TMEM.
+#include "gcn_mix.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -44,7 +45,6 @@ static_assert(SMEM_BYTES <= 232448, "exceeds 227 KiB of dynamic shared memory");
 // 0-31 / 32-63 of this CTA's 64, quadrants 2,3 the h1 lanes), 4-13 joint mix / store, 14 TMA producer, 15 MMA issuer.
 constexpr int NUM_WARPS = 16;
 constexpr int NUM_MIX_WARPS = 10;
-constexpr int NJH = NJ / 2;
 constexpr int NUM_THREADS = NUM_WARPS * 32;
 constexpr int LD_WARP0 = 0, MIX_WARP0 = 4, TMA_WARP = 14, MMA_WARP = 15;
 constexpr int TMEM_COLS = 512;
@@ -263,7 +263,7 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   } else if (warp >= MIX_WARP0 && warp < MIX_WARP0 + NUM_MIX_WARPS) {
     // ------------------------------------------------------------------ joint mix + BN + ReLU (+res) + store
     const int w = (warp - MIX_WARP0) % SLOTS_PER_TILE;   // slot within the tile
-    const int j0 = ((warp - MIX_WARP0) / SLOTS_PER_TILE) * NJH;  // first output joint of this warp
+    const int j0 = ((warp - MIX_WARP0) / SLOTS_PER_TILE) * MIX_NJH;  // first output joint of this warp
     uint32_t chunk_it = 0;
     float amax = 0.f;
     for (int u = unit0; u < total_units; u += unit_step) {
@@ -272,69 +272,9 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         // chunk = (tile ch / 2 of the pair) x (32-channel half ch % 2 of this CTA's 64 channels)
         const int m_tile = (u / n_cgroups) * 2 + (ch >> 1);
         const bool valid = (m_tile * SLOTS_PER_TILE + w) < p.n_slots;
-        float g[NJ], y[NJH], rsd[NJH];
         const int c = (u % n_cgroups) * 128 + static_cast<int>(rank) * 64 + (ch & 1) * CHUNK + lane;
         const size_t row0 = static_cast<size_t>(m_tile) * TILE_ROWS + NJ * w + j0;
-        // residual rows are fetched before the hand-off wait: independent loads in flight, latency hidden
-        const float* rp = p.res + row0 * p.C + c;
-        if (p.add_res && valid) {
-#pragma unroll
-          for (int jj = 0; jj < NJH; ++jj) rsd[jj] = __ldcg(rp + static_cast<size_t>(jj) * p.C);
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < NJH; ++jj) rsd[jj] = 0.f;
-        }
-        ptx::mbar_wait(&bars->cfull, chunk_it & 1);
-        {
-          const float4* gp = reinterpret_cast<const float4*>(G_T + lane * GT_LD + NJ * w);
-          const float4* dp = reinterpret_cast<const float4*>(D_T + lane * GT_LD + NJ * w + j0);
-#pragma unroll
-          for (int v = 0; v < NJ / 4; ++v) {
-            const float4 a = gp[v];
-            g[4 * v + 0] = a.x; g[4 * v + 1] = a.y; g[4 * v + 2] = a.z; g[4 * v + 3] = a.w;
-          }
-#pragma unroll
-          for (int v = 0; v < NJH / 4; ++v) {
-            const float4 b = dp[v];
-            y[4 * v + 0] = b.x; y[4 * v + 1] = b.y; y[4 * v + 2] = b.z; y[4 * v + 3] = b.w;
-          }
-        }
-        ptx::mbar_arrive(&bars->cempty);
-        if (!valid) continue;
-        if (j0 == 0) {
-#pragma unroll
-          for (int jj = 0; jj < NJH; ++jj) {
-            float acc = y[jj];
-#pragma unroll
-            for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[jj][i], g[i], acc);
-            y[jj] = acc;
-          }
-        } else {
-#pragma unroll
-          for (int jj = 0; jj < NJH; ++jj) {
-            float acc = y[jj];
-#pragma unroll
-            for (int i = 0; i < NJ; ++i) acc = fmaf(p.adj.off[NJH + jj][i], g[i], acc);
-            y[jj] = acc;
-          }
-        }
-        const float sc = __ldg(p.bn_scale + c);
-        const float sh = __ldg(p.bn_shift + c);
-        float* fp = p.res + row0 * p.C + c;
-        __half* hp = p.out_hl + row0 * (2 * static_cast<size_t>(p.C)) + c;
-#pragma unroll
-        for (int jj = 0; jj < NJH; ++jj) {
-          const float v = fmaxf(fmaf(y[jj], sc, sh), 0.f) + rsd[jj];
-          if (p.write_f32) fp[static_cast<size_t>(jj) * p.C] = v;
-          if (p.write_hl) {
-            const float sv = v * p.act_scale;
-            const __half hi = __float2half_rn(sv);
-            const __half lo = __float2half_rn(sv - __half2float(hi));
-            hp[static_cast<size_t>(jj) * 2 * p.C] = hi;
-            hp[static_cast<size_t>(jj) * 2 * p.C + p.C] = lo;
-            amax = fmaxf(amax, fabsf(sv));
-          }
-        }
+        mix_chunk<GT_LD>(p, G_T, D_T, &bars->cfull, &bars->cempty, chunk_it, valid, c, row0, w, j0, lane, amax);
       }
     }
     if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);  // also catches NaN
