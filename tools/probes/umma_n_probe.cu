@@ -109,6 +109,9 @@ int main() {
   run<224>(prop.multiProcessorCount, sink);
   run<192>(prop.multiProcessorCount, sink);
   run<128>(prop.multiProcessorCount, sink);
+  run<96>(prop.multiProcessorCount, sink);
+  run<64>(prop.multiProcessorCount, sink);
+  run<32>(prop.multiProcessorCount, sink);
   run<256>(prop.multiProcessorCount, sink);
   return 0;
 }
