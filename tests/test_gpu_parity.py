@@ -148,7 +148,7 @@ def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
     model.engine.set_schedule(0, np.array([[1, 1, 1, 0, 0, 0, 0, 0]], np.float32))
     xt = torch.from_numpy(x_t.astype(np.float32)).cuda()
     outs = {}
-    for mode in (1, 3, 0):
+    for mode in (1, 2, 3, 0):
         model.engine.set_gemm_mode(mode)
         x0, xp, oc, ou = (torch.empty_like(xt) for _ in range(4))
         model.engine.denoise_step(0, xt, None, None, xp, x0, oc, ou)
@@ -176,6 +176,7 @@ def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
     assert np.abs(outs[0][0] - outs[1][0]).max() < X0_TOL
     for a, b in zip(outs[0], outs[3]):
         assert np.array_equal(a, b)
+    assert np.abs(outs[2][0] - ref_x0).max() < X0_TOL      # single-CTA bring-up variant of the row-major kernel
 
 
 def test_forward_signature_and_outputs(full):
