@@ -50,6 +50,26 @@ struct Barriers {
 };
 static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
 
+// ---- optional per-warp timeline (nvcc -DEHB_CONV_TRACE; tools/conv_trace.sh): clock64 stamps of the first units of CTA 0 in
+// one chosen launch (ordinal modulo the 53 convolution GEMMs of a ResNet-50 forward).  Compiled out of the product build.
+#ifdef EHB_CONV_TRACE
+constexpr int TRACE_UNITS = 12, TRACE_SLOTS = 40;
+__device__ long long g_trace[TRACE_UNITS][TRACE_SLOTS];
+__device__ int g_trace_counter = 0, g_trace_target = -1, g_trace_period = 53;
+#define EHB_STAMP(cond, unit_i, slot)                                                                   \
+  do {                                                                                                  \
+    if (trace_on && (cond) && (unit_i) < TRACE_UNITS) g_trace[(unit_i)][(slot)] = clock64();            \
+  } while (0)
+#define EHB_NEXT_UNIT() ++ui
+#else
+#define EHB_NEXT_UNIT() \
+  do {                  \
+  } while (0)
+#define EHB_STAMP(cond, unit_i, slot) \
+  do {                                \
+  } while (0)
+#endif
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -74,6 +94,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool CHUNKED = BN <= 128;   // running sums live in registers: 64 / 32 per epilogue thread
   constexpr int NACC = TMEM_COLS / BN;  // accumulator stages: the MMA warp may run NACC - 1 chunks ahead of the epilogue
   const int kc = (CHUNKED && p.kc > 0 && p.kc < KB) ? p.kc : KB;   // k-blocks per accumulation chunk
+#ifdef EHB_CONV_TRACE
+  const bool trace_on = blockIdx.x == 0 && (g_trace_counter % g_trace_period) == g_trace_target;
+  int ui = 0;   // unit ordinal of this CTA
+#endif
 
   if (warp == TMA_WARP && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -122,7 +146,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int cpk = p.implicit ? p.Cin / BK : 1;
         const uint32_t a_box_bytes = p.implicit ? static_cast<uint32_t>(p.nb * p.th * p.Wo) * BK * 2 : A_BYTES;
         for (int kb = 0; kb < KB; ++kb) {
+          EHB_STAMP(kb == 0, ui, 30);
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          EHB_STAMP(kb == 0, ui, 31);
           uint8_t* s = smem + stage * STAGE_BYTES;
           const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);
           if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * (2 * a_box_bytes + 2 * B_BYTES));
@@ -157,6 +183,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             phase ^= 1;
           }
         }
+        EHB_STAMP(true, ui, 32);   // this unit's loads are issued
+        EHB_NEXT_UNIT();
       }
     }
     __syncwarp();
@@ -170,12 +198,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // in fp32 registers (round-to-nearest) — the tensor core's own fp32 accumulation truncates, a bias that grows
         // with the number of MMAs chained into one accumulator (DESIGN.md, K9 numerics)
         for (int kb0 = 0; kb0 < KB; kb0 += kc) {
+          EHB_STAMP(lane == 0 && kb0 == 0, ui, 24);
           ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
+          EHB_STAMP(lane == 0 && kb0 == 0, ui, 25);   // accumulator stage free
           ptx::tc_fence_after_sync();
           const uint32_t tacc = tmem_base + as * BN;
           const int kend = min(KB, kb0 + kc);
           for (int kb = kb0; kb < kend; ++kb) {
             ptx::mbar_wait(&bars->full[stage], phase);
+            EHB_STAMP(lane == 0 && kb == 0, ui, 26);    // first operands landed
             ptx::tc_fence_after_sync();
             const uint32_t sa = ptx::smem_u32(smem + stage * STAGE_BYTES);
             // the small cross terms (hi*lo, lo*hi: 2^-11 of the main term) of the whole k-block go first: the tensor
@@ -211,6 +242,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             aphase ^= 1;
           }
         }
+        EHB_STAMP(lane == 0, ui, 27);   // all MMAs of the unit issued and committed
+        EHB_NEXT_UNIT();
       }
     }
   } else {
@@ -227,6 +260,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int n_chunks = (KB + kc - 1) / kc;
     float acc[CHUNKED ? HALF : 1];        // fp32 running sum of the first n_chunks - 1 accumulation chunks
     for (int u = unit0; u < n_units; u += unit_step) {
+      EHB_STAMP(threadIdx.x == 0, ui, 0);
       const int n_tile = u % p.n_ntiles;
       const int tile = (u / p.n_ntiles) * 2 + static_cast<int>(rank);
       long long tile_first = static_cast<long long>(tile) * BM, tile_rows = BM;
@@ -295,7 +329,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      EHB_STAMP(threadIdx.x == 0, ui, 1);
       ptx::mbar_wait(&bars->tfull[as], aphase);
+      EHB_STAMP(threadIdx.x == 0, ui, 2);   // final accumulator ready
       ptx::tc_fence_after_sync();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BN + col_half * HALF;
 #pragma unroll(CHUNKED ? CHUNKS : 1)
@@ -303,6 +339,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
         ptx::tmem_ld_32x32b_x32(trow + ch * 32, v);
         ptx::tmem_ld_wait();
+        EHB_STAMP(threadIdx.x == 0, ui, 4 + 4 * ch);   // chunk's accumulator in registers
         if (ch == CHUNKS - 1) {
           ptx::tc_fence_before_sync();
           __syncwarp();
@@ -331,6 +368,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint4 rh[4], rl[4];
           warp_finish_rows_64B(scratch, raw_h, rh, lane);
           warp_finish_rows_64B(scratch, raw_l, rl, lane);
+          EHB_STAMP(threadIdx.x == 0, ui, 5 + 4 * ch);   // identity block arrived and transposed
           if (ch + 1 < CHUNKS) {
             warp_issue_rows_64B(raw_h, p.res_hl + row0w * p.out_ld + cg + 32, p.out_ld, rows_valid, lane);
             warp_issue_rows_64B(raw_l, p.res_hl + row0w * p.out_ld + p.Cout + cg + 32, p.out_ld, rows_valid, lane);
@@ -356,6 +394,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int c = 0; c < 8; ++c) o[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
+        EHB_STAMP(threadIdx.x == 0, ui, 6 + 4 * ch);     // arithmetic done
         if (p.out_hl) {
           __align__(16) __half2 hi[16], lo[16];
 #pragma unroll
@@ -370,7 +409,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           warp_store_rows_64B(scratch, *reinterpret_cast<const uint4(*)[4]>(lo), p.out_hl + row0w * p.out_ld + p.Cout + cg,
                               p.out_ld, rows_valid, lane);
         }
+        EHB_STAMP(threadIdx.x == 0, ui, 7 + 4 * ch);     // stores issued
       }
+      EHB_NEXT_UNIT();
       if (++as == NACC) {
         as = 0;
         aphase ^= 1;
@@ -386,7 +427,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
+#ifdef EHB_CONV_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_trace_counter = g_trace_counter + 1;   // launches are stream-ordered
+#endif
 }
+
+#ifdef EHB_CONV_TRACE
+}  // namespace
+// trace control (tools/conv_trace.sh builds a library with -DEHB_CONV_TRACE and calls these through ctypes)
+extern "C" int ehb_conv_trace_arm(int target, int period) {
+  int zero = 0;
+  static long long zeros[TRACE_UNITS][TRACE_SLOTS] = {};
+  if (cudaMemcpyToSymbol(g_trace_counter, &zero, sizeof(int)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(g_trace_target, &target, sizeof(int)) != cudaSuccess) return 1;
+  if (cudaMemcpyToSymbol(g_trace_period, &period, sizeof(int)) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros)) != cudaSuccess;
+}
+extern "C" int ehb_conv_trace_read(long long* out) {   // [TRACE_UNITS][TRACE_SLOTS]
+  return cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * TRACE_UNITS * TRACE_SLOTS) != cudaSuccess;
+}
+namespace {
+#endif
 
 template <int BN>
 cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA2, const CUtensorMap& tmB2,
