@@ -61,6 +61,25 @@ struct Barriers {
 };
 static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
 
+// ---- optional timeline (nvcc -DEHB_K1_TRACE; tools/k1_trace.sh): per unit of CTA 0 of the first launch after arming, the cycles
+// the MMA warp waited for a free accumulator and for operands, the TMA warp for free stages, one tcgen05.ld warp for the
+// accumulator and one mix warp for its chunks.  Compiled out of the product build.
+#ifdef EHB_K1_TRACE
+constexpr int TRACE_UNITS = 16, TRACE_SLOTS = 16;
+__device__ long long g_k1_trace[TRACE_UNITS][TRACE_SLOTS];
+__device__ int g_k1_armed = 0;
+#define K1_TRACE(unit_i, slot, val)                                                        \
+  do {                                                                                     \
+    if (trace_on && (unit_i) < TRACE_UNITS) g_k1_trace[(unit_i)][(slot)] = (val);          \
+  } while (0)
+#define K1_CLOCK() clock64()
+#else
+#define K1_TRACE(unit_i, slot, val) \
+  do {                              \
+  } while (0)
+#define K1_CLOCK() 0LL
+#endif
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                          const __grid_constant__ HiddenLayerParams p) {
@@ -83,6 +102,10 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   const int total_units = (p.n_mtiles / 2) * n_cgroups;
   const int unit0 = blockIdx.x / 2;
   const int unit_step = gridDim.x / 2;
+#ifdef EHB_K1_TRACE
+  const bool trace_on = blockIdx.x == 0 && g_k1_armed == 1 && lane == 0;
+#endif
+  [[maybe_unused]] int ui = 0;   // unit ordinal of this CTA (timeline only)
 
   if (warp == TMA_WARP && lane == 0) {
     ptx::prefetch_tensormap(&tmX);
@@ -124,8 +147,11 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         // weight rows of channel group cg are stored as [128 x h0 | 128 x h1]; this CTA takes 64 of each
         const int w_row0 = (u % n_cgroups) * 256 + static_cast<int>(rank) * 64;
         const int w_row1 = w_row0 + 128;
+        [[maybe_unused]] long long w_empty = 0;
         for (int kb = 0; kb < KB; ++kb) {
+          const long long c0 = K1_CLOCK();
           ptx::mbar_wait(&bars->empty[stage], phase ^ 1);
+          w_empty += K1_CLOCK() - c0;
           uint8_t* s = stage_base + stage * STAGE_BYTES;
           const uint32_t lfull = ptx::mapa(ptx::smem_u32(&bars->full[stage]), 0);  // the leader's barrier
           if (leader) ptx::mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_BYTES);
@@ -140,6 +166,9 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             phase ^= 1;
           }
         }
+        K1_TRACE(ui, 8, w_empty);
+        K1_TRACE(ui, 9, K1_CLOCK());
+        ++ui;
       }
     }
     __syncwarp();
@@ -152,11 +181,16 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       int as = 0;
       uint32_t aphase = 0;
       for (int u = unit0; u < total_units; u += unit_step) {
+        [[maybe_unused]] const long long t_unit = K1_CLOCK();
         ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
+        [[maybe_unused]] const long long t_acc = K1_CLOCK();
+        [[maybe_unused]] long long w_full = 0;
         ptx::tc_fence_after_sync();
         const uint32_t tacc = tmem_base + as * ACC_STRIDE;
         for (int kb = 0; kb < KB; ++kb) {
+          const long long c0 = K1_CLOCK();
           ptx::mbar_wait(&bars->full[stage], phase);
+          w_full += K1_CLOCK() - c0;
           ptx::tc_fence_after_sync();
           {
             const uint32_t sa = ptx::smem_u32(stage_base + stage * STAGE_BYTES);
@@ -182,6 +216,11 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
             phase ^= 1;
           }
         }
+        K1_TRACE(ui, 0, t_unit);
+        K1_TRACE(ui, 1, t_acc - t_unit);     // waited for a free accumulator
+        K1_TRACE(ui, 2, w_full);             // waited for operands (sum over the unit's k-blocks)
+        K1_TRACE(ui, 3, K1_CLOCK());         // all MMAs of the unit issued
+        ++ui;
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
@@ -204,7 +243,12 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       float m[NJ];
 #pragma unroll
       for (int j = 0; j < NJ; ++j) m[j] = __ldg(p.mod + static_cast<size_t>(j) * p.C + c);
+      [[maybe_unused]] const long long t_ld0 = K1_CLOCK();
       ptx::mbar_wait(&bars->tfull[as], aphase);
+      if (q == 0) {
+        K1_TRACE(ui, 4, K1_CLOCK() - t_ld0);   // tcgen05.ld warp 0 waited for the accumulator
+        K1_TRACE(ui, 5, K1_CLOCK());           // accumulator complete (MMAs retired)
+      }
       ptx::tc_fence_after_sync();
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_STRIDE;
 #pragma unroll 1
@@ -255,6 +299,8 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         }
         ptx::mbar_arrive(&bars->cfull);
       }
+      if (q == 3) K1_TRACE(ui, 6, K1_CLOCK());   // last chunk staged
+      ++ui;
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -276,6 +322,8 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         const size_t row0 = static_cast<size_t>(m_tile) * TILE_ROWS + NJ * w + j0;
         mix_chunk<GT_LD>(p, G_T, D_T, &bars->cfull, &bars->cempty, chunk_it, valid, c, row0, w, j0, lane, amax);
       }
+      if (warp == MIX_WARP0) K1_TRACE(ui, 7, K1_CLOCK());   // unit's outputs stored (mix warp 0)
+      ++ui;
     }
     if (!(amax <= 65504.f)) atomicExch(p.overflow_flag, 1);  // also catches NaN
   }
@@ -290,6 +338,17 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
 }
 
 }  // namespace
+
+#ifdef EHB_K1_TRACE
+extern "C" int ehb_k1_trace_arm(int on) {
+  static long long zeros[TRACE_UNITS][TRACE_SLOTS] = {};
+  if (on && cudaMemcpyToSymbol(g_k1_trace, zeros, sizeof(zeros)) != cudaSuccess) return 1;
+  return cudaMemcpyToSymbol(g_k1_armed, &on, sizeof(int)) != cudaSuccess;
+}
+extern "C" int ehb_k1_trace_read(long long* out) {   // [TRACE_UNITS][TRACE_SLOTS]
+  return cudaMemcpyFromSymbol(out, g_k1_trace, sizeof(long long) * TRACE_UNITS * TRACE_SLOTS) != cudaSuccess;
+}
+#endif
 
 cudaError_t launch_gcn_hidden_umma_t(const CUtensorMap& tmX, const CUtensorMap& tmW, const HiddenLayerParams& p, int num_sms,
                                      bool pdl, cudaStream_t stream) {
