@@ -102,6 +102,7 @@ SIGNATURES = {
     "ehb_debug_set_resnet_mode": (C.c_int, [_vp, C.c_int]),
     "ehb_debug_set_pdl": (C.c_int, [_vp, C.c_int]),
     "ehb_debug_set_input_mode": (C.c_int, [_vp, C.c_int]),
+    "ehb_debug_set_k1_fused": (C.c_int, [_vp, C.c_int]),
     "ehb_debug_set_conv_kc": (C.c_int, [_vp, C.c_int]),
     "ehb_debug_gemm_hl": (C.c_int, [_vp, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                     c_float_p]),

@@ -189,6 +189,9 @@ struct ehb_ctx {
   int64_t launches = 0;
   int gemm_mode = 0;   // 0 = tcgen05 CTA pairs, transposed product (product path), 1 = fp32 FFMA check path,
                        // 2 = tcgen05 one-CTA row-major kernel, 3 = tcgen05 CTA pairs, row-major product
+  int k1_fused = 0;    // 1 = the hidden layers of a reverse step as ONE persistent launch (gcn_umma_fused.cu): same bits, measured
+                       // 7-8 % slower than one launch per layer, opt-in through ehb_debug_set_k1_fused
+  DevBuf k1_done;      // its per-(layer, row group) completion counters
   int input_umma = 0;  // 1 = K2's joint mix on tcgen05 (gcn_input_umma.cu): measured equal to the FFMA kernel, opt-in
   int pdl = 1;         // hidden-layer launches use programmatic dependent launch (set-up overlaps the previous layer's tail)
   float act_scale = 8.f;
@@ -568,6 +571,7 @@ int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body) {
     }
     EHB_CUDA(ctx->res.ensure(rows * C * sizeof(float), true));
     EHB_CUDA(cudaMemset(ctx->res.p, 0, rows * C * sizeof(float)));
+    EHB_CUDA(ctx->k1_done.ensure(sizeof(int) * ehb::MAX_FUSED_LAYERS * (n_mtiles / 2), true));
   }
   ctx->n_bodies = n_bodies;
   ctx->n_slots = n_slots;
@@ -576,10 +580,33 @@ int ehb_set_bodies(ehb_ctx* ctx, int n_bodies, const int32_t* img_of_body) {
   return 0;
 }
 
-static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
+static void fill_hidden_params(ehb_ctx* ctx, int l, ehb::HiddenLayerParams& p);
+
+// All hidden layers of the step as one persistent launch (product path).
+static int run_hidden_fused(ehb_ctx* ctx, cudaStream_t stream) {
+  const int L = static_cast<int>(ctx->hidden.size());
+  ehb::FusedHiddenMaps maps;
+  ehb::FusedHiddenParams fp;
+  maps.x[0] = ctx->tmX[0];
+  maps.x[1] = ctx->tmX[1];
+  for (int l = 0; l < L; ++l) {
+    maps.w[l] = ctx->hidden[l]->tmW;
+    fill_hidden_params(ctx, l, fp.layer[l]);
+  }
+  for (int l = L; l < ehb::MAX_FUSED_LAYERS; ++l) {   // unused slots: defined contents
+    maps.w[l] = maps.w[0];
+    fp.layer[l] = fp.layer[0];
+  }
+  fp.n_layers = L;
+  fp.done = ctx->k1_done.as<int>();
+  EHB_CUDA(ehb::launch_gcn_hidden_fused(maps, fp, ctx->num_sms, ctx->pdl != 0, stream));
+  ctx->launches += 1;
+  return 0;
+}
+
+static void fill_hidden_params(ehb_ctx* ctx, int l, ehb::HiddenLayerParams& p) {
   const int L = static_cast<int>(ctx->hidden.size());
   ehb_ctx::Hidden& h = *ctx->hidden[l];
-  ehb::HiddenLayerParams p;
   p.adj = h.adj;
   p.mod = h.mod_scaled.as<float>();
   p.bn_scale = h.bn_scale.as<float>();
@@ -596,6 +623,13 @@ static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
   p.add_res = second ? 1 : 0;
   p.write_f32 = second ? 1 : 0;
   p.write_hl = (l != L - 1 || ctx->nl_loaded) ? 1 : 0;   // the non-local block consumes the last layer's operand
+}
+
+static int run_hidden(ehb_ctx* ctx, int l, cudaStream_t stream) {
+  ehb_ctx::Hidden& h = *ctx->hidden[l];
+  ehb::HiddenLayerParams p;
+  fill_hidden_params(ctx, l, p);
+  const bool second = (l & 1) == 1;
   if (ctx->gemm_mode == 0) {
     // product path: transposed product, N = 240 activation rows = 10 slots per CTA pair, no pad rows (gcn_umma_t.cu)
     EHB_CUDA(ehb::launch_gcn_hidden_umma_t(ctx->tmX[l & 1], h.tmW, p, ctx->num_sms, ctx->pdl != 0, stream));
@@ -694,8 +728,13 @@ static int denoise_step_impl(ehb_ctx* ctx, int step, const float* x_t, const flo
   EHB_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (run_input(ctx, step, x_t, stream)) return 1;
-  for (int l = 0; l < static_cast<int>(ctx->hidden.size()); ++l)
-    if (run_hidden(ctx, l, stream)) return 1;
+  const int L = static_cast<int>(ctx->hidden.size());
+  if (ctx->gemm_mode == 0 && ctx->k1_fused && L >= 2 && L <= ehb::MAX_FUSED_LAYERS) {
+    if (run_hidden_fused(ctx, stream)) return 1;
+  } else {
+    for (int l = 0; l < L; ++l)
+      if (run_hidden(ctx, l, stream)) return 1;
+  }
   if (ctx->nl_loaded && run_nonlocal(ctx, stream)) return 1;
   return run_output(ctx, step, x_t, noise, grad, x_prev, x0, out_cond, out_uncond, stream, x0_model);
 }
@@ -1600,6 +1639,12 @@ int ehb_debug_set_resnet_mode(ehb_ctx* ctx, int implicit_gemm) {
 int ehb_debug_set_pdl(ehb_ctx* ctx, int on) {
   if (!ctx) return fail("null ctx");
   ctx->pdl = on ? 1 : 0;
+  return 0;
+}
+
+int ehb_debug_set_k1_fused(ehb_ctx* ctx, int on) {
+  if (!ctx) return fail("null ctx");
+  ctx->k1_fused = on ? 1 : 0;
   return 0;
 }
 

@@ -17,22 +17,32 @@ constexpr int MIX_NJH = NJ / 2;   // output joints per mix warp
 
 // `p` must be the kernel's __grid_constant__ parameter (the adjacency is indexed with compile-time constants only).
 // row0 = first output row of this warp (tile row of slot w, joint j0); c = this lane's channel.
-template <int GT_LD>
+struct MixNoHook {
+  __device__ __forceinline__ void operator()() const {}
+};
+
+// after_wait: called right after the chunk's hand-off wait returns (the fused kernel publishes the PREVIOUS unit's completion
+// there: its stores have drained during the wait, so the fence that must precede the count costs nothing).
+template <int GT_LD, bool LATE_RES = false, typename AfterWait = MixNoHook>
 __device__ __forceinline__ void mix_chunk(const HiddenLayerParams& p, const float* G_T, const float* D_T, uint64_t* cfull,
                                           uint64_t* cempty, uint32_t chunk_it, bool valid, int c, size_t row0, int w, int j0,
-                                          int lane, float& amax) {
+                                          int lane, float& amax, AfterWait after_wait = AfterWait()) {
   constexpr int NJH = MIX_NJH;
   float g[NJ], y[NJH], rsd[NJH];
-  // residual rows are fetched before the hand-off wait: independent loads in flight, latency hidden
+  // residual rows are fetched before the hand-off wait: independent loads in flight, latency hidden.  (LATE_RES: after it —
+  // in the fused kernel a unit's rows may still be in flight from another CTA until its first chunk is staged; the double-
+  // buffered accumulator leaves the mix warps a whole unit of slack for the exposed latency.)
   const float* rp = p.res + row0 * p.C + c;
-  if (p.add_res && valid) {
-#pragma unroll
-    for (int jj = 0; jj < NJH; ++jj) rsd[jj] = __ldcg(rp + static_cast<size_t>(jj) * p.C);
-  } else {
-#pragma unroll
-    for (int jj = 0; jj < NJH; ++jj) rsd[jj] = 0.f;
-  }
+#define EHB_LOAD_RES()                                                                     \
+  do {                                                                                     \
+    _Pragma("unroll") for (int jj = 0; jj < NJH; ++jj)                                     \
+      rsd[jj] = (p.add_res && valid) ? __ldcg(rp + static_cast<size_t>(jj) * p.C) : 0.f;   \
+  } while (0)
+  if constexpr (!LATE_RES) EHB_LOAD_RES();
   ptx::mbar_wait(cfull, chunk_it & 1);
+  after_wait();
+  if constexpr (LATE_RES) EHB_LOAD_RES();
+#undef EHB_LOAD_RES
   {
     const float4* gp = reinterpret_cast<const float4*>(G_T + lane * GT_LD + NJ * w);
     const float4* dp = reinterpret_cast<const float4*>(D_T + lane * GT_LD + NJ * w + j0);

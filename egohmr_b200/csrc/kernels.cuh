@@ -46,6 +46,20 @@ cudaError_t launch_gcn_hidden_umma(const CUtensorMap& tmA, const CUtensorMap& tm
 // tmX: activation map with 120-row boxes; tmW: weight map with 64-row boxes.  n_mtiles even.
 cudaError_t launch_gcn_hidden_umma_t(const CUtensorMap& tmX, const CUtensorMap& tmW, const HiddenLayerParams& p,
                                      int num_sms, bool pdl, cudaStream_t stream);
+// all hidden layers of a reverse step as ONE persistent launch of the transposed kernel (gcn_umma_fused.cu): per-(layer, row
+// group) completion counters order the layers unit by unit.  done: [n_layers][n_mtiles / 2] ints (zeroed by the launcher).
+constexpr int MAX_FUSED_LAYERS = 8;
+struct FusedHiddenMaps {
+  CUtensorMap x[2];                    // the two activation operand buffers, 120-row boxes (layer l reads x[l & 1])
+  CUtensorMap w[MAX_FUSED_LAYERS];     // per-layer weights, 64-row boxes
+};
+struct FusedHiddenParams {
+  HiddenLayerParams layer[MAX_FUSED_LAYERS];
+  int n_layers;
+  int* done;
+};
+cudaError_t launch_gcn_hidden_fused(const FusedHiddenMaps& maps, const FusedHiddenParams& fp, int num_sms, bool pdl,
+                                    cudaStream_t stream);
 size_t gcn_hidden_umma_smem_bytes();
 int gcn_hidden_umma_bk();   // fp16 elements per TMA box row (32: SWIZZLE_64B, 64: SWIZZLE_128B)
 #ifndef EHB_UMMA_BK

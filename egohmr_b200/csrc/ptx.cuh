@@ -87,6 +87,9 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 }
 // Generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma operand reads, TMA stores).
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// Generic-proxy accesses (any space) before -> async-proxy accesses after, e.g. global data another SM wrote with ordinary stores
+// (observed through an acquire) and this thread is about to read with TMA.
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (fp16/bf16 operands, fp32 accumulate), one CTA.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {

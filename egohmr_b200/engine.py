@@ -429,6 +429,10 @@ class Engine:
     def set_pdl(self, on):
         check(self.lib.ehb_debug_set_pdl(self._h, 1 if on else 0))
 
+    def set_k1_fused(self, on):
+        """Hidden layers of a step as one persistent launch (True; same bits, slower) or one launch per layer (False, default)."""
+        check(self.lib.ehb_debug_set_k1_fused(self._h, 1 if on else 0))
+
     def set_input_mode(self, umma):
         """K2's joint mix on tcgen05 (True) or the fp32 FFMA kernel (False, default; measured equal)."""
         check(self.lib.ehb_debug_set_input_mode(self._h, 1 if umma else 0))

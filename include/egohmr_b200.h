@@ -307,6 +307,9 @@ int ehb_debug_set_pdl(ehb_ctx* ctx, int on);
 /* Input graph-convolution layer (K2): the fp32 FFMA kernel (0, default) or the variant with the 24x24 joint mix on the
  * tensor pipe (1; same result to fp32 rounding, same time: the kernel is bound by assembling the per-joint features). */
 int ehb_debug_set_input_mode(ehb_ctx* ctx, int umma);
+/* Hidden layers of a reverse step: one launch per layer (0, default) or ONE persistent launch ordered by per-(layer, row
+ * group) completion counters (1: same bits, measured 7-8 % slower; kept as an experiment). */
+int ehb_debug_set_k1_fused(ehb_ctx* ctx, int on);
 /* ResNet convolution GEMMs: k-blocks (of 64 operand columns) chained into one tensor-memory accumulation before the
  * epilogue takes the partial sum over in fp32 registers (0 = the whole contraction in one accumulator). */
 int ehb_debug_set_conv_kc(ehb_ctx* ctx, int kc);

@@ -179,6 +179,24 @@ def test_single_denoise_step_vs_oracle_and_check_path(full, golden_dir):
     assert np.abs(outs[2][0] - ref_x0).max() < X0_TOL      # single-CTA bring-up variant of the row-major kernel
 
 
+def test_fused_hidden_layers_equal_the_per_layer_launches(full):
+    """The opt-in persistent kernel over all hidden layers (gcn_umma_fused.cu: units ordered by per-(layer, row group)
+    completion counters, published through one warp per CTA) gives the per-layer launches' bits, on a batch whose
+    row groups (13 for 64 bodies x 2 passes) are fewer than the CTA pairs, so that units wait on units in flight."""
+    model, diffusion, *_ = full
+    batch = _tb(synth.make_batch(3, 8))
+    noise = torch.from_numpy(synth.make_noise(3, 1, 64, diffusion.num_timesteps)[0]).cuda()
+    a = diffusion.sample_many(model, batch, 8, "ddim5", noise=noise)["pred_x_start"].clone()
+    model.engine.set_k1_fused(True)
+    try:
+        for _ in range(3):
+            b = diffusion.sample_many(model, batch, 8, "ddim5", noise=noise)["pred_x_start"]
+            assert torch.equal(a, b)
+    finally:
+        model.engine.set_k1_fused(False)
+    assert not model.engine.check_overflow()
+
+
 def test_forward_signature_and_outputs(full):
     """model(batch, t) returns the reference's dict (egohmr.py:256-303) and mutates batch like the reference."""
     model, diffusion, sd, smpl_model, mean, std = full
