@@ -1,5 +1,5 @@
 #!/bin/bash
-# Timeline of the hidden-layer kernel (K1, transposed product): build/libegohmr_b200_trace.so = the library with gcn_umma_t.cu
+# Timeline of the hidden-layer kernel (K1, transposed product): build/libegohmr_b200_trace.so (tools/build_trace_lib.sh gcn_umma_t EHB_K1_TRACE) = the library with gcn_umma_t.cu
 # compiled -DEHB_K1_TRACE.  Per unit of CTA 0 of one launch: where the MMA, TMA, tcgen05.ld and mix warps wait.
 cp egohmr_b200/lib/libegohmr_b200.so /tmp/lib_product.so
 cp build/libegohmr_b200_trace.so egohmr_b200/lib/libegohmr_b200.so
