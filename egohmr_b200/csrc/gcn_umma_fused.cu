@@ -375,13 +375,24 @@ cudaError_t launch_gcn_hidden_fused(const FusedHiddenMaps& maps, const FusedHidd
   // the dependency counters: [n_layers][n_rgroups], zero before every launch
   cudaError_t e = cudaMemsetAsync(fp.done, 0, sizeof(int) * fp.n_layers * n_rgroups, stream);
   if (e != cudaSuccess) return e;
-  // every CTA must be resident (units wait for units of other CTAs): one CTA per SM, never more CTAs than SMs
-  const int grid = units * 2 < num_sms ? units * 2 : (num_sms / 2) * 2;
+  // every CTA must be resident (units wait for units of other CTAs): one CTA per SM, never more CTAs than SMs — and never
+  // more CTA pairs than the device reports as co-resident for this kernel (fewer than SMs / 2 on a partitioned device)
+  int grid = units * 2 < num_sms ? units * 2 : (num_sms / 2) * 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
+  static int max_pairs = -1;
+  if (max_pairs < 0) {
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    max_pairs = n;
+  }
+  if (max_pairs < 1) return cudaErrorLaunchOutOfResources;
+  if (grid > 2 * max_pairs) grid = 2 * max_pairs;
+  cfg.gridDim = dim3(grid);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
