@@ -68,6 +68,12 @@ static_assert(sizeof(Barriers) <= BAR_BYTES, "barrier block too small");
 constexpr int TRACE_UNITS = 16, TRACE_SLOTS = 16;
 __device__ long long g_k1_trace[TRACE_UNITS][TRACE_SLOTS];
 __device__ int g_k1_armed = 0;
+__device__ unsigned long long g_k1_pair_t[128][2];   // per CTA pair: globaltimer (ns) when its MMA warp started / issued its last unit
+__device__ __forceinline__ unsigned long long k1_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 #define K1_TRACE(unit_i, slot, val)                                                        \
   do {                                                                                     \
     if (trace_on && (unit_i) < TRACE_UNITS) g_k1_trace[(unit_i)][(slot)] = (val);          \
@@ -180,6 +186,9 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+#ifdef EHB_K1_TRACE
+      if (g_k1_armed == 1 && lane == 0 && unit0 < 128) g_k1_pair_t[unit0][0] = k1_globaltimer();
+#endif
       for (int u = unit0; u < total_units; u += unit_step) {
         [[maybe_unused]] const long long t_unit = K1_CLOCK();
         ptx::mbar_wait_cluster(&bars->tempty[as], aphase ^ 1);
@@ -220,6 +229,9 @@ gcn_hidden_umma_t_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
         K1_TRACE(ui, 1, t_acc - t_unit);     // waited for a free accumulator
         K1_TRACE(ui, 2, w_full);             // waited for operands (sum over the unit's k-blocks)
         K1_TRACE(ui, 3, K1_CLOCK());         // all MMAs of the unit issued
+#ifdef EHB_K1_TRACE
+        if (g_k1_armed == 1 && lane == 0 && unit0 < 128) g_k1_pair_t[unit0][1] = k1_globaltimer();
+#endif
         ++ui;
         if (++as == 2) {
           as = 0;
@@ -344,6 +356,9 @@ extern "C" int ehb_k1_trace_arm(int on) {
   static long long zeros[TRACE_UNITS][TRACE_SLOTS] = {};
   if (on && cudaMemcpyToSymbol(g_k1_trace, zeros, sizeof(zeros)) != cudaSuccess) return 1;
   return cudaMemcpyToSymbol(g_k1_armed, &on, sizeof(int)) != cudaSuccess;
+}
+extern "C" int ehb_k1_trace_pairs(unsigned long long* out) {   // [128][2] globaltimer ns: start, last unit issued
+  return cudaMemcpyFromSymbol(out, g_k1_pair_t, sizeof(unsigned long long) * 128 * 2) != cudaSuccess;
 }
 extern "C" int ehb_k1_trace_read(long long* out) {   // [TRACE_UNITS][TRACE_SLOTS]
   return cudaMemcpyFromSymbol(out, g_k1_trace, sizeof(long long) * TRACE_UNITS * TRACE_SLOTS) != cudaSuccess;

@@ -24,6 +24,16 @@ for layer in (1, 2):
     assert lib.ehb_k1_trace_arm(0) == 0
     buf = np.zeros((16, 16), np.int64)
     assert lib.ehb_k1_trace_read(buf.ctypes.data_as(C.POINTER(C.c_longlong))) == 0
+    pairs = np.zeros((128, 2), np.uint64)
+    assert lib.ehb_k1_trace_pairs(pairs.ctypes.data_as(C.POINTER(C.c_ulonglong))) == 0
+    pt = pairs[:74].astype(np.int64)
+    start0 = pt[:, 0].min()
+    last = (pt[:, 1] - start0) / 1e3     # us from the first pair's start to each pair's last unit being issued
+    n14 = last[:62]; n13 = last[62:]       # pairs 0-61 run 14 units, 62-73 run 13 (1024 = 13 * 74 + 62)
+    print(f"=== hidden layer {layer}: per CTA pair, us from the earliest start to the last unit issued: pairs with 14 units "
+          f"min {n14.min():.1f} median {np.median(n14):.1f} max {n14.max():.1f}; pairs with 13 units min {n13.min():.1f} "
+          f"median {np.median(n13):.1f} max {n13.max():.1f}; start spread {(pt[:, 0].max() - start0) / 1e3:.1f} us")
+    print("    per pair:", " ".join(f"{v:.0f}" for v in last))
     t0 = buf[0, 0]
     print(f"=== hidden layer {layer} (one launch, {ms:.3f} ms): cycles; unit = 192 MMAs of 256x240x16")
     for u in range(16):
